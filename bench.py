@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates/s of the implicit time-stepper (BASELINE.json metric).
+
+Workload at every N: BASELINE.json configs[1] = "batched 1D orthogonal diffusion: 1M independent 256-node lines,
+per-thread Thomas" per GPU (weak scaling: lines are independent, no collective).  A step = one OneDGrid.step of
+every line = nlines * n grid-point updates.  Inputs (4.3 GB of grid + predict per GPU) exceed L2 many times over.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`   : device-resident throughput (CUDA events on the library's stream, max over ranks).
+`e2e`     : same metric through the C ABI with HOST buffers: per step H2D of grid+predict+BCs from pinned
+            memory, the step, D2H of grid+predict.
+`roofline`: 32 algorithmic bytes per update / measured kernel time vs MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / --impl reference: the oracle's C restatement of the reference (the reference is Scala and no
+            JVM exists on the image) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLINES, NNODES = 1 << 20, 256
+TIME_STEP = 900.0
+SEED = 20261019
+BYTES_PER_UPDATE_1D = 32.0
+
+
+def workload_geometry(n):
+    rangeX = np.array([0.01 * (i + 1) for i in range(n)])
+    return 0.0, rangeX, 0.01 * (n + 1)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                smax = float(f[2])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:  # region shorter than the sampling period: use everything we saw
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(sample_lines, n, steps, threads):
+    """Times the oracle's restatement of OneDGrid.step on `sample_lines` lines of the workload."""
+    from oracle import oracle as O
+
+    r = np.random.default_rng(SEED)
+    leftX, rangeX, rightX = workload_geometry(n)
+    grid = r.uniform(0.0, 30.0, (sample_lines, n))
+    predict = np.full((sample_lines, n), 4.0)
+    lt, rt = r.uniform(10.0, 30.0, sample_lines), r.uniform(0.0, 10.0, sample_lines)
+    spl = O.Spline.const(1e-6)
+    O.batch1d_step(O.ORTHO, leftX, rangeX, rightX, spl, 1.0, grid, predict, lt, rt, TIME_STEP, 1, threads)  # warm
+    t0 = time.perf_counter()
+    O.batch1d_step(O.ORTHO, leftX, rangeX, rightX, spl, 1.0, grid, predict, lt, rt, TIME_STEP, steps, threads)
+    dt = time.perf_counter() - t0
+    return sample_lines * n * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_lines = 16384
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_reference(sample_lines, NNODES, 1, threads)
+    t_all = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_reference(sample_lines, NNODES, 4, threads)
+        per_step.append(dt / 4)
+        t_all += dt
+    ups = sample_lines * NNODES * 4 * args.steps / t_all
+    sample = f"{sample_lines} of {NLINES} lines x {NNODES} nodes, 4 OneDGrid.step per bench step, pthreads over lines"
+    line = {
+        "impl": "reference", "metric": "grid-point updates/s", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_step)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: batched 1-D orthogonal diffusion, 1M lines x 256 nodes, per-line Thomas, const properties",
+                   "note": "C restatement of the reference's Scala path (oracle/gs_oracle.c); JVM unavailable on the image"},
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import gridsplines_b200 as gs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gridsplines_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nlines, n = args.lines, args.nodes
+    stream = torch.cuda.Stream()
+    ctx = gs.Context(local, stream=stream.cuda_stream)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+
+    # ---- synthetic workload: every rank owns nlines independent lines
+    r = np.random.default_rng(SEED + rank)
+    leftX, rangeX, rightX = workload_geometry(n)
+    g = gs.BatchedOneDGrid(leftX, rangeX, rightX, gs.Spline.const(1e-6), 1.0, gs.ORTHO, nlines, ctx=ctx)
+    h_grid = torch.empty((nlines, n), dtype=torch.float64).pin_memory()
+    h_pred = torch.empty((nlines, n), dtype=torch.float64).pin_memory()
+    chunk = 1 << 16
+    for l0 in range(0, nlines, chunk):
+        l1 = min(nlines, l0 + chunk)
+        h_grid[l0:l1] = torch.from_numpy(r.uniform(0.0, 30.0, (l1 - l0, n)))
+    h_pred.fill_(4.0)
+    lt, rt = r.uniform(10.0, 30.0, nlines), r.uniform(0.0, 10.0, nlines)
+    g.upload_ptr(gs.GRID, h_grid.data_ptr())
+    g.upload_ptr(gs.PREDICT, h_pred.data_ptr())
+    g.set_bc(lt, rt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            g.step(TIME_STEP)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        launches0 = ctx.launch_count
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        t_wall0 = time.time()
+        ev[0].record(stream)
+        for i in range(args.steps):
+            g.step(TIME_STEP)
+            ev[i + 1].record(stream)
+        barrier()
+        t_wall1 = time.time()
+        launches = ctx.launch_count - launches0
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kernel_ms = float(np.mean(step_ms))  # one kernel per step; events bracket each launch on its stream
+    if g.status != 0:
+        raise SystemExit(f"status flags raised during the bench: {g.status}")
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h2d = 2 * nlines * n * 8 + 2 * nlines * 8
+    d2h = 2 * nlines * n * 8
+    with torch.cuda.stream(stream):
+        def e2e_step():
+            g.upload_ptr(gs.GRID, h_grid.data_ptr())
+            g.upload_ptr(gs.PREDICT, h_pred.data_ptr())
+            g.set_bc(lt, rt)
+            g.step(TIME_STEP)
+            g.download_ptr(gs.GRID, h_grid.data_ptr())
+            g.download_ptr(gs.PREDICT, h_pred.data_ptr())
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    times = torch.tensor([total_ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kernel_ms = (float(x) for x in times.cpu())
+    updates_per_step = float(nlines) * n * world
+    value = updates_per_step * args.steps / (total_ms * 1e-3)
+    e2e_value = updates_per_step * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_UPDATE_1D * float(nlines) * n / (kernel_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        threads = os.cpu_count() or 1
+        cpu_lines = 16384
+        cpu_ups, cpu_dt = cpu_reference(cpu_lines, n, args.cpu_steps, threads)
+        line = {
+            "metric": "grid-point updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: batched 1-D orthogonal diffusion, 1M lines x 256 nodes per GPU, per-thread Thomas, "
+                                   "const properties, per-line Dirichlet ends",
+                       "lines_per_gpu": nlines, "nodes": n, "time_step_s": TIME_STEP,
+                       "l2_policy": "inputs (4.3 GB/GPU) exceed L2 (126 MB); no flush needed",
+                       "parity": "bit-exact vs oracle (tests/test_gpu_1d.py)", "options": args.opt},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("k_step1d_bytes_per_launch"), "peak_source": peak_src,
+                         "kernel": "k_step1d", "kernel_ms": kernel_ms, "algorithmic_bytes_per_update": BYTES_PER_UPDATE_1D},
+            "cpu_baseline": {"value": cpu_ups, "unit": "updates/s", "cores": threads, "kind": "port",
+                             "sample": f"{cpu_lines} of {nlines} lines x {n} nodes x {args.cpu_steps} steps "
+                                       f"({cpu_dt:.1f} s), C restatement of the Scala reference, pthreads over lines"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lines", type=int, default=NLINES)
+    ap.add_argument("--nodes", type=int, default=NNODES)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--opt", action="append", default=[], help="gs_ctx_set_option name=value")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

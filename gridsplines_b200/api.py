@@ -1,0 +1,641 @@
+"""Host-side mirror of the reference's Scala surface for the time-stepper path, on top of the
+C ABI (include/gs_b200.h).  Names and argument meaning follow the reference so that parity tests
+read like approximation/src/test/scala/approximation/*.scala:
+
+    Spline, AlwaysDefinedSpline           piecewise/.../Spline.scala, approximation/.../AlwaysDefinedSpline.scala
+    XDim, YDim, Ortho, Radial             approximation/.../XDim.scala, YDim.scala, TypeDir.scala
+    OneDGrid (+ BatchedOneDGrid)          approximation/.../OneDGrid.scala
+    TwoDGrid, Temperature, HeatFlow, One, Many, Temp, Flow,
+    ConstantCoef, VarXCoef, VarYCoef      approximation/.../TwoDGrid.scala
+
+Host code here only builds tables and marshals arrays; every number the stepper produces comes
+from the CUDA library.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (CONST, CUBIC, DENSE, FLOW, GRID, INTERLEAVED, LEFT, LINE, LINE_MAJOR, LOW, MAP_DENSE,
+                   MAP_PER_COL, MAP_PER_ROW, MAP_SINGLE, ORTHO, PREDICT, RADIAL, RESULT, RIGHT, SEL_APPLY,
+                   SEL_CAP, SEL_TEMPCOND, SEL_THERM, SPARSE, SPLINE_PER_NODE, SPLINE_SINGLE, TEMP, UPP, GsError)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+DBL_MAX = 1.7976931348623157e308
+
+
+def _d(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+# direction tags (approximation/package.scala:5-8)
+Ortho, Radial = ORTHO, RADIAL
+
+
+class Context:
+    """One CUDA device + stream; owns the spline pool (gs_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        L.check(L.lib().gs_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib().gs_ctx_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        L.check(L.lib().gs_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        c = C.c_uint64()
+        L.check(L.lib().gs_ctx_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def set_option(self, name: str, value: int):
+        L.check(L.lib().gs_ctx_set_option(self._h, name.encode(), int(value)))
+
+    # K1
+    def predef(self, direction, low, rng, upp, sigma=1.0) -> np.ndarray:
+        rng = _d(rng)
+        out = np.empty((len(rng), 2))
+        L.check(L.lib().gs_predef(self._h, direction, low, _p(rng), len(rng), upp, sigma, _p(out)))
+        return out
+
+    def heatflow_geometry(self, direction, low, rng, upp) -> np.ndarray:
+        rng = _d(rng)
+        out = np.empty(4)
+        L.check(L.lib().gs_heatflow_geometry(self._h, direction, low, _p(rng), len(rng), upp, _p(out)))
+        return out
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ------------------------------------------------------------------------------------------
+# piecewise.Spline: host-side table (kind, knots, x0, coefs).  Construction follows
+# piecewise/.../Spline.scala:355-411, M1Hermite3.scala:76-126, Hermite3.scala:139-170, 256-272.
+# ------------------------------------------------------------------------------------------
+def _sq(x: float) -> float:
+    # scala.math.pow(x, 2.0); HotSpot evaluates exponent 2 as x*x
+    return x * x
+
+
+def _jmin(a: float, b: float) -> float:
+    if a != a:
+        return a
+    if a == 0.0 and b == 0.0:
+        return a if math.copysign(1.0, a) < 0 else b
+    return a if a <= b else b
+
+
+def _fdiv(a: float, b: float) -> float:
+    """IEEE-754 division (Python raises on x / 0.0; the JVM returns Inf/NaN)."""
+    with np.errstate(all="ignore"):
+        return float(np.float64(a) / np.float64(b))
+
+
+def _signum(x: float) -> float:
+    return x if (x == 0.0 or x != x) else (1.0 if x > 0.0 else -1.0)
+
+
+class Spline:
+    def __init__(self, kind: int, knots, x0, coefs):
+        self.kind = kind
+        self.knots = _d(knots)
+        self.x0 = _d(x0)
+        self.coefs = _d(coefs).reshape(-1, 4)
+        assert len(self.knots) == len(self.x0) + 1 == len(self.coefs) + 1
+
+    # -- factories
+    @staticmethod
+    def const(value: float, lo: float = -DBL_MAX, hi: float = DBL_MAX) -> "Spline":
+        """Spline.const(value) = singleton over (Double.MinValue, Double.MaxValue) (Spline.scala:355-369)."""
+        return Spline(CONST, [lo, hi], [0.0], [[value, 0.0, 0.0, 0.0]])
+
+    @staticmethod
+    def from_pieces(kind, knots, x0, coefs) -> "Spline":
+        return Spline(kind, knots, x0, coefs)
+
+    @staticmethod
+    def _sorted(points):
+        return sorted(((float(x), float(y)) for x, y in points), key=lambda p: p[0])  # stable, like sortBy
+
+    @staticmethod
+    def lines(points) -> "Spline":
+        """Spline.lines (Spline.scala:384-385); Line.apply(xLow, xUpp, yLow, yUpp) Line.scala:69-73."""
+        pts = Spline._sorted(points)
+        knots, coefs = [pts[0][0]], []
+        for (xl, yl), (xu, yu) in zip(pts[:-1], pts[1:]):
+            slope = (yu - yl) / (xu - xl)
+            intercept = yl if (xu - xl) == 0.0 else yl + (yu - yl) / (xu - xl) * (0.0 - xl)
+            coefs.append([intercept, slope, 0.0, 0.0])
+            knots.append(xu)
+        return Spline(LINE, knots, [0.0] * len(coefs), coefs)
+
+    @staticmethod
+    def line(xl, yl, xu, yu) -> "Spline":
+        return Spline.lines([(xl, yl), (xu, yu)])
+
+    @staticmethod
+    def _sources(pts):
+        """Hermite3.makeSources (Hermite3.scala:256-272): [yLow, yUpp, dLow, dUpp, xLow, xUpp]."""
+        def deriv(a, b):
+            return _fdiv(b[1] - a[1], b[0] - a[0])
+
+        n = len(pts)
+        src = []
+        der1 = deriv(pts[0], pts[1])
+        for k in range(n - 1):
+            der2 = deriv(pts[k], pts[k + 2]) if k + 2 < n else deriv(pts[k], pts[k + 1])
+            src.append([pts[k][1], pts[k + 1][1], der1, der2, pts[k][0], pts[k + 1][0]])
+            der1 = der2
+        return src
+
+    @staticmethod
+    def _cubic(src) -> "Spline":
+        """constructSpline (M1Hermite3.scala:76-86 / Hermite3.scala:20-29)."""
+        knots, x0, coefs = [src[0][4]], [], []
+        for yl, yu, dl, du, xl, xu in src:
+            delta = _fdiv(yu - yl, xu - xl)
+            h = xu - xl
+            coefs.append([yl, dl, _fdiv(-2.0 * dl - du + 3.0 * delta, h), _fdiv(dl + du - 2.0 * delta, _sq(h))])
+            x0.append(xl)
+            knots.append(xu)
+        return Spline(CUBIC, knots, x0, coefs)
+
+    @staticmethod
+    def m1Hermite3(points) -> "Spline":
+        """Spline.m1Hermite3 (Spline.scala:387-389): secant derivatives, Fritsch-Carlson
+        monotonisation (Hermite3.monothone(Normal) :86-91, 139-170), neighbour smoothing
+        (M1Hermite3.scala:88-121)."""
+        pts = Spline._sorted(points)
+        src = Spline._sources(pts)
+        for s in src:
+            yl, yu, dl, du, xl, xu = s
+            h = xu - xl
+            delta = _fdiv(yu - yl, h)
+            alpha, beta = abs(_fdiv(dl, delta)), abs(_fdiv(du, delta))
+            if any(math.isnan(v) or math.isinf(v) for v in (alpha, beta)):  # SmoothType.monotonize :70-73
+                sa = sb = 0.0
+            else:  # Normal.withType :86-91
+                tau = _fdiv(3.0, math.sqrt(_sq(alpha) + _sq(beta)))
+                sa, sb = _jmin(alpha, tau * alpha), _jmin(beta, tau * beta)
+            s[2], s[3] = sa * delta, sb * delta
+            if math.isnan(s[2]) or math.isnan(s[3]):
+                # the reference throws here ("Function after monotonization must be monothone", :163-164)
+                raise ValueError("m1Hermite3: degenerate piece (both end derivatives zero on a sloped piece)")
+        for k in range(len(src) - 1):
+            d_left, d_right = src[k][3], src[k + 1][2]
+            der = _signum(d_left) * _jmin(abs(d_right), abs(d_left))
+            src[k][3] = der
+            src[k + 1][2] = der
+        return Spline._cubic(src)
+
+    @staticmethod
+    def fHermite3(points) -> "Spline":
+        return Spline._cubic(Spline._sources(Spline._sorted(points)))
+
+    # -- bounds (Spline.scala:304-306)
+    @property
+    def size(self) -> int:
+        return len(self.x0)
+
+    @property
+    def lowerBound(self) -> float:
+        return float(self.knots[0])
+
+    @property
+    def upperBound(self) -> float:
+        """AbsITree.greatestK returns the LOWER bound of the trailing UpBoundLeaf
+        (AbsITree.scala:271-280): kept literally."""
+        return float(self.knots[-2])
+
+    @property
+    def trueUpperBound(self) -> float:
+        return float(self.knots[-1])
+
+
+class AlwaysDefinedSpline:
+    """approximation.AlwaysDefinedSpline (AlwaysDefinedSpline.scala:4-46) registered in a context's
+    device pool.  `clamps` = (lowerX, upperX, lowerY, upperY) overrides the literal rule."""
+
+    def __init__(self, spl: Spline, ctx: Optional[Context] = None, true_upper: bool = False, clamps=None):
+        self.ctx = ctx or default_context()
+        self.spl = spl
+        if clamps is None:
+            lower_x = spl.lowerBound
+            upper_x = spl.trueUpperBound if true_upper else spl.upperBound
+            if spl.kind == CONST and spl.size == 1:
+                lower_y = upper_y = float(spl.coefs[0][0])
+            else:
+                # lowerY = spl(lowerX), upperY = spl(upperX) (:7-8), evaluated by the device's own
+                # Spline.apply through an unclamped registration of the same table
+                raw = self._register(spl, -math.inf, math.inf, math.nan, math.nan)
+                lower_y, upper_y = (float(v) for v in self._eval_apply(raw, [lower_x, upper_x]))
+            clamps = (lower_x, upper_x, lower_y, upper_y)
+        self.clamps = tuple(float(c) for c in clamps)
+        self.id = self._register(spl, *self.clamps)
+
+    def _register(self, spl, lx, ux, ly, uy) -> int:
+        out = C.c_int()
+        L.check(L.lib().gs_spline_create(self.ctx._h, spl.kind, spl.size, _p(spl.knots), _p(spl.x0),
+                                         _p(np.ascontiguousarray(spl.coefs)), lx, ux, ly, uy, C.byref(out)))
+        return out.value
+
+    def _eval_apply(self, sid, xs) -> np.ndarray:
+        xs = _d(xs)
+        out = np.empty_like(xs)
+        L.check(L.lib().gs_spline_eval_apply(self.ctx._h, sid, len(xs), _p(xs), _p(out)))
+        return out
+
+    def __call__(self, x):
+        xs = np.atleast_1d(_d(x))
+        out = self._eval_apply(self.id, xs)
+        return out if np.ndim(x) else float(out[0])
+
+    def average(self, lo, hi):
+        lo_a, hi_a = np.atleast_1d(_d(lo)), np.atleast_1d(_d(hi))
+        out = np.empty_like(lo_a)
+        L.check(L.lib().gs_spline_eval_average(self.ctx._h, self.id, len(lo_a), _p(lo_a), _p(hi_a), _p(out)))
+        return out if np.ndim(lo) else float(out[0])
+
+
+def _as_ads(s, ctx) -> AlwaysDefinedSpline:
+    if isinstance(s, AlwaysDefinedSpline):
+        return s
+    return AlwaysDefinedSpline(s, ctx)
+
+
+# ------------------------------------------------------------------------------------------
+# OneDGrid
+# ------------------------------------------------------------------------------------------
+class BatchedOneDGrid:
+    """nlines independent OneDGrid (OneDGrid.scala:14-34) sharing geometry and conductivity.
+    `conductivity`: a Spline / AlwaysDefinedSpline (companion apply, :66-79) or a list of n
+    (left, right) AlwaysDefinedSpline pairs (`conductivities(z)(0..1)`)."""
+
+    def __init__(self, leftX, rangeX, rightX, conductivity, sigma, direction=ORTHO, nlines=1,
+                 ctx: Optional[Context] = None, predef=None):
+        self.ctx = ctx or default_context()
+        self.rangeX = _d(rangeX)
+        self.n = len(self.rangeX)
+        self.nlines = int(nlines)
+        if isinstance(conductivity, (Spline, AlwaysDefinedSpline)):
+            self._splines = [_as_ads(conductivity, self.ctx)]
+            mode, ids = SPLINE_SINGLE, [self._splines[0].id]
+        else:
+            self._splines = [(_as_ads(a, self.ctx), _as_ads(b, self.ctx)) for a, b in conductivity]
+            mode, ids = SPLINE_PER_NODE, [s.id for pair in self._splines for s in pair]
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        pd = None if predef is None else _d(predef)
+        self._h = C.c_void_p()
+        L.check(L.lib().gs_grid1d_create(self.ctx._h, self.nlines, self.n, direction, leftX, _p(self.rangeX),
+                                         rightX, sigma, mode, ids.ctypes.data_as(_ip),
+                                         _p(pd) if pd is not None else None, C.byref(self._h)))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib().gs_grid1d_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, which: int, host: np.ndarray, layout: int = LINE_MAJOR):
+        host = _d(host)
+        assert host.size == self.nlines * self.n
+        L.check(L.lib().gs_grid1d_upload(self._h, which, layout, host.ctypes.data))
+
+    def download(self, which: int = GRID, layout: int = LINE_MAJOR, out: Optional[np.ndarray] = None) -> np.ndarray:
+        shape = (self.nlines, self.n) if layout == LINE_MAJOR else (self.n, self.nlines)
+        if out is None:
+            out = np.empty(shape)
+        L.check(L.lib().gs_grid1d_download(self._h, which, layout, out.ctypes.data))
+        return out
+
+    def upload_ptr(self, which: int, host_ptr: int, layout: int = LINE_MAJOR):
+        L.check(L.lib().gs_grid1d_upload(self._h, which, layout, host_ptr))
+
+    def download_ptr(self, which: int, host_ptr: int, layout: int = LINE_MAJOR):
+        L.check(L.lib().gs_grid1d_download(self._h, which, layout, host_ptr))
+
+    def fill(self, which: int, value: float):
+        L.check(L.lib().gs_grid1d_fill(self._h, which, value))
+
+    def set_bc(self, leftT, rightT):
+        lt, rt = np.atleast_1d(_d(leftT)), np.atleast_1d(_d(rightT))
+        stride = 0 if (lt.size == 1 and rt.size == 1) else 1
+        if stride:
+            lt = np.ascontiguousarray(np.broadcast_to(lt, (self.nlines,)))
+            rt = np.ascontiguousarray(np.broadcast_to(rt, (self.nlines,)))
+        L.check(L.lib().gs_grid1d_set_bc(self._h, _p(lt), _p(rt), stride))
+
+    def step(self, time: float, leftT=None, rightT=None, nsteps: int = 1):
+        if leftT is not None:
+            self.set_bc(leftT, rightT)
+        L.check(L.lib().gs_grid1d_step(self._h, time, nsteps))
+
+    def set_solver(self, solver: int):
+        L.check(L.lib().gs_grid1d_set_solver(self._h, solver))
+
+    @property
+    def status(self) -> int:
+        f = C.c_uint32()
+        L.check(L.lib().gs_grid1d_status(self._h, C.byref(f)))
+        return f.value
+
+    def clear_status(self):
+        L.check(L.lib().gs_grid1d_clear_status(self._h))
+
+    @property
+    def bytes_per_step(self) -> float:
+        b = C.c_double()
+        L.check(L.lib().gs_grid1d_bytes_per_step(self._h, C.byref(b)))
+        return b.value
+
+
+class OneDGrid(BatchedOneDGrid):
+    """approximation.OneDGrid: `grid` is the public array (OneDGrid.scala:20), `step(time, leftT, rightT)`."""
+
+    def __init__(self, leftX, rangeX, rightX, conductivity, sigma, direction=ORTHO, ctx=None):
+        super().__init__(leftX, rangeX, rightX, conductivity, sigma, direction, 1, ctx)
+
+    @property
+    def grid(self) -> np.ndarray:
+        return self.download(GRID)[0]
+
+    @grid.setter
+    def grid(self, values):
+        self.upload(GRID, _d(values).reshape(1, -1))
+
+    @property
+    def predict(self) -> np.ndarray:
+        return self.download(PREDICT)[0]
+
+
+# ------------------------------------------------------------------------------------------
+# TwoDGrid
+# ------------------------------------------------------------------------------------------
+class _Dim:
+    def __init__(self, low: float, rng_or_inc, upp: float, t: int = ORTHO):
+        if callable(rng_or_inc):
+            # generator ctor: Iterator.iterate(inc(low))(inc).takeWhile(_ < upp)  (XDim.scala:10-15)
+            out, x = [], rng_or_inc(low)
+            while x < upp:
+                out.append(x)
+                x = rng_or_inc(x)
+            rng_or_inc = out
+        self.low, self.upp, self.t = float(low), float(upp), t
+        self.range = _d(rng_or_inc)
+
+    @property
+    def values(self) -> np.ndarray:  # Dim.values, Dim.scala:13
+        return np.concatenate([[self.low], self.range, [self.upp]])
+
+    def coord(self, i):
+        return float(self.range[i])
+
+
+class XDim(_Dim):
+    @property
+    def colsNum(self):
+        return len(self.range)
+
+
+class YDim(_Dim):
+    @property
+    def rowsNum(self):
+        return len(self.range)
+
+
+# bound-building tags of TwoDGrid.apply (TwoDGrid.scala:521-551)
+One, Many = SPARSE, DENSE
+Temp, Flow = TEMP, FLOW
+
+
+class Coefficients:
+    """Flattened Coefficients hierarchy (TwoDGrid.scala:782-1137): for each member a (mode, ids) pair."""
+
+    def maps(self, cols: int, rows: int):
+        raise NotImplementedError
+
+
+class ConstantCoef(Coefficients):
+    """ConstantCoef(thermConductivity, capacity, tempConductivity) (:790-816); apply == tempConductivity."""
+
+    def __init__(self, therm, cap, tempcond, ctx=None):
+        ctx = ctx or default_context()
+        self.therm, self.cap, self.tempcond = _as_ads(therm, ctx), _as_ads(cap, ctx), _as_ads(tempcond, ctx)
+
+    def maps(self, cols, rows):
+        return {SEL_APPLY: (MAP_SINGLE, [self.tempcond.id]), SEL_THERM: (MAP_SINGLE, [self.therm.id]),
+                SEL_CAP: (MAP_SINGLE, [self.cap.id]), SEL_TEMPCOND: (MAP_SINGLE, [self.tempcond.id])}
+
+
+class _VarCoef(Coefficients):
+    mode = MAP_PER_ROW
+
+    def __init__(self, therm: Sequence, cap: Sequence, tempcond: Sequence, ctx=None):
+        ctx = ctx or default_context()
+        self.therm = [_as_ads(s, ctx) for s in therm]
+        self.cap = [_as_ads(s, ctx) for s in cap]
+        self.tempcond = [_as_ads(s, ctx) for s in tempcond]
+
+    def maps(self, cols, rows):
+        n = (rows if self.mode == MAP_PER_ROW else cols) + 1
+        assert len(self.therm) == len(self.cap) == len(self.tempcond) == n, "one spline per index from -1"
+        ids = lambda lst: [s.id for s in lst]
+        return {SEL_APPLY: (self.mode, ids(self.tempcond)), SEL_THERM: (self.mode, ids(self.therm)),
+                SEL_CAP: (self.mode, ids(self.cap)), SEL_TEMPCOND: (self.mode, ids(self.tempcond))}
+
+
+class VarYCoef(_VarCoef):
+    """per-row splines, index row+1 (:897-909)"""
+    mode = MAP_PER_ROW
+
+
+class VarXCoef(_VarCoef):
+    """per-column splines.  The reference indexes VarXCoef by y+1 as well (:835-847, App. B Q2); the
+    flattening host decides what `coefs(col,row)` returns, here the per-column reading."""
+    mode = MAP_PER_COL
+
+
+class DenseCoef(Coefficients):
+    """Arbitrary coefs(col,row): id arrays of shape (rows+1, cols+1), entry [row+1, col+1] (Patch*Coef)."""
+
+    def __init__(self, apply_ids, therm_ids, cap_ids, tempcond_ids):
+        self.ids = {SEL_APPLY: apply_ids, SEL_THERM: therm_ids, SEL_CAP: cap_ids, SEL_TEMPCOND: tempcond_ids}
+
+    def maps(self, cols, rows):
+        return {k: (MAP_DENSE, np.asarray(v, dtype=np.int32).reshape(rows + 1, cols + 1).ravel())
+                for k, v in self.ids.items()}
+
+
+class _Bound:
+    def __init__(self, grid: "TwoDGrid", side: int, kind: int, rep: int):
+        self.grid, self.side, self.kind, self.rep = grid, side, kind, rep
+
+    def update(self, values):
+        v = np.atleast_1d(_d(values))
+        L.check(L.lib().gs_grid2d_set_bound(self.grid._h, self.side, self.kind, self.rep, _p(v), len(v)))
+
+    def get(self, i: Optional[int] = None):
+        n = self.grid.cols if self.side in (UPP, LOW) else self.grid.rows
+        out = np.empty(n)
+        L.check(L.lib().gs_grid2d_get_bound(self.grid._h, self.side, _p(out), n))
+        return out if i is None else float(out[i])
+
+
+class _Bounds:
+    def __init__(self, upp, low, right, left):
+        self.upp, self.low, self.right, self.left = upp, low, right, left
+
+
+class _GridArrays:
+    """TwoDGrid.Grid (:461-519): grid / predict / result as host copies on demand."""
+
+    def __init__(self, owner: "TwoDGrid"):
+        self._o = owner
+
+    def _get(self, which):
+        out = np.empty((self._o.rows, self._o.cols))
+        L.check(L.lib().gs_grid2d_download(self._o._h, which, out.ctypes.data))
+        return out
+
+    def _set(self, which, values):
+        v = _d(values)
+        assert v.size == self._o.rows * self._o.cols
+        L.check(L.lib().gs_grid2d_upload(self._o._h, which, v.ctypes.data))
+
+    grid = property(lambda s: s._get(GRID), lambda s, v: s._set(GRID, v))
+    predict = property(lambda s: s._get(PREDICT), lambda s, v: s._set(PREDICT, v))
+    result = property(lambda s: s._get(RESULT), lambda s, v: s._set(RESULT, v))
+
+    def update(self):
+        L.check(L.lib().gs_grid2d_update(self._o._h))
+
+    @property
+    def avValue(self) -> float:
+        out = C.c_double()
+        L.check(L.lib().gs_grid2d_av_value(self._o._h, C.byref(out)))
+        return out.value
+
+
+class TwoDGrid:
+    """approximation.TwoDGrid.  TwoDGrid(x, y)(upCount, upKind)(lowCount, lowKind)(rightCount,
+    rightKind)(leftCount, leftKind)(coefs) of the reference (:553-574) becomes keyword pairs."""
+
+    def __init__(self, x: XDim, y: YDim, upp=(One, Temp), low=(One, Temp), right=(One, Temp), left=(One, Temp),
+                 coefs: Optional[Coefficients] = None, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.x, self.y = x, y
+        self.cols, self.rows = x.colsNum, y.rowsNum
+        xv, yv = _d(x.values), _d(y.values)
+        self._h = C.c_void_p()
+        L.check(L.lib().gs_grid2d_create(self.ctx._h, self.cols, self.rows, x.t, y.t, _p(xv), _p(yv), C.byref(self._h)))
+        self.grid = _GridArrays(self)
+        mk = lambda side, spec: _Bound(self, side, spec[1], spec[0])
+        self.bounds = _Bounds(mk(UPP, upp), mk(LOW, low), mk(RIGHT, right), mk(LEFT, left))
+        for b in (self.bounds.upp, self.bounds.low, self.bounds.right, self.bounds.left):
+            b.update(0.0)
+        self.coefs = coefs
+        if coefs is not None:
+            self.set_coefs(coefs)
+        # the class body ends with noHeatFlow on all four sides (:446-449)
+        for side in (UPP, LOW, RIGHT, LEFT):
+            self.noHeatFlow(side)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib().gs_grid2d_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_coefs(self, coefs: Coefficients):
+        self.coefs = coefs
+        for sel, (mode, ids) in coefs.maps(self.cols, self.rows).items():
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+            L.check(L.lib().gs_grid2d_set_map(self._h, sel, mode, ids.ctypes.data_as(_ip)))
+
+    def fill(self, v: float):  # `grid *= v` (:84, 488-495)
+        L.check(L.lib().gs_grid2d_fill(self._h, v))
+
+    def xIter(self, time: float):
+        L.check(L.lib().gs_grid2d_xiter(self._h, time))
+
+    def yIter(self, time: float):
+        L.check(L.lib().gs_grid2d_yiter(self._h, time))
+
+    def iteration(self, time: float, nsteps: int = 1):
+        L.check(L.lib().gs_grid2d_iteration(self._h, time, nsteps))
+
+    def updatePredicted(self):
+        L.check(L.lib().gs_grid2d_update_predicted(self._h))
+
+    def noHeatFlow(self, side: int):
+        L.check(L.lib().gs_grid2d_no_heat_flow(self._h, side))
+
+    def _edge(self, side) -> float:
+        out = C.c_double()
+        L.check(L.lib().gs_grid2d_edge_average(self._h, side, C.byref(out)))
+        return out.value
+
+    leftAverage = property(lambda s: s._edge(LEFT))
+    rightAverage = property(lambda s: s._edge(RIGHT))
+    upperAverage = property(lambda s: s._edge(UPP))
+    lowerAverage = property(lambda s: s._edge(LOW))
+
+    @property
+    def avValue(self) -> float:
+        return self.grid.avValue
+
+    def set_solver(self, solver: int):
+        L.check(L.lib().gs_grid2d_set_solver(self._h, solver))
+
+    @property
+    def status(self) -> int:
+        f = C.c_uint32()
+        L.check(L.lib().gs_grid2d_status(self._h, C.byref(f)))
+        return f.value
+
+    def clear_status(self):
+        L.check(L.lib().gs_grid2d_clear_status(self._h))
+
+    @property
+    def bytes_per_step(self) -> float:
+        b = C.c_double()
+        L.check(L.lib().gs_grid2d_bytes_per_step(self._h, C.byref(b)))
+        return b.value

@@ -1,0 +1,110 @@
+// gs_internal.h -- host-side structures behind the opaque handles of include/gs_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gs_b200.h"
+
+void gs_set_error(const char *fmt, ...);
+
+#define GS_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      gs_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return (e__ == cudaErrorMemoryAllocation) ? GS_ERR_OOM : GS_ERR_CUDA;                 \
+    }                                                                                       \
+  } while (0)
+
+#define GS_REQUIRE(cond, msg)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      gs_set_error("bad argument: %s", msg);  \
+      return GS_ERR_BAD_ARG;                  \
+    }                                         \
+  } while (0)
+
+#define GS_TRY(expr)             \
+  do {                           \
+    int s__ = (expr);            \
+    if (s__ != GS_OK) return s__; \
+  } while (0)
+
+struct gs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  uint64_t launches = 0;
+  // spline pool (host copy + device mirror, re-uploaded when it grows)
+  std::vector<double> pool;
+  std::vector<int> spline_off;
+  double *pool_dev = nullptr;
+  size_t pool_dev_len = 0;
+  bool pool_dirty = true;
+  // staging buffer for host<->device transposes and reductions
+  double *stage = nullptr;
+  size_t stage_bytes = 0;
+  // options
+  int64_t opt_threads_per_sm_1d = 512;
+  int64_t opt_block_1d = 128;
+  int64_t opt_block_y = 128;
+  int64_t opt_native_div = 0;
+  int64_t opt_const_hoist = 1;
+  int64_t opt_smem_nodes = -1;
+};
+
+int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice
+int gs_ctx_sync_pool(gs_ctx *ctx);           // upload the spline pool if it changed
+int gs_ctx_stage(gs_ctx *ctx, size_t bytes); // make sure ctx->stage holds at least `bytes`
+
+struct gs_grid1d {
+  gs_ctx *ctx = nullptr;
+  int64_t nlines = 0, pitch = 0;
+  int n = 0, dir = 0;
+  int spline_mode = 0;
+  int single_off = 0;
+  bool all_const = false;       // every selected spline is temperature independent
+  int *node_off = nullptr;      // [2n] pool offsets (PER_NODE)
+  double *predef = nullptr;     // [2n]
+  double *grid = nullptr, *predict = nullptr;
+  double *leftT = nullptr, *rightT = nullptr;
+  int bc_stride = 0;
+  bool bc_set = false;
+  double2 *scratch = nullptr;
+  size_t scratch_elems = 0;
+  unsigned *status = nullptr;
+  int solver = GS_SOLVER_AUTO;
+};
+
+struct gs_dim2d {
+  int dir = 0, n = 0;
+  double *values = nullptr;  // [n+2] low ++ range ++ upp
+  double *coefs = nullptr;   // [2n] Dim.coefs, sigma = 1.0
+  double hf[4] = {0, 0, 0, 0};  // firstVol, fC, lastVol, lA
+};
+
+struct gs_bound2d {
+  int kind = GS_TEMP, rep = GS_SPARSE;
+  double *values = nullptr;  // device, side length (SPARSE keeps the scalar broadcast)
+};
+
+struct gs_grid2d {
+  gs_ctx *ctx = nullptr;
+  int cols = 0, rows = 0;
+  gs_dim2d x, y;
+  gs_bound2d b[4];
+  double *grid = nullptr, *predict = nullptr, *result = nullptr;
+  bool result_is_grid = false;  // after a fused iteration `result` equals `grid`
+  int map_mode[4] = {0, 0, 0, 0};
+  int *map[4] = {nullptr, nullptr, nullptr, nullptr};  // device, pool OFFSETS (not ids)
+  std::vector<int> map_host[4];                         // ids as given
+  double2 *scratch = nullptr;
+  size_t scratch_elems = 0;
+  unsigned *status = nullptr;
+  int solver = GS_SOLVER_AUTO;
+};

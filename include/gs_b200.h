@@ -1,0 +1,182 @@
+/*
+ * gs_b200.h -- C ABI of libgs_b200.so: the B200-native (sm_100a, FP64 CUDA)
+ * implicit heat/diffusion time-stepper of gridsplines.
+ *
+ * This is the drop-in boundary for ONE path of the reference: everything that
+ * runs under TwoDGrid.iteration / xIter / yIter / Grid.update, OneDGrid.step and
+ * passion.iteration.  The reference has no FFI of its own (it is pure Scala);
+ * each entry point below names the Scala member it replaces.  Citations are
+ * relative to the reference tree:
+ *   A/ = approximation/src/main/scala/approximation/
+ *   P/ = piecewise/src/main/scala/piecewise/
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, enums; no C++/torch/CUDA types in signatures.
+ *     `stream` arguments are a cudaStream_t passed as void* (NULL = the library
+ *     creates its own non-blocking stream).
+ *   - every function returns GS_OK (0) or a negative gs_status; gs_last_error()
+ *     returns a thread-local message for the last failure.  No exception
+ *     crosses the ABI.
+ *   - host arrays are caller-owned and copied; handles own device memory.
+ *   - a context and the handles made from it belong to one host thread at a
+ *     time (the reference is single-threaded and non-reentrant per Dim,
+ *     A/Dim.scala:18-19).
+ *   - there is NO CPU implementation behind these symbols: without a CUDA
+ *     device gs_ctx_create fails with GS_ERR_NO_DEVICE.
+ *   - numeric faults that the JVM reports by exception are reported through a
+ *     sticky device status word (gs_*_status): see GS_FLAG_*.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum gs_status {
+  GS_OK = 0,
+  GS_ERR_BAD_ARG = -1,
+  GS_ERR_NO_DEVICE = -2,
+  GS_ERR_CUDA = -3,
+  GS_ERR_OOM = -4,
+  GS_ERR_STATE = -5
+} gs_status;
+
+/* piece kinds: P/Const.scala, P/Line.scala, P/Hermite3.scala + P/M1Hermite3.scala
+ * (shifted cubic, FMA Horner, P/PieceFunction.scala:188-198) */
+enum { GS_CONST = 0, GS_LINE = 1, GS_CUBIC = 2 };
+/* direction kinds: A/TypeDir.scala:23-51 (Ortho), :54-98 (Radial) */
+enum { GS_ORTHO = 0, GS_RADIAL = 1 };
+/* bound kinds A/TwoDGrid.scala:687-728, representations :593-665, sides :744-781 */
+enum { GS_TEMP = 0, GS_FLOW = 1 };
+enum { GS_SPARSE = 0, GS_DENSE = 1 };
+enum { GS_UPP = 0, GS_LOW = 1, GS_RIGHT = 2, GS_LEFT = 3 };
+/* Coefficients members A/TwoDGrid.scala:782-787 */
+enum { GS_SEL_APPLY = 0, GS_SEL_THERM = 1, GS_SEL_CAP = 2, GS_SEL_TEMPCOND = 3 };
+/* how a selector map is indexed (flattened Coefficients hierarchy, A/TwoDGrid.scala:790-1137):
+ * SINGLE 1 id; PER_ROW rows+1 ids at [row+1]; PER_COL cols+1 ids at [col+1];
+ * DENSE (rows+1)*(cols+1) ids at [(row+1)*(cols+1)+(col+1)]  (indices start at -1) */
+enum { GS_MAP_SINGLE = 0, GS_MAP_PER_ROW = 1, GS_MAP_PER_COL = 2, GS_MAP_DENSE = 3 };
+/* arrays of a grid: Grid.grid / predict / result  A/TwoDGrid.scala:461-463, A/OneDGrid.scala:20-22 */
+enum { GS_GRID = 0, GS_PREDICT = 1, GS_RESULT = 2 };
+/* host layouts of a 1-D batch: LINE_MAJOR host[line*n + node] (one OneDGrid.grid after
+ * another); INTERLEAVED host[node*nlines + line] (the device-internal order) */
+enum { GS_LINE_MAJOR = 0, GS_INTERLEAVED = 1 };
+/* 1-D spline selection: SINGLE = OneDGrid.apply(leftX, rangeX, rightX, conductivity, sigma)
+ * A/OneDGrid.scala:66-79 / passion.iteration overload 2 A/passion/package.scala:97-139;
+ * PER_NODE = conductivities(z)(0), conductivities(z)(1), overload 1 :52-95 (2n ids) */
+enum { GS_SPLINE_SINGLE = 0, GS_SPLINE_PER_NODE = 1 };
+/* line-solver algorithm.  THOMAS = one thread per line in the reference's operation order
+ * (bit-exact).  PARTITIONED = a line is cut into segments solved concurrently and stitched
+ * through a reduced system (changes the operation order: <= 1e-12 relative, not bit-exact). */
+enum { GS_SOLVER_AUTO = 0, GS_SOLVER_THOMAS = 1, GS_SOLVER_PARTITIONED = 2 };
+
+/* sticky status flags */
+#define GS_FLAG_SPLINE_UNDEFINED 1u /* RuntimeException, P/intervaltree/AbsITree.scala:475-479 (NaN argument) */
+#define GS_FLAG_NOT_DOMINANT 2u     /* AssertionError, A/passion/package.scala:279-282 */
+#define GS_FLAG_NONFINITE 4u        /* a solved temperature is NaN/Inf (no JVM analogue: values just propagate) */
+
+typedef struct gs_ctx gs_ctx;
+typedef struct gs_grid1d gs_grid1d;
+typedef struct gs_grid2d gs_grid2d;
+
+int gs_version(void);
+const char *gs_last_error(void);
+
+/* ---- context ---------------------------------------------------------- */
+int gs_ctx_create(int device, void *stream, gs_ctx **out);
+int gs_ctx_destroy(gs_ctx *ctx);
+int gs_ctx_synchronize(gs_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int gs_ctx_launch_count(gs_ctx *ctx, uint64_t *count);
+/* tuning knobs (documented in DESIGN.md); returns GS_ERR_BAD_ARG for unknown names */
+int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value);
+
+/* ---- spline tables ---------------------------------------------------- */
+/* One AlwaysDefinedSpline (A/AlwaysDefinedSpline.scala:4-46) over a piecewise.Spline
+ * (P/Spline.scala:13-133): npieces contiguous pieces, piece p owning [knots[p], knots[p+1])
+ * and the last one [knots[np-1], knots[np]] (P/intervaltree/AbsITree.scala:141-146).
+ * x0[p], coefs[4p..4p+3]: CONST c0=value; LINE c0=intercept c1=slope (evaluated slope*x+intercept,
+ * P/Line.scala:24); CUBIC c0..c3 about x0 (P/M1Hermite3.scala:18).  The four clamp scalars are
+ * AlwaysDefinedSpline.lowerX/upperX/lowerY/upperY (:5-8) exactly as the host computed them
+ * (including the reference's greatestK quirk).  *id_out indexes the context pool. */
+int gs_spline_create(gs_ctx *ctx, int kind, int npieces, const double *knots, const double *x0,
+                     const double *coefs, double lowerX, double upperX, double lowerY,
+                     double upperY, int *id_out);
+/* device evaluation of the pool (used by the parity tests; mirrors
+ * AlwaysDefinedSpline.apply :10-14 and .average :43-46); n host values in/out */
+int gs_spline_eval_apply(gs_ctx *ctx, int id, int n, const double *x, double *out);
+int gs_spline_eval_average(gs_ctx *ctx, int id, int n, const double *lo, const double *hi,
+                           double *out);
+
+/* ---- metric coefficients (K1) ----------------------------------------- */
+/* TypeDir.preDef: arraygrid.makeOrthogonalMatrix A/arraygrid/package.scala:21-78 /
+ * makeRadialMatrix :120-176; out[2i], out[2i+1] = (a_i, c_i).  Computed on the device. */
+int gs_predef(gs_ctx *ctx, int dir, double low, const double *range, int n, double upp,
+              double sigma, double *out_2n);
+/* (firstVol, fC, lastVol, lA): TypeDir.lowerHeatFlow/upperHeatFlow A/TypeDir.scala:31-44, 65-79 */
+int gs_heatflow_geometry(gs_ctx *ctx, int dir, double low, const double *range, int n, double upp,
+                         double *out4);
+
+/* ---- batched 1-D grids: nlines independent OneDGrid (A/OneDGrid.scala:14-34) ---- */
+/* All lines share geometry and spline selection.  grid = predict = result = 4.0 at creation
+ * (:20-22).  spline_ids: 1 id (SINGLE) or 2n ids (PER_NODE).  host_predef (2n doubles) may be
+ * NULL (computed on the device from dir/leftX/rangeX/rightX/sigma, :24). */
+int gs_grid1d_create(gs_ctx *ctx, int64_t nlines, int n, int dir, double leftX, const double *rangeX,
+                     double rightX, double sigma, int spline_mode, const int *spline_ids,
+                     const double *host_predef, gs_grid1d **out);
+int gs_grid1d_destroy(gs_grid1d *g);
+int gs_grid1d_upload(gs_grid1d *g, int which, int layout, const double *host);
+int gs_grid1d_download(gs_grid1d *g, int which, int layout, double *host);
+int gs_grid1d_fill(gs_grid1d *g, int which, double value);
+/* Dirichlet end temperatures; stride 0 = one value for all lines, 1 = per line */
+int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double *rightT, int stride);
+/* nsteps x OneDGrid.step(time, leftT, rightT) (A/OneDGrid.scala:26-34) for every line */
+int gs_grid1d_step(gs_grid1d *g, double time, int nsteps);
+int gs_grid1d_set_solver(gs_grid1d *g, int solver);
+int gs_grid1d_status(gs_grid1d *g, uint32_t *flags);
+int gs_grid1d_clear_status(gs_grid1d *g);
+/* raw device pointer + element pitch of the interleaved array (zero-copy hosts, multi-GPU glue) */
+int gs_grid1d_device_ptr(gs_grid1d *g, int which, void **dptr, int64_t *pitch);
+/* algorithmic HBM bytes one step moves (32 B per node) */
+int gs_grid1d_bytes_per_step(gs_grid1d *g, double *bytes);
+
+/* ---- 2-D grids: TwoDGrid (A/TwoDGrid.scala) ---------------------------- */
+/* xvalues = low ++ range ++ upp (cols+2 doubles), yvalues likewise (rows+2): Dim.values
+ * A/Dim.scala:13.  grid/predict/result are zero at creation (makeArray :453-459); all four
+ * bounds start as Temperature(Sparse(0.0)); all selector maps start SINGLE -> id 0. */
+int gs_grid2d_create(gs_ctx *ctx, int cols, int rows, int xdir, int ydir, const double *xvalues,
+                     const double *yvalues, gs_grid2d **out);
+int gs_grid2d_destroy(gs_grid2d *g);
+/* flattened Coefficients: ids index the context spline pool */
+int gs_grid2d_set_map(gs_grid2d *g, int selector, int mode, const int *ids);
+/* Bound.update(value) / update(values): n == 1 scalar, else n == side length.  SPARSE with
+ * n > 1 stores the mean (Sparse.update(vals) A/TwoDGrid.scala:595-604) */
+int gs_grid2d_set_bound(gs_grid2d *g, int side, int kind, int rep, const double *values, int n);
+int gs_grid2d_get_bound(gs_grid2d *g, int side, double *out, int n);
+int gs_grid2d_fill(gs_grid2d *g, double value);          /* Grid.*=(v): grid and predict :488-495 */
+int gs_grid2d_upload(gs_grid2d *g, int which, const double *host);   /* row-major rows x cols */
+int gs_grid2d_download(gs_grid2d *g, int which, double *host);
+int gs_grid2d_xiter(gs_grid2d *g, double time);           /* TwoDGrid.xIter :135-193 */
+int gs_grid2d_yiter(gs_grid2d *g, double time);           /* TwoDGrid.yIter :195-252 */
+int gs_grid2d_update(gs_grid2d *g);                       /* Grid.update :474-481 */
+int gs_grid2d_iteration(gs_grid2d *g, double time, int nsteps); /* TwoDGrid.iteration :254-258 */
+int gs_grid2d_update_predicted(gs_grid2d *g);             /* :442-444 */
+int gs_grid2d_no_heat_flow(gs_grid2d *g, int side);       /* :413-440 */
+int gs_grid2d_edge_average(gs_grid2d *g, int side, double *out); /* left/right/upper/lowerAverage :353-411 */
+int gs_grid2d_av_value(gs_grid2d *g, double *out);        /* Grid.avValue :483-486 */
+int gs_grid2d_set_solver(gs_grid2d *g, int solver);
+int gs_grid2d_status(gs_grid2d *g, uint32_t *flags);
+int gs_grid2d_clear_status(gs_grid2d *g);
+int gs_grid2d_device_ptr(gs_grid2d *g, int which, void **dptr);
+int gs_grid2d_bytes_per_step(gs_grid2d *g, double *bytes); /* 64 B per node */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */

@@ -1,0 +1,49 @@
+"""Shared builders: the same problem set up in the oracle (O.*) and in gridsplines_b200 (gs.*)."""
+import numpy as np
+
+README_T = [100.0 + 10.0 * i for i in range(11)]
+README_RHO = [0.598, 0.826, 1.121, 1.496, 1.966, 2.547, 3.258, 4.122, 5.156, 6.397, 7.862]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bit_equal(a, b, what=""):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    ba, bb = bits(a), bits(b)
+    if not np.array_equal(ba, bb):
+        bad = np.flatnonzero(ba.ravel() != bb.ravel())
+        i = bad[0]
+        raise AssertionError(
+            f"{what}: {bad.size} of {a.size} values differ; first at flat index {i}: "
+            f"{a.ravel()[i]!r} ({ba.ravel()[i]:#x}) vs {b.ravel()[i]!r} ({bb.ravel()[i]:#x})"
+        )
+
+
+def max_rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    denom = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.abs(a - b) / denom))
+
+
+def both_splines(O, gs, kind, *args):
+    """(oracle spline, gs spline) built by the same factory."""
+    return getattr(O.Spline, kind)(*args), getattr(gs.Spline, kind)(*args)
+
+
+def table_points(lo=-20.0, hi=80.0, n=11, base=1.0, scale=0.1):
+    """y_i = base + scale * rho_i over n knots in [lo, hi]."""
+    xs = np.linspace(lo, hi, n)
+    return [(float(x), base + scale * README_RHO[i % len(README_RHO)]) for i, x in enumerate(xs)]
+
+
+def hermite_coefs(O, gs, ctx=None):
+    """k(T), c(T) M1Hermite3 tables and alpha = k / c rebuilt as M1Hermite3 (Spline./, P/Spline.scala:207-210)."""
+    kp = table_points(base=1.0, scale=0.1)
+    cp = table_points(base=2.0e6, scale=1.0e5)
+    ap = [(x, k / c) for (x, k), (_, c) in zip(kp, cp)]
+    ok, oc, oa = (O.Spline.m1Hermite3(p) for p in (kp, cp, ap))
+    gk, gc, ga = (gs.Spline.m1Hermite3(p) for p in (kp, cp, ap))
+    return (ok, oc, oa), (gk, gc, ga)

@@ -1,0 +1,193 @@
+"""GPU parity of the 2-D stepper (K3 x-sweep, K4 y-sweep, Grid.update) against the oracle and the committed
+fixtures: all four boundary kinds, both direction types, every coefficient-map mode.  GS_SOLVER_THOMAS keeps
+the reference's operation order: bit-exact (against the ascending-fold oracle for multi-piece tables;
+<= 1e-12 against the literal tree-order fold)."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import assert_bit_equal, max_rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _small(coefs="unit"):
+    xv, yv = cases.small2d_dims()
+    b = {s: (0, 0, [1.0]) for s in range(4)}
+    return cases.Problem2D(xv, yv, 1, 0, b, coefs=coefs, init=(np.ones((10, 8)), np.ones((10, 8))))
+
+
+def test_kat_r3_r4_r5(O, gs):
+    p = _small()
+    p.bounds[3] = (0, 0, [4.0])
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.xIter(900.0); o.xIter(900.0)
+    g.grid.update(); o.update()
+    assert list(g.grid.grid[0]) == [3.10981041911049, 2.5775720576159933, 2.1989042489843205, 1.9055689452327573,
+                                    1.6664820491786831, 1.464861323850035, 1.2906054403084588, 1.137154150062293]
+    assert g.leftAverage == o.edgeAverage(O.LEFT) and g.rightAverage == o.edgeAverage(O.RIGHT)
+    assert g.leftAverage > g.rightAverage  # AT/TwoDGridUnit.scala:63-73
+    # R4: yIter alone consumes whatever `result` holds (zeros)
+    p = _small()
+    p.bounds[0] = (0, 0, [4.0])
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.yIter(900.0); o.yIter(900.0)
+    g.grid.update(); o.update()
+    for k, v in cases.snapshot(o).items():
+        assert_bit_equal(cases.snapshot(g)[k], v, "R4 " + k)
+    assert g.upperAverage == o.edgeAverage(O.UPP) and g.lowerAverage == o.edgeAverage(O.LOW)
+    assert g.upperAverage > g.lowerAverage  # :75-85
+    # R5
+    p = _small()
+    p.bounds[3] = (0, 0, [4.0])
+    g = p.build_gs(gs)
+    g.iteration(900.0)
+    assert g.grid.grid[0, 0] == 1.0115798259742925
+    assert g.avValue == pytest.approx(1.0110804508847722, rel=1e-13) and g.avValue > 1.0  # :87-94
+
+
+@pytest.mark.parametrize("name,combo,xdir,coefs", [
+    ("grid2d_TTFF_ortho_const", "TTFF", 0, "const"),
+    ("grid2d_FFTT_radial_const", "FFTT", 1, "const"),
+    ("grid2d_TTTT_radial_hermite", "TTTT", 1, "hermite"),
+])
+def test_vs_golden(gs, name, combo, xdir, coefs):
+    p = cases.bc_problem(combo, xdir=xdir, coefs=coefs)
+    g = p.build_gs(gs)
+    g.iteration(900.0, nsteps=3)
+    want = np.load(os.path.join(GOLDEN, name + ".npz"))
+    got = cases.snapshot(g)
+    for k in want.files:
+        assert_bit_equal(got[k], want[k], f"{name}.{k}")
+    assert g.status == 0
+
+
+@pytest.mark.parametrize("combo", ["".join(c) for c in itertools.product("TF", repeat=4)])
+@pytest.mark.parametrize("dense", [True, False])
+def test_all_boundary_kinds(O, gs, combo, dense):
+    xdir = 1 if combo.count("F") % 2 else 0
+    p = cases.bc_problem(combo, xdir=xdir, ydir=0, cols=41, rows=35, dense=dense)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    # separate calls first (xIter, yIter, update), then fused iterations
+    g.xIter(900.0); o.xIter(900.0)
+    assert_bit_equal(g.grid.result, o.result, combo + " xIter result")
+    g.yIter(900.0); o.yIter(900.0)
+    assert_bit_equal(g.grid.result, o.result, combo + " yIter result")
+    g.grid.update(); o.update()
+    g.iteration(900.0, nsteps=2)
+    o.iteration(900.0); o.iteration(900.0)
+    for k, v in cases.snapshot(o).items():
+        assert_bit_equal(cases.snapshot(g)[k], v, f"{combo} dense={dense} {k}")
+
+
+@pytest.mark.parametrize("cols,rows", [(2, 2), (2, 9), (9, 2), (3, 3), (32, 32), (33, 31), (64, 65), (130, 97)])
+@pytest.mark.parametrize("combo", ["TTTT", "FFFF", "TFTF"])
+def test_ragged_sizes(O, gs, cols, rows, combo):
+    p = cases.bc_problem(combo, xdir=1, ydir=1, cols=cols, rows=rows)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.iteration(900.0, nsteps=2)
+    o.iteration(900.0); o.iteration(900.0)
+    for k, v in cases.snapshot(o).items():
+        assert_bit_equal(cases.snapshot(g)[k], v, f"{cols}x{rows} {combo} {k}")
+
+
+@pytest.mark.parametrize("coefs", ["hermite", "per_row", "per_col", "dense"])
+@pytest.mark.parametrize("combo", ["TTTT", "TTFT"])
+def test_coefficient_maps_and_tables(O, gs, coefs, combo):
+    p = cases.bc_problem(combo, xdir=1, cols=37, rows=29, coefs=coefs)
+    # spread the temperatures over several table pieces so the interval average crosses knots
+    r = np.random.default_rng(4)
+    p.grid0 = r.uniform(-15.0, 70.0, p.grid0.shape)
+    p.predict0 = p.grid0 + r.uniform(-12.0, 12.0, p.grid0.shape)
+    g, o = p.build_gs(gs), p.build_oracle(O, ascending=True)
+    g.iteration(900.0, nsteps=3)
+    for _ in range(3):
+        o.iteration(900.0)
+    got = cases.snapshot(g)
+    for k, v in cases.snapshot(o).items():
+        assert_bit_equal(got[k], v, f"{coefs} {combo} {k}")
+    lit = p.build_oracle(O, ascending=False)
+    for _ in range(3):
+        lit.iteration(900.0)
+    O.set_ascending_fold(True)
+    for k, v in cases.snapshot(lit).items():
+        assert max_rel_err(got[k], v) <= 1e-12, k
+
+
+def test_gridtest_physical_validation(O, gs):
+    """AT/GridTest.scala: 137 x 45 radial x ortho, heated Neumann wall, 195 steps; bit-exact vs golden and
+    the wall temperature of KAT R1."""
+    p = cases.gridtest_problem()
+    g = p.build_gs(gs)
+    g.fill(7.0)
+    got = cases.run_gridtest(g, True)
+    want = np.load(os.path.join(GOLDEN, "gridtest_137x45x195.npz"))
+    for k in want.files:
+        assert_bit_equal(got[k], want[k], "GridTest " + k)
+    assert got["grid"][0, 0] == 54.44328715390563
+
+
+def test_no_heat_flow_and_bounds(O, gs):
+    p = cases.bc_problem("TFTF", cols=13, rows=11, dense=True)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    for side in range(4):
+        g.noHeatFlow(side); o.noHeatFlow(side)
+    for side, b in zip((0, 1, 2, 3), (g.bounds.upp, g.bounds.low, g.bounds.right, g.bounds.left)):
+        assert_bit_equal(b.get(), o.get_bound(side), f"noHeatFlow side {side}")  # AT/TwoDGridUnit.scala:104-130
+    p = cases.bc_problem("TFTF", cols=13, rows=11, dense=False)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    for side in range(4):
+        g.noHeatFlow(side); o.noHeatFlow(side)
+    for side, b in zip((0, 1, 2, 3), (g.bounds.upp, g.bounds.low, g.bounds.right, g.bounds.left)):
+        assert_bit_equal(b.get(), o.get_bound(side), f"sparse noHeatFlow side {side}")
+    # Sparse.update(vals) stores the mean
+    vals = np.linspace(1.0, 2.0, 13)
+    g.bounds.upp.update(vals); o.set_bound(0, 0, 0, vals)
+    assert_bit_equal(g.bounds.upp.get(), o.get_bound(0))
+
+
+def test_medium_grid_properties(O, gs):
+    """512 x 384 against the oracle (bit-exact), then a 2048 x 2048 run checked through properties: a field that
+    is uniform along x with x-independent BCs stays uniform along x (every column solve is identical)."""
+    p = cases.bc_problem("TTFF", cols=512, rows=384)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.iteration(900.0, nsteps=2)
+    o.iteration(900.0); o.iteration(900.0)
+    for k, v in cases.snapshot(o).items():
+        assert_bit_equal(cases.snapshot(g)[k], v, "512x384 " + k)
+    # 2048 x 2048 through properties: lines are independent, so a field that is uniform across the lines
+    # gives bit-identical lines, and each equals the oracle's solve of a 2-line grid with the same data.
+    n = 2048
+    xv, yv = 0.05 + 0.01 * np.arange(n + 2), 0.01 * np.arange(n + 2)
+    r = np.random.default_rng(2)
+    line_p, line_g = 7.0 + r.uniform(size=n), 7.0 + r.uniform(size=n)
+    bx = {0: (0, 1, np.full(n, 20.0)), 1: (0, 1, np.full(n, 4.0)), 2: (1, 0, [3.0]), 3: (0, 0, [9.0])}
+    for sweep in ("x", "y"):
+        tile = (lambda v: np.tile(v[None, :], (n, 1))) if sweep == "x" else (lambda v: np.tile(v[:, None], (1, n)))
+        big = cases.Problem2D(xv, yv, 1, 0, bx, coefs="const", init=(tile(line_g), tile(line_p)))
+        g = big.build_gs(gs)
+        if sweep == "x":
+            small = cases.Problem2D(xv, yv[:4], 1, 0, {k: (v[0], v[1], v[2][:2] if len(v[2]) > 1 else v[2]) for k, v in bx.items()},
+                                    coefs="const", init=(tile(line_g)[:2], tile(line_p)[:2]))
+            o = small.build_oracle(O)
+            g.xIter(900.0); o.xIter(900.0)
+            res = g.grid.result
+            assert np.all(res.view(np.uint64) == res[:1].view(np.uint64))
+            assert_bit_equal(res[0], o.result[0], "2048^2 xIter row")
+        else:
+            by = {0: (0, 0, [20.0]), 1: (0, 0, [4.0]), 2: (0, 0, [1.0]), 3: (0, 0, [1.0])}
+            big.bounds = by
+            g = big.build_gs(gs)
+            g.grid.result = tile(line_g)
+            small = cases.Problem2D(xv[:4], yv, 1, 0, by, coefs="const", init=(tile(line_g)[:, :2], tile(line_p)[:, :2]))
+            o = small.build_oracle(O)
+            o.result[:] = tile(line_g)[:, :2]
+            g.yIter(900.0); o.yIter(900.0)
+            res = g.grid.result
+            assert np.all(res.view(np.uint64) == res[:, :1].view(np.uint64))
+            assert_bit_equal(res[:, 0], o.result[:, 0], "2048^2 yIter column")
+        assert g.status == 0

@@ -1,0 +1,66 @@
+"""GPU parity: K1 metric coefficients and device spline evaluation against the oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from helpers import README_RHO, README_T, assert_bit_equal, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("direction", [0, 1])
+@pytest.mark.parametrize("n", [2, 3, 200, 4097])
+def test_predef_and_heatflow_geometry(O, gs, ctx, direction, n):
+    r = np.random.default_rng(n)
+    rng = 0.05 + np.cumsum(r.uniform(1e-3, 2e-2, n))
+    low, upp = 0.05, rng[-1] + 0.013
+    for sigma in (1.0, 0.37):
+        assert_bit_equal(ctx.predef(direction, low, rng, upp, sigma), O.predef(direction, low, rng, upp, sigma), "preDef")
+    assert_bit_equal(ctx.heatflow_geometry(direction, low, rng, upp), O.heatflow_geometry(direction, low, rng, upp), "heatflow")
+
+
+def _pairs(O, gs):
+    pts = list(zip(README_T, README_RHO))
+    lin = [(0.0, 1.0), (10.0, 3.0), (25.0, 2.0), (40.0, 7.5)]
+    return [
+        (O.Spline.const(1.5), gs.Spline.const(1.5)),
+        (O.Spline.const(2.0, 0.0, 50.0), gs.Spline.const(2.0, 0.0, 50.0)),
+        (O.Spline.lines(lin), gs.Spline.lines(lin)),
+        (O.Spline.m1Hermite3(pts), gs.Spline.m1Hermite3(pts)),
+        (O.Spline.fHermite3(pts), gs.Spline.fHermite3(pts)),
+    ]
+
+
+@pytest.mark.parametrize("true_upper", [False, True])
+def test_always_defined_spline_apply_and_average(O, gs, ctx, true_upper):
+    r = np.random.default_rng(11)
+    for os_, gsp in _pairs(O, gs):
+        oa = O.AlwaysDefinedSpline(os_, true_upper=true_upper)
+        ga = gs.AlwaysDefinedSpline(gsp, ctx, true_upper=true_upper)
+        assert oa.clamps == ga.clamps
+        lo_k, hi_k = max(gsp.knots[0], -50.0), min(gsp.knots[-1], 250.0)
+        xs = np.concatenate([r.uniform(lo_k - 30.0, hi_k + 30.0, 4000), gsp.knots[np.isfinite(gsp.knots)],
+                             [lo_k, hi_k, 0.0, -0.0]])
+        xs = xs[np.abs(xs) < 1e300]
+        assert_bit_equal(ga(xs), np.array([oa(x) for x in xs]), "apply")
+        a = r.uniform(lo_k - 30.0, hi_k + 30.0, 4000)
+        b = np.where(r.uniform(size=4000) < 0.5, a + r.uniform(0.0, 3.0, 4000), r.uniform(lo_k - 30.0, hi_k + 30.0, 4000))
+        b[:50] = a[:50]  # the t_lo == t_hi branch
+        # ordered (takeAverage) and raw order (Neumann calls, A/Dim.scala:55,116)
+        O.set_ascending_fold(True)
+        want = np.array([oa.average(x, y) for x, y in zip(a, b)])
+        assert_bit_equal(ga.average(a, b), want, "average (ascending fold)")
+        O.set_ascending_fold(False)
+        lit = np.array([oa.average(x, y) for x, y in zip(a, b)])
+        ok = np.isfinite(lit) & (lit != 0.0)
+        assert max_rel_err(ga.average(a, b)[ok], lit[ok]) <= 1e-12
+
+
+def test_spline_undefined_is_flagged(gs, ctx):
+    g = gs.OneDGrid(0.0, [0.1, 0.2, 0.3], 0.4, gs.Spline.const(1e-6), 1.0)
+    g.grid = [1.0, float("nan"), 2.0]
+    g.step(900.0, 1.0, 2.0)
+    assert g.status & gs.FLAG_NONFINITE
+    g2 = gs.OneDGrid(0.0, [0.1, 0.2, 0.3], 0.4, gs.Spline.const(1e-6), 1.0)
+    g2.upload(gs.PREDICT, np.array([[1.0, float("nan"), 2.0]]))
+    g2.step(900.0, 1.0, 2.0)
+    assert g2.status & gs.FLAG_SPLINE_UNDEFINED  # RuntimeException in the reference (AbsITree.scala:475-479)
