@@ -98,6 +98,8 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "native_div")) ctx->opt_native_div = value;
   else if (!strcmp(name, "const_hoist")) ctx->opt_const_hoist = value;
   else if (!strcmp(name, "smem_nodes")) ctx->opt_smem_nodes = value;
+  else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = value;
+  else if (!strcmp(name, "pipe_cfg")) ctx->opt_pipe_cfg = value;
   else {
     gs_set_error("unknown option '%s'", name);
     return GS_ERR_BAD_ARG;
@@ -200,7 +202,8 @@ __global__ void k_eval_average(const double *pool, int off, int n, const double 
   if (i >= n) return;
   GsSpline s = gs_spline_view(pool, off);
   unsigned flags = 0;
-  out[i] = gs_ads_average(s, lo[i], hi[i], flags);
+  bool ok = true;
+  out[i] = gs_ads_average<false>(s, lo[i], hi[i], flags, ok);
   gs_raise(status, flags);
 }
 

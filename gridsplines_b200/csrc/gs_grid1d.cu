@@ -1,12 +1,13 @@
 // gs_grid1d.cu -- batched 1-D grids: nlines independent OneDGrid.step() (A/OneDGrid.scala:26-34
 // = passion.iteration A/passion/package.scala:52-139 + predictor A/arraygrid/package.scala:85-87).
 //
-// Device layout: node-major ("interleaved") arrays a[node * pitch + line], so the 32 lines of a
-// warp are 32 adjacent doubles at every node step (one 256 B coalesced access per array).
-// One thread owns one line and runs the reference's Thomas recurrence in the reference's
-// operation order; (delta, lambda) of the forward pass go to a per-thread scratch column that is
-// reused for every line the thread processes (persistent grid), laid out [node][thread] so it is
-// coalesced too.
+// Device layout: blocked node-major arrays a[line / 32][node][line % 32].  The 32 lines of a warp are
+// 32 adjacent doubles at every node step (one 256 B coalesced access per array) AND a warp's whole
+// working set (n x 256 B per array) is one contiguous stream, so DRAM pages / TLB entries are not
+// thrashed by a large line stride.  One thread owns one line and runs the reference's Thomas
+// recurrence in the reference's operation order; (delta, lambda) of the forward pass go to a per-warp
+// scratch block with the same [node][lane] shape, reused for every line block the warp processes
+// (persistent grid), so its footprint is bounded by the number of resident warps, not by nlines.
 #include <stdio.h>
 #include <string.h>
 
@@ -14,12 +15,15 @@
 
 #include "gs_device.cuh"
 #include "gs_internal.h"
+#include "gs_tma.cuh"
 
 int gs_launch_predef(gs_ctx *ctx, int dir, const double *values_dev, int n, double sigma, double *coefs_dev);
 
+#define GS_LB 32  // lines per block of the device layout (one warp)
+
 struct Step1dParams {
   int n;
-  long long nlines, pitch, G;
+  long long nlines, nblocks, nwarps;
   double *grid, *predict;
   double2 *scratch;
   const double *predef;
@@ -33,115 +37,446 @@ struct Step1dParams {
   int nsteps;
   unsigned *status;
   int smem_predef, smem_pool;
+  int allow_fast;
 };
 
-// K2: one thread = one line, all nsteps of it (lines are independent and their end
-// temperatures are fixed during the call, so the step loop sits inside the line loop).
+struct Line1d {
+  const double *pd;     // preDef [2n]
+  const double *pool;   // spline pool
+  const int *node_off;  // PER_NODE offsets
+  GsSpline z;           // SINGLE spline
+  GsRcp rt;             // time step
+  double inv_time;      // 1.0 / time
+  int n;
+};
+
+// Forward pass of one line (passion.iteration :52-95 / :97-139): assembly + elimination.
+// G, P: this lane's column of the line block (node stride GS_LB); sc: its scratch column.
+// Returns the FAST-mode validity; (delta, lambda) of the last node stay in registers.
+template <int MODE, bool FAST>
+GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const double *__restrict__ P,
+                         double2 *__restrict__ sc, double firstT, double lastT, double &delta, double &lambda,
+                         unsigned &flags) {
+  const int n = L.n;
+  bool ok = true;
+  double t1 = firstT, t2 = P[0], t3 = P[GS_LB];
+  double condL, condR;
+  if (MODE == GS_SPLINE_SINGLE) {
+    condL = gs_ads_apply(L.z, (t1 + t2) / 2.0, flags);   // cons :21-25
+    condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+  } else {
+    condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[0]), (t1 + t2) / 2.0, flags);
+    condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[1]), (t2 + t3) / 2.0, flags);
+  }
+  double a = condL * L.pd[0];
+  double c = condR * L.pd[1];
+  double vect = gs_div<FAST>(-G[0], L.rt, ok) - a * t1;
+  gs_forward_first<FAST>(-(a + c) - L.inv_time, c, vect, delta, lambda, ok);
+  sc[0] = make_double2(delta, lambda);
+  int i = 1;
+#pragma unroll 4
+  for (; i < n - 1; ++i) {
+    t1 = t2;
+    t2 = t3;
+    t3 = P[(i + 1) * GS_LB];
+    if (MODE == GS_SPLINE_SINGLE) {
+      // node i's left face is node i-1's right face evaluated with the same spline at the same
+      // argument: the same double, so it is carried instead of re-evaluated
+      condL = condR;
+      condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+    } else {
+      condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
+      condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
+    }
+    a = condL * L.pd[2 * i];
+    c = condR * L.pd[2 * i + 1];
+    vect = gs_div<FAST>(-G[i * GS_LB], L.rt, ok);
+    gs_forward_unit<FAST>(a, -(a + c) - L.inv_time, c, vect, delta, lambda, flags, ok);
+    sc[i * GS_LB] = make_double2(delta, lambda);
+  }
+  t1 = t2;
+  t2 = t3;
+  t3 = lastT;
+  if (MODE == GS_SPLINE_SINGLE) {
+    condL = condR;
+    condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+  } else {
+    condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
+    condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
+  }
+  a = condL * L.pd[2 * i];
+  c = condR * L.pd[2 * i + 1];
+  vect = gs_div<FAST>(-G[i * GS_LB], L.rt, ok) - c * t3;
+  gs_forward_last<FAST>(a, -(a + c) - L.inv_time, vect, delta, lambda, ok);
+  return ok;
+}
+
+// K2: one warp = one block of 32 lines, one thread = one line, all nsteps of it (lines are
+// independent and their end temperatures are fixed during the call, so the step loop sits inside
+// the block loop).  Persistent: warp w processes blocks w, w + nwarps, ... and reuses its scratch.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_step1d(Step1dParams p) {
   extern __shared__ double sm[];
   const int n = p.n;
-  const double *pd = p.predef;
-  const double *pool = p.pool;
+  Line1d L;
+  L.n = n;
+  L.pd = p.predef;
+  L.pool = p.pool;
+  L.node_off = p.node_off;
   {
     int base = 0;
     if (p.smem_predef) {
       for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) sm[i] = p.predef[i];
-      pd = sm;
+      L.pd = sm;
       base = 2 * n;
     }
     if (p.smem_pool) {
       for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) sm[base + i] = p.pool[i];
-      pool = sm + base;
+      L.pool = sm + base;
     }
     __syncthreads();
   }
-  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long G = p.G, pitch = p.pitch;
-  double2 *sc = p.scratch + gtid;
-  const GsRcp rt = gs_rcp(p.time);
-  const GsRcp r3 = gs_rcp(3.0);
-  const double inv_time = 1.0 / p.time;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= p.nwarps) return;
+  bool fast_allowed = p.allow_fast != 0;
+  L.rt = gs_rcp_invariant(p.time, fast_allowed);
+  GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
+  L.inv_time = 1.0 / p.time;
+  if (MODE == GS_SPLINE_SINGLE) L.z = gs_spline_view(L.pool, p.single_off);
   unsigned flags = 0;
-  GsSpline z;
-  if (MODE == GS_SPLINE_SINGLE) z = gs_spline_view(pool, p.single_off);
+  const size_t block_elems = (size_t)n * GS_LB;
+  double2 *sc = p.scratch + (size_t)warp * block_elems + lane;
 
-  for (long long line = gtid; line < p.nlines; line += G) {
-    double *Gp = p.grid + line;
-    double *Pp = p.predict + line;
-    const double firstT = p.leftT[line * p.bc_stride];
-    const double lastT = p.rightT[line * p.bc_stride];
+  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+    const long long line = blk * GS_LB + lane;
+    const bool valid = line < p.nlines;  // padding lanes compute on the padding lines (kept finite)
+    const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
+    double *Gp = p.grid + (size_t)blk * block_elems + lane;
+    double *Pp = p.predict + (size_t)blk * block_elems + lane;
+    const double firstT = p.leftT[bcl], lastT = p.rightT[bcl];
+    bool try_fast = fast_allowed;
     for (int step = 0; step < p.nsteps; ++step) {
-      // ---- forward: assembly + elimination (passion.iteration :52-95 / :97-139) ----
-      double t1 = firstT, t2 = Pp[0], t3 = Pp[pitch];
-      double condL, condR;
-      if (MODE == GS_SPLINE_SINGLE) {
-        condL = gs_ads_apply(z, (t1 + t2) / 2.0, flags);   // cons :21-25
-        condR = gs_ads_apply(z, (t2 + t3) / 2.0, flags);
-      } else {
-        condL = gs_ads_apply(gs_spline_view(pool, p.node_off[0]), (t1 + t2) / 2.0, flags);
-        condR = gs_ads_apply(gs_spline_view(pool, p.node_off[1]), (t2 + t3) / 2.0, flags);
-      }
-      double a = condL * pd[0];
-      double c = condR * pd[1];
-      double vect = gs_div(-Gp[0], rt) - a * t1;
       double delta, lambda;
-      gs_forward_first(-(a + c) - inv_time, c, vect, delta, lambda);
-      sc[0] = make_double2(delta, lambda);
-      int i = 1;
+      unsigned lf = 0;
+      bool ok = false;
+      if (try_fast) ok = forward_line<MODE, true>(L, Gp, Pp, sc, firstT, lastT, delta, lambda, lf);
+      if (!ok) {
+        // operands outside the proven range of the shared-reciprocal division (zeros, denormals,
+        // Inf/NaN, absurd magnitudes): this lane redoes the line with plain IEEE division
+        lf = 0;
+        forward_line<MODE, false>(L, Gp, Pp, sc, firstT, lastT, delta, lambda, lf);
+      }
+      // a warp whose data keeps failing the range test stops trying (uniform decision)
+      if (try_fast && __any_sync(0xffffffffu, !ok)) try_fast = false;
+
+      // ---- backward (backwardPassion :345-365) fused with OneDGrid.step's predictor and
+      // grid <- result (A/OneDGrid.scala:29-33) ----
+      double u = 0.0;
+      int i = n - 1;
+      {
+        u = delta * u + lambda;
+        double g = Gp[i * GS_LB];
+        double d = u - g;
+        bool okd = true;
+        double q = gs_div<true>(d, r3, okd);
+        if (!(okd && fast_allowed)) q = d / 3.0;
+        Pp[i * GS_LB] = u + q;   // arraygrid.aVal :85-87
+        Gp[i * GS_LB] = u;
+      }
 #pragma unroll 4
-      for (; i < n - 1; ++i) {
+      for (i = n - 2; i >= 0; --i) {
+        double2 dl = sc[i * GS_LB];
+        u = dl.x * u + dl.y;
+        double g = Gp[i * GS_LB];
+        double d = u - g;
+        bool okd = true;
+        double q = gs_div<true>(d, r3, okd);
+        if (!(okd && fast_allowed)) q = d / 3.0;
+        Pp[i * GS_LB] = u + q;
+        Gp[i * GS_LB] = u;
+      }
+      if (!(fabs(u) <= 1.7976931348623157e308)) lf |= GS_FLAG_NONFINITE;
+      if (valid) flags |= lf;
+    }
+  }
+  gs_raise(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------------
+// K2 (pipelined): the same per-thread Thomas, but every byte moves through the bulk-copy engine.
+//
+// A warp's line block is one contiguous stream per array (blocked layout), so the inputs of CH nodes are
+// one cp.async.bulk each (CH x 256 B).  Each warp runs its own ring of NSI input stages guarded by
+// mbarriers (lane 0 arms expect_tx and issues; all lanes wait on the phase bit) and two output stages
+// drained by bulk stores.  Threads only touch shared memory; no LDG/STG sits on the Thomas chain and no
+// registers are spent on prefetching.
+//   forward  stage : grid[CH] | predict[CH+1]  (one look-ahead node)       -> out: (delta, lambda)[CH]
+//   backward stage : (delta, lambda)[CH] | grid[CH]                         -> out: grid'[CH] | predict'[CH]
+// ---------------------------------------------------------------------------------
+template <int CH, int NSI>
+struct Pipe1d {
+  static constexpr int kInBytes = CH * 768;   // max(fwd (2CH+1)*256, bwd CH*768)
+  static constexpr int kOutBytes = CH * 512;
+  static constexpr int kWarpBytes = NSI * kInBytes + 2 * kOutBytes + 128;  // + mbarriers
+  static_assert((2 * CH + 1) * 256 <= CH * 768, "stage too small");
+};
+
+template <int MODE, bool FAST, int CH, int NSI>
+GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32_t &seq, uint32_t &oseq,
+                              const double *Gblk, const double *Pblk, double2 *Sblk, int lane, double firstT,
+                              double lastT, double &delta, double &lambda, unsigned &flags) {
+  typedef Pipe1d<CH, NSI> PP;
+  const int n = L.n;
+  const int NC = (n + CH - 1) / CH;
+  bool ok = true;
+  auto issue = [&](int c, uint32_t sq) {
+    int len = min(CH, n - c * CH);
+    int lenP = (c == NC - 1) ? len : len + 1;
+    int s = sq % NSI;
+    char *st = wsm + s * PP::kInBytes;
+    gs_mbar_expect_tx(&full[s], (uint32_t)(len + lenP) * 256u);
+    gs_bulk_g2s(st, Gblk + (size_t)c * CH * GS_LB, (uint32_t)len * 256u, &full[s]);
+    gs_bulk_g2s(st + CH * 256, Pblk + (size_t)c * CH * GS_LB, (uint32_t)lenP * 256u, &full[s]);
+  };
+  const uint32_t seq0 = seq;
+  if (lane == 0) {
+    for (int c = 0; c < min(NSI, NC); ++c) issue(c, seq0 + c);
+  }
+  double condL = 0.0, condR = 0.0, t1 = firstT, t2 = 0.0, t3 = 0.0, a, c_, vect;
+  for (int c = 0; c < NC; ++c) {
+    const uint32_t sq = seq0 + c;
+    const int s = sq % NSI;
+    gs_mbar_wait(&full[s], (sq / NSI) & 1u);
+    const char *st = wsm + s * PP::kInBytes;
+    const double *sG = reinterpret_cast<const double *>(st) + lane;
+    const double *sP = reinterpret_cast<const double *>(st + CH * 256) + lane;
+    char *ob = wsm + NSI * PP::kInBytes + (oseq & 1u) * PP::kOutBytes;
+    double2 *so = reinterpret_cast<double2 *>(ob) + lane;
+    if (oseq >= 2) {  // the bulk store that last used this output stage must have read it
+      if (lane == 0) gs_bulk_wait_read<1>();
+      __syncwarp();
+    }
+    const int len = min(CH, n - c * CH);
+    int mb = 0, me = len;
+    if (c == 0) {
+      // node 0 (:59-66)
+      t2 = sP[0];
+      t3 = sP[GS_LB];
+      if (MODE == GS_SPLINE_SINGLE) {
+        condL = gs_ads_apply(L.z, (t1 + t2) / 2.0, flags);   // cons :21-25
+        condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+      } else {
+        condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[0]), (t1 + t2) / 2.0, flags);
+        condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[1]), (t2 + t3) / 2.0, flags);
+      }
+      a = condL * L.pd[0];
+      c_ = condR * L.pd[1];
+      vect = gs_div<FAST>(-sG[0], L.rt, ok) - a * t1;
+      gs_forward_first<FAST>(-(a + c_) - L.inv_time, c_, vect, delta, lambda, ok);
+      so[0] = make_double2(delta, lambda);
+      mb = 1;
+    }
+    if (c == NC - 1) me = len - 1;
+#pragma unroll
+    for (int m = 0; m < CH; ++m) {
+      if (m >= mb && m < me) {
+        const int i = c * CH + m;
         t1 = t2;
         t2 = t3;
-        t3 = Pp[(long long)(i + 1) * pitch];
+        t3 = sP[(m + 1) * GS_LB];
         if (MODE == GS_SPLINE_SINGLE) {
-          // node i's left face is node i-1's right face evaluated with the same spline at the
-          // same argument: the same double, so it is carried instead of re-evaluated
+          // node i's left face is node i-1's right face evaluated with the same spline at the same
+          // argument: the same double, so it is carried instead of re-evaluated
           condL = condR;
-          condR = gs_ads_apply(z, (t2 + t3) / 2.0, flags);
+          condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
         } else {
-          condL = gs_ads_apply(gs_spline_view(pool, p.node_off[2 * i]), (t1 + t2) / 2.0, flags);
-          condR = gs_ads_apply(gs_spline_view(pool, p.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
+          condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
+          condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
         }
-        a = condL * pd[2 * i];
-        c = condR * pd[2 * i + 1];
-        vect = gs_div(-Gp[(long long)i * pitch], rt);
-        gs_forward_unit(a, -(a + c) - inv_time, c, vect, delta, lambda, flags);
-        sc[(long long)i * G] = make_double2(delta, lambda);
+        a = condL * L.pd[2 * i];
+        c_ = condR * L.pd[2 * i + 1];
+        vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok);
+        gs_forward_unit<FAST>(a, -(a + c_) - L.inv_time, c_, vect, delta, lambda, flags, ok);
+        so[m * GS_LB] = make_double2(delta, lambda);
       }
+    }
+    if (c == NC - 1) {
+      // node n-1 (:83-92); its (delta, lambda) stay in registers
+      const int i = n - 1, m = len - 1;
       t1 = t2;
       t2 = t3;
       t3 = lastT;
       if (MODE == GS_SPLINE_SINGLE) {
         condL = condR;
-        condR = gs_ads_apply(z, (t2 + t3) / 2.0, flags);
+        condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
       } else {
-        condL = gs_ads_apply(gs_spline_view(pool, p.node_off[2 * i]), (t1 + t2) / 2.0, flags);
-        condR = gs_ads_apply(gs_spline_view(pool, p.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
+        condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
+        condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
       }
-      a = condL * pd[2 * i];
-      c = condR * pd[2 * i + 1];
-      vect = gs_div(-Gp[(long long)i * pitch], rt) - c * t3;
-      gs_forward_last(a, -(a + c) - inv_time, vect, delta, lambda);
+      a = condL * L.pd[2 * i];
+      c_ = condR * L.pd[2 * i + 1];
+      vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok) - c_ * t3;
+      gs_forward_last<FAST>(a, -(a + c_) - L.inv_time, vect, delta, lambda, ok);
+    }
+    gs_fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const int lenS = (c == NC - 1) ? len - 1 : len;
+      if (lenS > 0) gs_bulk_s2g(Sblk + (size_t)c * CH * GS_LB, ob, (uint32_t)lenS * 512u);
+      gs_bulk_commit();
+      if (c + NSI < NC) issue(c + NSI, sq + NSI);
+    }
+    ++oseq;
+  }
+  seq = seq0 + NC;
+  return ok;
+}
+
+template <int MODE, int CH, int NSI>
+__global__ void __launch_bounds__(128) k_step1d_tma(Step1dParams p) {
+  typedef Pipe1d<CH, NSI> PP;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = p.n;
+  Line1d L;
+  L.n = n;
+  L.pd = p.predef;
+  L.pool = p.pool;
+  L.node_off = p.node_off;
+  const int nw = blockDim.x >> 5;
+  double *smd = reinterpret_cast<double *>(smraw + (size_t)nw * PP::kWarpBytes);
+  {
+    int base = 0;
+    if (p.smem_predef) {
+      for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) smd[i] = p.predef[i];
+      L.pd = smd;
+      base = 2 * n;
+    }
+    if (p.smem_pool) {
+      for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) smd[base + i] = p.pool[i];
+      L.pool = smd + base;
+    }
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  char *wsm = reinterpret_cast<char *>(smraw) + (size_t)wib * PP::kWarpBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(wsm + NSI * PP::kInBytes + 2 * PP::kOutBytes);
+  if (lane == 0) {
+    for (int s = 0; s < NSI; ++s) gs_mbar_init(&full[s], 1);
+    gs_mbar_init_fence();
+  }
+  gs_fence_proxy_async();
+  __syncthreads();
+  const long long warp = (long long)blockIdx.x * nw + wib;
+  if (warp >= p.nwarps) return;
+  bool fast_allowed = p.allow_fast != 0;
+  L.rt = gs_rcp_invariant(p.time, fast_allowed);
+  GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
+  L.inv_time = 1.0 / p.time;
+  if (MODE == GS_SPLINE_SINGLE) L.z = gs_spline_view(L.pool, p.single_off);
+  unsigned flags = 0;
+  const size_t block_elems = (size_t)n * GS_LB;
+  double2 *Sblk = p.scratch + (size_t)warp * block_elems;
+  uint32_t seq = 0, oseq = 0;
+  const int NC = (n + CH - 1) / CH;
+
+  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+    const long long line = blk * GS_LB + lane;
+    const bool valid = line < p.nlines;  // padding lanes compute on the padding lines (kept finite)
+    const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
+    double *Gblk = p.grid + (size_t)blk * block_elems;
+    double *Pblk = p.predict + (size_t)blk * block_elems;
+    const double firstT = p.leftT[bcl], lastT = p.rightT[bcl];
+    bool try_fast = fast_allowed;
+    for (int step = 0; step < p.nsteps; ++step) {
+      double delta, lambda;
+      unsigned lf = 0;
+      bool ok = false;
+      if (try_fast) {
+        ok = forward_block_tma<MODE, true, CH, NSI>(L, wsm, full, seq, oseq, Gblk, Pblk, Sblk, lane, firstT, lastT,
+                                                    delta, lambda, lf);
+        ok = __all_sync(0xffffffffu, ok);
+      }
+      if (!ok) {
+        // some lane met operands outside the proven range of the shared-reciprocal division (zeros,
+        // denormals, Inf/NaN, absurd magnitudes): the warp redoes the block with plain IEEE division
+        try_fast = false;
+        lf = 0;
+        if (lane == 0) gs_bulk_wait<0>();
+        __syncwarp();
+        forward_block_tma<MODE, false, CH, NSI>(L, wsm, full, seq, oseq, Gblk, Pblk, Sblk, lane, firstT, lastT,
+                                                delta, lambda, lf);
+      }
+      // scratch stores must be complete before the backward pass streams them back
+      if (lane == 0) gs_bulk_wait<0>();
+      __syncwarp();
 
       // ---- backward (backwardPassion :345-365) fused with OneDGrid.step's predictor and
       // grid <- result (A/OneDGrid.scala:29-33) ----
+      auto issue = [&](int c, uint32_t sq) {
+        int len = min(CH, n - c * CH);
+        int lenS = (c == NC - 1) ? len - 1 : len;
+        int s = sq % NSI;
+        char *st = wsm + s * PP::kInBytes;
+        gs_mbar_expect_tx(&full[s], (uint32_t)lenS * 512u + (uint32_t)len * 256u);
+        if (lenS > 0) gs_bulk_g2s(st, Sblk + (size_t)c * CH * GS_LB, (uint32_t)lenS * 512u, &full[s]);
+        gs_bulk_g2s(st + CH * 512, Gblk + (size_t)c * CH * GS_LB, (uint32_t)len * 256u, &full[s]);
+      };
+      const uint32_t seq0 = seq;
+      if (lane == 0) {
+        for (int k = 0; k < min(NSI, NC); ++k) issue(NC - 1 - k, seq0 + k);
+      }
       double u = 0.0;
-      {
-        u = delta * u + lambda;
-        double g = Gp[(long long)i * pitch];
-        Pp[(long long)i * pitch] = u + gs_div(u - g, r3);   // arraygrid.aVal :85-87
-        Gp[(long long)i * pitch] = u;
+      for (int k = 0; k < NC; ++k) {
+        const int c = NC - 1 - k;
+        const uint32_t sq = seq0 + k;
+        const int s = sq % NSI;
+        gs_mbar_wait(&full[s], (sq / NSI) & 1u);
+        const char *st = wsm + s * PP::kInBytes;
+        const double2 *sS = reinterpret_cast<const double2 *>(st) + lane;
+        const double *sG = reinterpret_cast<const double *>(st + CH * 512) + lane;
+        char *ob = wsm + NSI * PP::kInBytes + (oseq & 1u) * PP::kOutBytes;
+        double *oG = reinterpret_cast<double *>(ob) + lane;
+        double *oP = oG + CH * GS_LB;
+        if (oseq >= 2) {
+          if (lane == 0) gs_bulk_wait_read<1>();
+          __syncwarp();
+        }
+        const int len = min(CH, n - c * CH);
+#pragma unroll
+        for (int m = CH - 1; m >= 0; --m) {
+          if (m < len) {
+            double dl = delta, ll = lambda;
+            if (c * CH + m != n - 1) {
+              double2 v = sS[m * GS_LB];
+              dl = v.x;
+              ll = v.y;
+            }
+            u = dl * u + ll;
+            double g = sG[m * GS_LB];
+            double d = u - g;
+            bool okd = true;
+            double q = gs_div<true>(d, r3, okd);
+            if (!(okd && fast_allowed)) q = d / 3.0;
+            oG[m * GS_LB] = u;
+            oP[m * GS_LB] = u + q;   // arraygrid.aVal :85-87
+          }
+        }
+        gs_fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          gs_bulk_s2g(Gblk + (size_t)c * CH * GS_LB, ob, (uint32_t)len * 256u);
+          gs_bulk_s2g(Pblk + (size_t)c * CH * GS_LB, ob + CH * 256, (uint32_t)len * 256u);
+          gs_bulk_commit();
+          if (k + NSI < NC) issue(c - NSI, sq + NSI);
+        }
+        ++oseq;
       }
-#pragma unroll 4
-      for (i = n - 2; i >= 0; --i) {
-        double2 dl = sc[(long long)i * G];
-        u = dl.x * u + dl.y;
-        double g = Gp[(long long)i * pitch];
-        Pp[(long long)i * pitch] = u + gs_div(u - g, r3);
-        Gp[(long long)i * pitch] = u;
-      }
-      if (!(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
+      seq = seq0 + NC;
+      // grid'/predict' must be complete before the next step (or another kernel) streams them back
+      if (lane == 0) gs_bulk_wait<0>();
+      __syncwarp();
+      if (!(fabs(u) <= 1.7976931348623157e308)) lf |= GS_FLAG_NONFINITE;
+      if (valid) flags |= lf;
     }
   }
   gs_raise(p.status, flags);
@@ -150,7 +485,11 @@ __global__ void __launch_bounds__(256) k_step1d(Step1dParams p) {
 // ---------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------
-// src line-major [L][n]  ->  dst[node * pitch + line0 + l]
+// device index of (line, node) in the blocked layout [line / 32][node][line % 32]
+__host__ __device__ inline size_t blocked_index(long long line, int node, int n) {
+  return (size_t)(line / GS_LB) * ((size_t)n * GS_LB) + (size_t)node * GS_LB + (size_t)(line % GS_LB);
+}
+// src line-major [L][n] (lines line0 .. line0+L)  ->  blocked dst
 __global__ void k_lines_to_interleaved(const double *src, double *dst, int L, int n, long long pitch,
                                        long long line0) {
   __shared__ double tile[32][33];
@@ -163,7 +502,7 @@ __global__ void k_lines_to_interleaved(const double *src, double *dst, int L, in
   int l = blockIdx.y * 32 + threadIdx.x;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int nd = blockIdx.x * 32 + j;
-    if (l < L && nd < n) dst[(long long)nd * pitch + line0 + l] = tile[threadIdx.x][j];
+    if (l < L && nd < n) dst[blocked_index(line0 + l, nd, n)] = tile[threadIdx.x][j];
   }
 }
 __global__ void k_interleaved_to_lines(const double *src, double *dst, int L, int n, long long pitch,
@@ -172,7 +511,7 @@ __global__ void k_interleaved_to_lines(const double *src, double *dst, int L, in
   int l = blockIdx.y * 32 + threadIdx.x;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int nd = blockIdx.x * 32 + j;
-    if (l < L && nd < n) tile[j][threadIdx.x] = src[(long long)nd * pitch + line0 + l];
+    if (l < L && nd < n) tile[j][threadIdx.x] = src[blocked_index(line0 + l, nd, n)];
   }
   __syncthreads();
   int node = blockIdx.x * 32 + threadIdx.x;
@@ -180,6 +519,19 @@ __global__ void k_interleaved_to_lines(const double *src, double *dst, int L, in
     int ll = blockIdx.y * 32 + j;
     if (ll < L && node < n) dst[(long long)ll * n + node] = tile[threadIdx.x][j];
   }
+}
+// src node-major slab [n][L] (lines line0 .. line0+L)  <->  blocked
+__global__ void k_nodemajor_to_blocked(const double *src, double *dst, int L, int n, long long line0) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)L * n) return;
+  int node = (int)(idx / L), l = (int)(idx % L);
+  dst[blocked_index(line0 + l, node, n)] = src[idx];
+}
+__global__ void k_blocked_to_nodemajor(const double *src, double *dst, int L, int n, long long line0) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)L * n) return;
+  int node = (int)(idx / L), l = (int)(idx % L);
+  dst[idx] = src[blocked_index(line0 + l, node, n)];
 }
 __global__ void k_fill(double *a, long long count, double v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,7 +577,7 @@ extern "C" int gs_grid1d_create(gs_ctx *ctx, int64_t nlines, int n, int dir, dou
   g->nlines = nlines;
   g->n = n;
   g->dir = dir;
-  g->pitch = (nlines + 15) / 16 * 16;
+  g->pitch = (nlines + GS_LB - 1) / GS_LB * GS_LB;  // padded line count (whole blocks)
   g->spline_mode = spline_mode;
   g->all_const = true;
   for (int i = 0; i < nids; ++i) g->all_const = g->all_const && spline_is_const(ctx, spline_ids[i]);
@@ -301,28 +653,34 @@ static double *array_of(gs_grid1d *g, int which) {
 
 static const size_t kStageBytes = (size_t)128 << 20;
 
+static long long chunk_lines(const gs_grid1d *g) {
+  size_t line_bytes = (size_t)g->n * sizeof(double);
+  long long chunk = (long long)std::max<size_t>(GS_LB, kStageBytes / line_bytes / GS_LB * GS_LB);
+  return std::min<long long>(chunk, g->pitch);
+}
+
 extern "C" int gs_grid1d_upload(gs_grid1d *g, int which, int layout, const double *host) {
   GS_REQUIRE(g && host, "NULL argument");
   GS_REQUIRE(which == GS_GRID || which == GS_PREDICT || which == GS_RESULT, "unknown array");
+  GS_REQUIRE(layout == GS_LINE_MAJOR || layout == GS_INTERLEAVED, "unknown layout");
   gs_ctx *ctx = g->ctx;
   GS_TRY(gs_ctx_use(ctx));
   double *dst = array_of(g, which);
-  if (layout == GS_INTERLEAVED) {
-    GS_CUDA(cudaMemcpy2DAsync(dst, (size_t)g->pitch * sizeof(double), host, (size_t)g->nlines * sizeof(double),
-                              (size_t)g->nlines * sizeof(double), (size_t)g->n, cudaMemcpyHostToDevice, ctx->stream));
-    GS_CUDA(cudaStreamSynchronize(ctx->stream));
-    return GS_OK;
-  }
-  GS_REQUIRE(layout == GS_LINE_MAJOR, "unknown layout");
   size_t line_bytes = (size_t)g->n * sizeof(double);
-  long long chunk = (long long)std::max<size_t>(32, kStageBytes / line_bytes / 32 * 32);
-  chunk = std::min<long long>(chunk, (g->nlines + 31) / 32 * 32);
+  long long chunk = chunk_lines(g);
   GS_TRY(gs_ctx_stage(ctx, (size_t)chunk * line_bytes));
   for (long long l0 = 0; l0 < g->nlines; l0 += chunk) {
     int L = (int)std::min<long long>(chunk, g->nlines - l0);
-    GS_CUDA(cudaMemcpyAsync(ctx->stage, host + (size_t)l0 * g->n, (size_t)L * line_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    dim3 blk(32, 8), grd((g->n + 31) / 32, (L + 31) / 32);
-    k_lines_to_interleaved<<<grd, blk, 0, ctx->stream>>>(ctx->stage, dst, L, g->n, g->pitch, l0);
+    if (layout == GS_LINE_MAJOR) {
+      GS_CUDA(cudaMemcpyAsync(ctx->stage, host + (size_t)l0 * g->n, (size_t)L * line_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      dim3 blk(32, 8), grd((g->n + 31) / 32, (L + 31) / 32);
+      k_lines_to_interleaved<<<grd, blk, 0, ctx->stream>>>(ctx->stage, dst, L, g->n, g->pitch, l0);
+    } else {
+      GS_CUDA(cudaMemcpy2DAsync(ctx->stage, (size_t)L * sizeof(double), host + l0, (size_t)g->nlines * sizeof(double),
+                                (size_t)L * sizeof(double), (size_t)g->n, cudaMemcpyHostToDevice, ctx->stream));
+      long long cnt = (long long)L * g->n;
+      k_nodemajor_to_blocked<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage, dst, L, g->n, l0);
+    }
     ctx->launches++;
     GS_CUDA(cudaGetLastError());
   }
@@ -333,27 +691,29 @@ extern "C" int gs_grid1d_upload(gs_grid1d *g, int which, int layout, const doubl
 extern "C" int gs_grid1d_download(gs_grid1d *g, int which, int layout, double *host) {
   GS_REQUIRE(g && host, "NULL argument");
   GS_REQUIRE(which == GS_GRID || which == GS_PREDICT || which == GS_RESULT, "unknown array");
+  GS_REQUIRE(layout == GS_LINE_MAJOR || layout == GS_INTERLEAVED, "unknown layout");
   gs_ctx *ctx = g->ctx;
   GS_TRY(gs_ctx_use(ctx));
   const double *src = array_of(g, which);
-  if (layout == GS_INTERLEAVED) {
-    GS_CUDA(cudaMemcpy2DAsync(host, (size_t)g->nlines * sizeof(double), src, (size_t)g->pitch * sizeof(double),
-                              (size_t)g->nlines * sizeof(double), (size_t)g->n, cudaMemcpyDeviceToHost, ctx->stream));
-    GS_CUDA(cudaStreamSynchronize(ctx->stream));
-    return GS_OK;
-  }
-  GS_REQUIRE(layout == GS_LINE_MAJOR, "unknown layout");
   size_t line_bytes = (size_t)g->n * sizeof(double);
-  long long chunk = (long long)std::max<size_t>(32, kStageBytes / line_bytes / 32 * 32);
-  chunk = std::min<long long>(chunk, (g->nlines + 31) / 32 * 32);
+  long long chunk = chunk_lines(g);
   GS_TRY(gs_ctx_stage(ctx, (size_t)chunk * line_bytes));
   for (long long l0 = 0; l0 < g->nlines; l0 += chunk) {
     int L = (int)std::min<long long>(chunk, g->nlines - l0);
-    dim3 blk(32, 8), grd((g->n + 31) / 32, (L + 31) / 32);
-    k_interleaved_to_lines<<<grd, blk, 0, ctx->stream>>>(src, ctx->stage, L, g->n, g->pitch, l0);
-    ctx->launches++;
-    GS_CUDA(cudaGetLastError());
-    GS_CUDA(cudaMemcpyAsync(host + (size_t)l0 * g->n, ctx->stage, (size_t)L * line_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (layout == GS_LINE_MAJOR) {
+      dim3 blk(32, 8), grd((g->n + 31) / 32, (L + 31) / 32);
+      k_interleaved_to_lines<<<grd, blk, 0, ctx->stream>>>(src, ctx->stage, L, g->n, g->pitch, l0);
+      ctx->launches++;
+      GS_CUDA(cudaGetLastError());
+      GS_CUDA(cudaMemcpyAsync(host + (size_t)l0 * g->n, ctx->stage, (size_t)L * line_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      long long cnt = (long long)L * g->n;
+      k_blocked_to_nodemajor<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->stage, L, g->n, l0);
+      ctx->launches++;
+      GS_CUDA(cudaGetLastError());
+      GS_CUDA(cudaMemcpy2DAsync(host + l0, (size_t)g->nlines * sizeof(double), ctx->stage, (size_t)L * sizeof(double),
+                                (size_t)L * sizeof(double), (size_t)g->n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     GS_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return GS_OK;
@@ -398,9 +758,10 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   GS_TRY(gs_ctx_sync_pool(ctx));
 
   int block = (int)std::max<int64_t>(32, std::min<int64_t>(256, ctx->opt_block_1d / 32 * 32));
-  long long want = (long long)ctx->sm_count * std::max<int64_t>(block, ctx->opt_threads_per_sm_1d);
-  long long G = std::min<long long>((g->nlines + block - 1) / block * block, want / block * block);
-  size_t need = (size_t)G * (size_t)(g->n - 1);
+  long long nblocks = g->pitch / GS_LB;
+  long long want_warps = (long long)ctx->sm_count * std::max<int64_t>(32, ctx->opt_threads_per_sm_1d) / 32;
+  long long nwarps = std::min<long long>(nblocks, want_warps);
+  size_t need = (size_t)nwarps * (size_t)g->n * GS_LB;
   if (g->scratch_elems < need) {
     GS_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(g->scratch);
@@ -412,8 +773,9 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   Step1dParams p;
   p.n = g->n;
   p.nlines = g->nlines;
-  p.pitch = g->pitch;
-  p.G = G;
+  p.nblocks = nblocks;
+  p.nwarps = nwarps;
+  p.allow_fast = ctx->opt_native_div ? 0 : 1;
   p.grid = g->grid;
   p.predict = g->predict;
   p.scratch = g->scratch;
@@ -429,14 +791,34 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   p.nsteps = nsteps;
   p.status = g->status;
   size_t smem = 0;
-  const size_t budget = 48 * 1024;
+  const size_t budget = 40 * 1024;
   p.smem_predef = (2 * (size_t)g->n * sizeof(double) <= budget / 2) ? 1 : 0;
   if (p.smem_predef) smem += 2 * (size_t)g->n * sizeof(double);
   p.smem_pool = (smem + (size_t)p.pool_len * sizeof(double) <= budget) ? 1 : 0;
   if (p.smem_pool) smem += (size_t)p.pool_len * sizeof(double);
-  int blocks = (int)(G / block);
-  if (g->spline_mode == GS_SPLINE_SINGLE) k_step1d<GS_SPLINE_SINGLE><<<blocks, block, smem, ctx->stream>>>(p);
-  else k_step1d<GS_SPLINE_PER_NODE><<<blocks, block, smem, ctx->stream>>>(p);
+  if (ctx->opt_pipeline) {
+    // persistent warps, each with its own bulk-copy ring
+    int pblock = (int)std::max<int64_t>(32, std::min<int64_t>(128, ctx->opt_block_1d / 32 * 32));
+    int blocks = (int)((nwarps + pblock / 32 - 1) / (pblock / 32));
+    const bool single = g->spline_mode == GS_SPLINE_SINGLE;
+#define GS_LAUNCH_PIPE(CH, NSI)                                                                             \
+  do {                                                                                                      \
+    size_t psmem = smem + (size_t)(pblock / 32) * Pipe1d<CH, NSI>::kWarpBytes;                              \
+    auto kern = single ? k_step1d_tma<GS_SPLINE_SINGLE, CH, NSI> : k_step1d_tma<GS_SPLINE_PER_NODE, CH, NSI>; \
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));            \
+    kern<<<blocks, pblock, psmem, ctx->stream>>>(p);                                                         \
+  } while (0)
+    switch (ctx->opt_pipe_cfg) {
+      case 1: GS_LAUNCH_PIPE(4, 6); break;
+      case 2: GS_LAUNCH_PIPE(8, 4); break;
+      default: GS_LAUNCH_PIPE(4, 3); break;
+    }
+#undef GS_LAUNCH_PIPE
+  } else {
+    int blocks = (int)((nwarps * 32 + block - 1) / block);
+    if (g->spline_mode == GS_SPLINE_SINGLE) k_step1d<GS_SPLINE_SINGLE><<<blocks, block, smem, ctx->stream>>>(p);
+    else k_step1d<GS_SPLINE_PER_NODE><<<blocks, block, smem, ctx->stream>>>(p);
+  }
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
@@ -466,7 +848,7 @@ extern "C" int gs_grid1d_device_ptr(gs_grid1d *g, int which, void **dptr, int64_
   GS_REQUIRE(g && dptr, "NULL argument");
   GS_REQUIRE(which == GS_GRID || which == GS_PREDICT || which == GS_RESULT, "unknown array");
   *dptr = array_of(g, which);
-  if (pitch) *pitch = g->pitch;
+  if (pitch) *pitch = GS_LB;  // lines per block of the [line/32][node][line%32] layout
   return GS_OK;
 }
 extern "C" int gs_grid1d_bytes_per_step(gs_grid1d *g, double *bytes) {

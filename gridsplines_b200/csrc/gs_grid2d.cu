@@ -87,63 +87,69 @@ struct LineState {
 
 struct SweepConsts {
   GsRcp rt;
+  bool fast_allowed;
   double inv_time;
   double firstVol, fC, lastVol, lA;
 };
 
 // Dim.first  A/Dim.scala:28-43
+template <bool FAST>
 GS_DEV void node_first_temp(LineState &st, const SweepConsts &k, double cf0, double cf1, double t1, double t2,
-                            double t3, double t, const GsSpline &z0, const GsSpline &z, unsigned &flags) {
-  double co0 = gs_take_average(z0, t1, t2, flags);
-  double co = gs_take_average(z, t2, t3, flags);
+                            double t3, double t, const GsSpline &z0, const GsSpline &z, unsigned &flags, bool &ok) {
+  double co0 = gs_take_average<FAST>(z0, t1, t2, flags, ok);
+  double co = gs_take_average<FAST>(z, t2, t3, flags, ok);
   double a = cf0 * co0;
   double c = cf1 * co;
-  double vect = gs_div(-t, k.rt) - a * t1;
-  gs_forward_first(-(a + c) - k.inv_time, c, vect, st.delta, st.lambda);
+  double vect = gs_div<FAST>(-t, k.rt, ok) - a * t1;
+  gs_forward_first<FAST>(-(a + c) - k.inv_time, c, vect, st.delta, st.lambda, ok);
   st.carry = co;
 }
 // Dim.firstHeatFlow :46-64
+template <bool FAST>
 GS_DEV void node_first_flow(LineState &st, const SweepConsts &k, double heatFlow, double t2, double t3, double t,
-                            const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags) {
+                            const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags, bool &ok) {
   double cap = gs_ads_apply(capacity, t, flags);
-  double cond = gs_ads_average(conductivity, t2, t3, flags);
-  double vol = gs_div(k.firstVol * cap, k.rt);
+  double cond = gs_ads_average<FAST>(conductivity, t2, t3, flags, ok);
+  double vol = gs_div<FAST>(k.firstVol * cap, k.rt, ok);
   double c = -cond * k.fC;
   double b = vol - c;
   double vect = vol + heatFlow;
-  double tCond = gs_div(cond, gs_rcp(cap));
-  gs_forward_first(b, c, vect, st.delta, st.lambda);
+  double tCond = gs_div<FAST>(cond, gs_rcp<FAST>(cap, ok), ok);
+  gs_forward_first<FAST>(b, c, vect, st.delta, st.lambda, ok);
   st.carry = tCond;
 }
 // Dim.general :67-83
+template <bool FAST>
 GS_DEV void node_general(LineState &st, const SweepConsts &k, double cf0, double cf1, double t2, double t3,
-                         double t, const GsSpline &z, unsigned &flags) {
-  double co = gs_take_average(z, t2, t3, flags);
+                         double t, const GsSpline &z, unsigned &flags, bool &ok) {
+  double co = gs_take_average<FAST>(z, t2, t3, flags, ok);
   double a = cf0 * st.carry;
   double c = cf1 * co;
-  double vect = gs_div(-t, k.rt);
-  gs_forward_unit(a, -(a + c) - k.inv_time, c, vect, st.delta, st.lambda, flags);
+  double vect = gs_div<FAST>(-t, k.rt, ok);
+  gs_forward_unit<FAST>(a, -(a + c) - k.inv_time, c, vect, st.delta, st.lambda, flags, ok);
   st.carry = co;
 }
 // Dim.last :86-103
+template <bool FAST>
 GS_DEV void node_last_temp(LineState &st, const SweepConsts &k, double cf0, double cf1, double t2, double t3,
-                           double t, const GsSpline &z, unsigned &flags) {
-  double co = gs_take_average(z, t2, t3, flags);
+                           double t, const GsSpline &z, unsigned &flags, bool &ok) {
+  double co = gs_take_average<FAST>(z, t2, t3, flags, ok);
   double a = cf0 * st.carry;
   double c = cf1 * co;
-  double vect = gs_div(-t, k.rt) - c * t3;
-  gs_forward_last(a, -(a + c) - k.inv_time, vect, st.delta, st.lambda);
+  double vect = gs_div<FAST>(-t, k.rt, ok) - c * t3;
+  gs_forward_last<FAST>(a, -(a + c) - k.inv_time, vect, st.delta, st.lambda, ok);
 }
 // Dim.lastHeatFlow :106-128
+template <bool FAST>
 GS_DEV void node_last_flow(LineState &st, const SweepConsts &k, double heatFlow, double t1, double t2, double t,
-                           const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags) {
+                           const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags, bool &ok) {
   double cap = gs_ads_apply(capacity, t, flags);
-  double cond = gs_ads_average(conductivity, t1, t2, flags);
-  double vol = gs_div(cap * k.lastVol, k.rt);
+  double cond = gs_ads_average<FAST>(conductivity, t1, t2, flags, ok);
+  double vol = gs_div<FAST>(cap * k.lastVol, k.rt, ok);
   double a = -cond * k.lA;
   double b = vol - a;
   double vect = vol - heatFlow;
-  gs_forward_last(a, b, vect, st.delta, st.lambda);
+  gs_forward_last<FAST>(a, b, vect, st.delta, st.lambda, ok);
 }
 
 // Grid.aVal  A/TwoDGrid.scala:508-512
@@ -178,7 +184,9 @@ __global__ void __launch_bounds__(128) k_ysweep(Sweep2dParams p) {
   double2 *__restrict__ sc = p.scratch + col;
   CoefSel<SINGLE> sel(p.maps, pool, cols);
   SweepConsts k;
-  k.rt = gs_rcp(p.time);
+  k.fast_allowed = true;
+  k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
+  bool ok = true;
   k.inv_time = 1.0 / p.time;
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
@@ -188,11 +196,11 @@ __global__ void __launch_bounds__(128) k_ysweep(Sweep2dParams p) {
   double t2 = P[0], t3 = P[cols], t = R[0];
   if (p.kind_first == GS_TEMP) {
     double t1 = p.bound_first[col];
-    node_first_temp(st, k, p.coefs[0], p.coefs[1], t1, t2, t3, t, sel.get(GS_SEL_APPLY, col, -1),
-                    sel.get(GS_SEL_APPLY, col, row), flags);
+    node_first_temp<false>(st, k, p.coefs[0], p.coefs[1], t1, t2, t3, t, sel.get(GS_SEL_APPLY, col, -1),
+                    sel.get(GS_SEL_APPLY, col, row), flags, ok);
   } else {
-    node_first_flow(st, k, p.bound_first[col], t2, t3, t, sel.get(GS_SEL_TEMPCOND, col, row),
-                    sel.get(GS_SEL_CAP, col, row), flags);
+    node_first_flow<false>(st, k, p.bound_first[col], t2, t3, t, sel.get(GS_SEL_TEMPCOND, col, row),
+                    sel.get(GS_SEL_CAP, col, row), flags, ok);
   }
   sc[0] = make_double2(st.delta, st.lambda);
   row = 1;
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(128) k_ysweep(Sweep2dParams p) {
     t2 = t3;
     t3 = P[i + cols];
     t = R[i];
-    node_general(st, k, p.coefs[2 * row], p.coefs[2 * row + 1], t2, t3, t, sel.get(GS_SEL_APPLY, col, row), flags);
+    node_general<false>(st, k, p.coefs[2 * row], p.coefs[2 * row + 1], t2, t3, t, sel.get(GS_SEL_APPLY, col, row), flags, ok);
     sc[i] = make_double2(st.delta, st.lambda);
   }
   {
@@ -211,12 +219,12 @@ __global__ void __launch_bounds__(128) k_ysweep(Sweep2dParams p) {
     t = R[i];
     if (p.kind_last == GS_TEMP) {
       t3 = p.bound_last[col];
-      node_last_temp(st, k, p.coefs[2 * row], p.coefs[2 * row + 1], t2, t3, t, sel.get(GS_SEL_APPLY, col, row), flags);
+      node_last_temp<false>(st, k, p.coefs[2 * row], p.coefs[2 * row + 1], t2, t3, t, sel.get(GS_SEL_APPLY, col, row), flags, ok);
     } else {
       // `val t1 = grid(i - 1)`: the left neighbour in the same row (sic, :241)
       double t1 = FUSE ? p.low_snap[col] : p.predict[i + col - 1];
-      node_last_flow(st, k, p.bound_last[col], t1, t3, t, sel.get(GS_SEL_TEMPCOND, col, row),
-                     sel.get(GS_SEL_CAP, col, row), flags);
+      node_last_flow<false>(st, k, p.bound_last[col], t1, t3, t, sel.get(GS_SEL_TEMPCOND, col, row),
+                     sel.get(GS_SEL_CAP, col, row), flags, ok);
     }
   }
   // backwardColumn :324-342
@@ -294,7 +302,9 @@ __global__ void __launch_bounds__(32) k_xsweep(Sweep2dParams p) {
 
   CoefSel<SINGLE> sel(p.maps, pool, cols);
   SweepConsts k;
-  k.rt = gs_rcp(p.time);
+  k.fast_allowed = true;
+  k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
+  bool ok = true;
   k.inv_time = 1.0 / p.time;
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
@@ -325,15 +335,15 @@ __global__ void __launch_bounds__(32) k_xsweep(Sweep2dParams p) {
           int col = cnext - 1;
           if (col == 0) {
             if (p.kind_first == GS_TEMP) {
-              node_first_temp(st, k, p.coefs[0], p.coefs[1], p.bound_first[row], pcur, pnext, gcur,
-                              sel.get(GS_SEL_APPLY, -1, row), sel.get(GS_SEL_APPLY, 0, row), flags);
+              node_first_temp<false>(st, k, p.coefs[0], p.coefs[1], p.bound_first[row], pcur, pnext, gcur,
+                              sel.get(GS_SEL_APPLY, -1, row), sel.get(GS_SEL_APPLY, 0, row), flags, ok);
             } else {
-              node_first_flow(st, k, p.bound_first[row], pcur, pnext, gcur, sel.get(GS_SEL_THERM, 0, row),
-                              sel.get(GS_SEL_CAP, 0, row), flags);
+              node_first_flow<false>(st, k, p.bound_first[row], pcur, pnext, gcur, sel.get(GS_SEL_THERM, 0, row),
+                              sel.get(GS_SEL_CAP, 0, row), flags, ok);
             }
           } else {
-            node_general(st, k, p.coefs[2 * col], p.coefs[2 * col + 1], pcur, pnext, gcur,
-                         sel.get(GS_SEL_APPLY, col, row), flags);
+            node_general<false>(st, k, p.coefs[2 * col], p.coefs[2 * col + 1], pcur, pnext, gcur,
+                         sel.get(GS_SEL_APPLY, col, row), flags, ok);
           }
           sc[(size_t)col * rows] = make_double2(st.delta, st.lambda);
         }
@@ -346,12 +356,12 @@ __global__ void __launch_bounds__(32) k_xsweep(Sweep2dParams p) {
   if (active) {
     int col = cols - 1;
     if (p.kind_last == GS_TEMP) {
-      node_last_temp(st, k, p.coefs[2 * col], p.coefs[2 * col + 1], pcur, p.bound_last[row], gcur,
-                     sel.get(GS_SEL_APPLY, col, row), flags);
+      node_last_temp<false>(st, k, p.coefs[2 * col], p.coefs[2 * col + 1], pcur, p.bound_last[row], gcur,
+                     sel.get(GS_SEL_APPLY, col, row), flags, ok);
     } else {
       // (t1, t2) = (predict[last], stale t3 = predict[last])  :172-187
-      node_last_flow(st, k, p.bound_last[row], pcur, pcur, gcur, sel.get(GS_SEL_TEMPCOND, col, row),
-                     sel.get(GS_SEL_CAP, col, row), flags);
+      node_last_flow<false>(st, k, p.bound_last[row], pcur, pcur, gcur, sel.get(GS_SEL_TEMPCOND, col, row),
+                     sel.get(GS_SEL_CAP, col, row), flags, ok);
     }
   }
 

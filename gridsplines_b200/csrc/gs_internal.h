@@ -56,6 +56,8 @@ struct gs_ctx {
   int64_t opt_native_div = 0;
   int64_t opt_const_hoist = 1;
   int64_t opt_smem_nodes = -1;
+  int64_t opt_pipeline = 1;
+  int64_t opt_pipe_cfg = 0;
 };
 
 int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice

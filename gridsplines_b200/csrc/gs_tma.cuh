@@ -1,0 +1,55 @@
+// gs_tma.cuh -- thin wrappers over the sm_100a bulk-copy engine (TMA, cp.async.bulk) and mbarriers.
+// Per-warp streaming pipelines in gs_grid1d.cu / gs_grid2d.cu are built from these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GS_TMA_DEV __device__ __forceinline__
+
+GS_TMA_DEV uint32_t gs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+GS_TMA_DEV void gs_mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(count) : "memory");
+}
+GS_TMA_DEV void gs_mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+GS_TMA_DEV void gs_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+GS_TMA_DEV void gs_mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t addr = gs_smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, completion signalled on an mbarrier (bytes: multiple of 16, both addresses 16 B aligned)
+GS_TMA_DEV void gs_bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   gs_smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(gs_smem_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by bulk async-groups
+GS_TMA_DEV void gs_bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(gs_smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+GS_TMA_DEV void gs_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N groups still have their SOURCE (shared memory) unread
+template <int N>
+GS_TMA_DEV void gs_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// wait until at most N groups are incomplete (writes performed)
+template <int N>
+GS_TMA_DEV void gs_bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// orders this thread's generic-proxy accesses before subsequent async-proxy (bulk copy) accesses
+GS_TMA_DEV void gs_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// same, restricted to shared memory (what a bulk store's source needs)
+GS_TMA_DEV void gs_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

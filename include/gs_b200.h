@@ -65,7 +65,7 @@ enum { GS_MAP_SINGLE = 0, GS_MAP_PER_ROW = 1, GS_MAP_PER_COL = 2, GS_MAP_DENSE =
 /* arrays of a grid: Grid.grid / predict / result  A/TwoDGrid.scala:461-463, A/OneDGrid.scala:20-22 */
 enum { GS_GRID = 0, GS_PREDICT = 1, GS_RESULT = 2 };
 /* host layouts of a 1-D batch: LINE_MAJOR host[line*n + node] (one OneDGrid.grid after
- * another); INTERLEAVED host[node*nlines + line] (the device-internal order) */
+ * another); INTERLEAVED host[node*nlines + line] (node-major) */
 enum { GS_LINE_MAJOR = 0, GS_INTERLEAVED = 1 };
 /* 1-D spline selection: SINGLE = OneDGrid.apply(leftX, rangeX, rightX, conductivity, sigma)
  * A/OneDGrid.scala:66-79 / passion.iteration overload 2 A/passion/package.scala:97-139;
@@ -141,7 +141,7 @@ int gs_grid1d_step(gs_grid1d *g, double time, int nsteps);
 int gs_grid1d_set_solver(gs_grid1d *g, int solver);
 int gs_grid1d_status(gs_grid1d *g, uint32_t *flags);
 int gs_grid1d_clear_status(gs_grid1d *g);
-/* raw device pointer + element pitch of the interleaved array (zero-copy hosts, multi-GPU glue) */
+/* raw device pointer of the blocked array a[line / B][node][line % B]; *pitch receives B (32) */
 int gs_grid1d_device_ptr(gs_grid1d *g, int which, void **dptr, int64_t *pitch);
 /* algorithmic HBM bytes one step moves (32 B per node) */
 int gs_grid1d_bytes_per_step(gs_grid1d *g, double *bytes);
