@@ -50,7 +50,7 @@ struct gs_ctx {
   double *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  int64_t opt_threads_per_sm_1d = 512;
+  int64_t opt_threads_per_sm_1d = 0;  // 0 = per-path default
   int64_t opt_block_1d = 128;
   int64_t opt_block_y = 128;
   int64_t opt_native_div = 0;
@@ -79,6 +79,9 @@ struct gs_grid1d {
   bool bc_set = false;
   double2 *scratch = nullptr;
   size_t scratch_elems = 0;
+  double *hoist_table = nullptr;  // K2h coefficients for hoist_time
+  bool hoist_valid = false;
+  double hoist_time = 0.0;
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };

@@ -53,3 +53,27 @@ GS_TMA_DEV void gs_bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"
 GS_TMA_DEV void gs_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // same, restricted to shared memory (what a bulk store's source needs)
 GS_TMA_DEV void gs_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// L2 eviction-priority policies for bulk copies
+GS_TMA_DEV uint64_t gs_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+GS_TMA_DEV uint64_t gs_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+GS_TMA_DEV void gs_bulk_g2s_hint(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          gs_smem_u32(sdst)),
+      "l"(gsrc), "r"(bytes), "r"(gs_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+GS_TMA_DEV void gs_bulk_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(gs_smem_u32(ssrc)), "r"(bytes), "l"(policy)
+               : "memory");
+}

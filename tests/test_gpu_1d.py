@@ -45,18 +45,75 @@ def test_batch_vs_golden(gs, name, args):
         assert_bit_equal(got[k], want[k], f"{name}.{k}")
 
 
-@pytest.mark.parametrize("nlines,n", [(1, 2), (3, 3), (33, 5), (1000, 256), (4099, 33), (257, 1024)])
+@pytest.fixture
+def options(ctx):
+    """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
+    defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0}
+
+    def set_(**kw):
+        for k, v in kw.items():
+            ctx.set_option(k, v)
+
+    yield set_
+    for k, v in defaults.items():
+        ctx.set_option(k, v)
+
+
+# every code path of K2: hoisted coefficients (K2h), the general TMA pipeline, the direct-load kernel,
+# plain IEEE division instead of the shared-reciprocal one, other ring shapes
+PATHS = {
+    "default": {},
+    "general": {"const_hoist": 0},
+    "direct": {"const_hoist": 0, "pipeline": 0},
+    "native_div": {"native_div": 1},
+    "general_native_div": {"const_hoist": 0, "native_div": 1},
+    "ring1": {"pipe_cfg": 1},
+    "general_ring2": {"const_hoist": 0, "pipe_cfg": 2},
+    "few_warps": {"threads_per_sm_1d": 32},
+}
+
+
+@pytest.mark.parametrize("nlines,n", [(1, 2), (3, 3), (33, 5), (1000, 256), (4099, 33), (257, 1024), (40, 4099)])
 @pytest.mark.parametrize("spline", ["const", "hermite", "lines"])
-def test_batch_vs_oracle(O, gs, nlines, n, spline):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_batch_vs_oracle(O, gs, options, nlines, n, spline, path):
+    options(**PATHS[path])
     kw = dict(nlines=nlines, n=n, steps=3, spline=spline, random_grid=True)
     got, want = cases.run_batch(gs, **kw), cases.run_batch(O, oracle=True, **kw)
     for k in ("grid", "predict"):
-        assert_bit_equal(got[k], want[k], f"{spline} {nlines}x{n} {k}")
+        assert_bit_equal(got[k], want[k], f"{path} {spline} {nlines}x{n} {k}")
+
+
+def test_zero_and_tiny_values_take_the_ieee_division_path(O, gs):
+    """Zeros / denormal-range values are outside the proven range of the shared-reciprocal division; the warp
+    redoes the block with plain division.  Results stay bit-exact."""
+    nlines, n = 70, 64
+    s = cases.batch_setup(nlines, n)
+    grid0 = np.zeros((nlines, n))
+    grid0[::3, ::5] = 1e-300
+    grid0[1::7] = np.random.default_rng(3).uniform(0.0, 30.0, n)
+    for const in (True, False):
+        spl = (lambda m: m.Spline.const(1e-6)) if const else (
+            lambda m: m.Spline.lines([(-20.0 + 25.0 * i, 1e-6 * (1.0 + 0.3 * i)) for i in range(5)]))
+        g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], spl(gs), 1.0, nlines=nlines)
+        g.upload(gs.GRID, grid0)
+        g.fill(gs.PREDICT, 0.0)
+        lt, rt = np.zeros(nlines), np.zeros(nlines)
+        lt[::2] = 5.0
+        g.step(900.0, lt, rt, nsteps=3)
+        og, op = grid0.copy(), np.zeros((nlines, n))
+        O.batch1d_step(0, s["leftX"], s["rangeX"], s["rightX"], spl(O), 1.0, og, op, lt, rt, 900.0, nsteps=3)
+        assert_bit_equal(g.download(gs.GRID), og, "zeros grid")
+        assert_bit_equal(g.download(gs.PREDICT), op, "zeros predict")
 
 
 @pytest.mark.parametrize("direction", [0, 1])
 def test_per_node_spline_pairs(O, gs, direction):
     """passion.iteration overload 1: conductivities(z)(0) != conductivities(z)(1)."""
+    kwc = dict(nlines=37, n=40, steps=3, spline="const", random_grid=True, per_node=True, direction=direction)
+    got, want = cases.run_batch(gs, **kwc), cases.run_batch(O, oracle=True, **kwc)  # all-const pairs: K2h
+    for k in ("grid", "predict"):
+        assert_bit_equal(got[k], want[k], "const pairs " + k)
     kw = dict(nlines=5, n=40, steps=3, spline="hermite", random_grid=True, per_node=True, direction=direction)
     got, want = cases.run_batch(gs, **kw), cases.run_batch(O, oracle=True, **kw)
     for k in ("grid", "predict"):
