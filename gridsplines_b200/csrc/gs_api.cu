@@ -100,6 +100,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "smem_nodes")) ctx->opt_smem_nodes = value;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = value;
   else if (!strcmp(name, "pipe_cfg")) ctx->opt_pipe_cfg = value;
+  else if (!strcmp(name, "seg_len")) ctx->opt_seg_len = value;
   else {
     gs_set_error("unknown option '%s'", name);
     return GS_ERR_BAD_ARG;

@@ -394,6 +394,377 @@ __global__ void __launch_bounds__(32) k_xsweep(Sweep2dParams p) {
 }
 
 // ---------------------------------------------------------------------------------
+// GS_SOLVER_PARTITIONED: a line is cut into segments of m nodes solved concurrently.
+//
+// The serial Thomas chain costs ~140 clk per node (tools/microbench), so a 4096^2 sweep with one thread per
+// line is latency-bound at a few percent of the HBM roofline.  Here thread (line, k) owns nodes
+// [s, e] = [k m, k m + m) and the interface values E_k = x_e are found from a reduced system:
+//   A  forward sweep of the segment with the left neighbour value L = x_{s-1} as a parameter:
+//        x_i = delta_i x_{i+1} + lambda_i + omega_i L      (same assembly and recurrences as the reference,
+//        plus omega_i = -(sub_i omega_{i-1}) / Delta_i), and the composed map  x_s = p x_e + q + r L.
+//        Nothing per node is stored: six doubles per segment leave the kernel.
+//   B  one thread per line solves the S x S tridiagonal system for E_k (Thomas):
+//        (1 - delta_e^k r^{k+1}) E_k - delta_e^k p^{k+1} E_{k+1} - omega_e^k E_{k-1} = lambda_e^k + delta_e^k q^{k+1}
+//   C  every segment is now a Dirichlet problem (left value E_{k-1}, own last value E_k): the reference's
+//        forward step with (delta, lambda) kept in shared memory, then the back-substitution
+//        (fused with Grid.update in the y direction; predict' goes to a second buffer because neighbouring
+//        segments still read predict).
+// Operation order differs from the reference's single chain: results agree to rounding (<= 1e-12 relative per
+// field, tests/test_gpu_2d.py), not bit for bit.  HBM traffic: inputs are read by A and again by C.
+// Thread mapping: y sweep lanes <-> adjacent columns (coalesced rows); x sweep lanes <-> adjacent segments of
+// one row (each lane streams its own contiguous 8 m bytes; a warp covers 32 m contiguous columns).
+// ---------------------------------------------------------------------------------
+struct Row4 {
+  double sub, diag, sup, rhs;
+};
+
+struct PartParams {
+  Sweep2dParams sw;
+  int m, S;            // segment length, segments per line
+  double *iface;       // [7][nlines * S]: delta_e, lambda_e, omega_e, p, q, r, E
+  double *predict_alt; // fused y: predict' destination
+};
+
+// Dim.general :67-83 up to the elimination: (sub, diag, sup, rhs) of an interior node
+template <bool FAST>
+GS_DEV Row4 asm_general(const SweepConsts &k, double cf0, double cf1, double face_left, double p0, double p1,
+                        double t, const GsSpline &z, double &face_right, unsigned &flags, bool &ok) {
+  double co = gs_take_average<FAST>(z, p0, p1, flags, ok);
+  Row4 r;
+  r.sub = cf0 * face_left;
+  r.sup = cf1 * co;
+  r.rhs = gs_div<FAST>(-t, k.rt, ok);
+  r.diag = -(r.sub + r.sup) - k.inv_time;
+  face_right = co;
+  return r;
+}
+// Dim.first :28-43
+template <bool FAST>
+GS_DEV Row4 asm_first_temp(const SweepConsts &k, double cf0, double cf1, double t1, double p0, double p1, double t,
+                           const GsSpline &z0, const GsSpline &z, double &face_right, unsigned &flags, bool &ok) {
+  double co0 = gs_take_average<FAST>(z0, t1, p0, flags, ok);
+  double co = gs_take_average<FAST>(z, p0, p1, flags, ok);
+  double a = cf0 * co0;
+  Row4 r;
+  r.sub = 0.0;
+  r.sup = cf1 * co;
+  r.rhs = gs_div<FAST>(-t, k.rt, ok) - a * t1;
+  r.diag = -(a + r.sup) - k.inv_time;
+  face_right = co;
+  return r;
+}
+// Dim.firstHeatFlow :46-64
+template <bool FAST>
+GS_DEV Row4 asm_first_flow(const SweepConsts &k, double heatFlow, double p0, double p1, double t,
+                           const GsSpline &conductivity, const GsSpline &capacity, double &face_right,
+                           unsigned &flags, bool &ok) {
+  double cap = gs_ads_apply(capacity, t, flags);
+  double cond = gs_ads_average<FAST>(conductivity, p0, p1, flags, ok);
+  double vol = gs_div<FAST>(k.firstVol * cap, k.rt, ok);
+  Row4 r;
+  r.sub = 0.0;
+  r.sup = -cond * k.fC;
+  r.diag = vol - r.sup;
+  r.rhs = vol + heatFlow;
+  face_right = gs_div<FAST>(cond, gs_rcp<FAST>(cap, ok), ok);
+  return r;
+}
+// Dim.last :86-103
+template <bool FAST>
+GS_DEV Row4 asm_last_temp(const SweepConsts &k, double cf0, double cf1, double face_left, double p0, double t3,
+                          double t, const GsSpline &z, unsigned &flags, bool &ok) {
+  double co = gs_take_average<FAST>(z, p0, t3, flags, ok);
+  Row4 r;
+  r.sub = cf0 * face_left;
+  double c = cf1 * co;
+  r.sup = 0.0;
+  r.rhs = gs_div<FAST>(-t, k.rt, ok) - c * t3;
+  r.diag = -(r.sub + c) - k.inv_time;
+  return r;
+}
+// Dim.lastHeatFlow :106-128
+template <bool FAST>
+GS_DEV Row4 asm_last_flow(const SweepConsts &k, double heatFlow, double t1, double t2, double t,
+                          const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags, bool &ok) {
+  double cap = gs_ads_apply(capacity, t, flags);
+  double cond = gs_ads_average<FAST>(conductivity, t1, t2, flags, ok);
+  double vol = gs_div<FAST>(cap * k.lastVol, k.rt, ok);
+  Row4 r;
+  r.sub = -cond * k.lA;
+  r.sup = 0.0;
+  r.diag = vol - r.sub;
+  r.rhs = vol - heatFlow;
+  return r;
+}
+
+// one line of the swept direction as seen by a segment thread
+template <bool XDIR>
+struct LineAcc {
+  const Sweep2dParams &p;
+  int line;
+  size_t base, stride;
+  GS_DEV LineAcc(const Sweep2dParams &p_, int line_) : p(p_), line(line_) {
+    base = XDIR ? (size_t)line_ * p_.cols : (size_t)line_;
+    stride = XDIR ? 1 : (size_t)p_.cols;
+  }
+  GS_DEV int n() const { return XDIR ? p.cols : p.rows; }
+  GS_DEV size_t idx(int i) const { return base + (size_t)i * stride; }
+  GS_DEV double pred(int i) const { return p.predict[idx(i)]; }
+  GS_DEV double rhs(int i) const { return p.rhs[idx(i)]; }
+  GS_DEV int col(int i) const { return XDIR ? i : line; }
+  GS_DEV int row(int i) const { return XDIR ? line : i; }
+};
+
+// assembles node i of the line (any position) from the reference's formulas; `face` is the carried face value
+// (Dim's co0), `pm`, `p0` the predict values of nodes i-1 and i (pm unused at i = 0)
+template <bool XDIR, bool SINGLE, bool FAST>
+GS_DEV Row4 asm_node(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, const SweepConsts &k, int i, double p0,
+                     double &pnext, double &face, unsigned &flags, bool &ok) {
+  const Sweep2dParams &p = A.p;
+  const int n = A.n();
+  const double t = A.rhs(i);
+  if (i == 0) {
+    pnext = A.pred(1);
+    if (p.kind_first == GS_TEMP) {
+      return asm_first_temp<FAST>(k, p.coefs[0], p.coefs[1], p.bound_first[A.line], p0, pnext, t,
+                                  XDIR ? sel.get(GS_SEL_APPLY, -1, A.line) : sel.get(GS_SEL_APPLY, A.line, -1),
+                                  sel.get(GS_SEL_APPLY, A.col(0), A.row(0)), face, flags, ok);
+    }
+    // left: thermConductivity (:154); upper: tempConductivity (:212)
+    return asm_first_flow<FAST>(k, p.bound_first[A.line], p0, pnext, t,
+                                sel.get(XDIR ? GS_SEL_THERM : GS_SEL_TEMPCOND, A.col(0), A.row(0)),
+                                sel.get(GS_SEL_CAP, A.col(0), A.row(0)), face, flags, ok);
+  }
+  if (i == n - 1) {
+    if (p.kind_last == GS_TEMP) {
+      return asm_last_temp<FAST>(k, p.coefs[2 * i], p.coefs[2 * i + 1], face, p0, p.bound_last[A.line], t,
+                                 sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), flags, ok);
+    }
+    // right: (t1, t2) = (predict[last], predict[last]) (:172-187); lower: t1 = predict[flat - 1] (:241)
+    double t1 = XDIR ? p0 : (p.low_snap ? p.low_snap[A.line] : p.predict[A.idx(i) - 1]);
+    return asm_last_flow<FAST>(k, p.bound_last[A.line], t1, p0, t, sel.get(GS_SEL_TEMPCOND, A.col(i), A.row(i)),
+                               sel.get(GS_SEL_CAP, A.col(i), A.row(i)), flags, ok);
+  }
+  pnext = A.pred(i + 1);
+  return asm_general<FAST>(k, p.coefs[2 * i], p.coefs[2 * i + 1], face, p0, pnext, t,
+                           sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), face, flags, ok);
+}
+
+// face value between nodes s-1 and s as node s-1 would have carried it (Dim.general's `co`)
+template <bool XDIR, bool SINGLE, bool FAST>
+GS_DEV double face_before(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, const SweepConsts &k, int s, double pm,
+                          double p0, unsigned &flags, bool &ok) {
+  const Sweep2dParams &p = A.p;
+  if (s - 1 == 0 && p.kind_first == GS_FLOW) {
+    // the carry out of a heat-flow first node is cond / cap (Dim.firstHeatFlow :60)
+    double t = A.rhs(0);
+    double cap = gs_ads_apply(sel.get(GS_SEL_CAP, A.col(0), A.row(0)), t, flags);
+    double cond = gs_ads_average<FAST>(sel.get(XDIR ? GS_SEL_THERM : GS_SEL_TEMPCOND, A.col(0), A.row(0)), pm, p0,
+                                       flags, ok);
+    return gs_div<FAST>(cond, gs_rcp<FAST>(cap, ok), ok);
+  }
+  return gs_take_average<FAST>(sel.get(GS_SEL_APPLY, A.col(s - 1), A.row(s - 1)), pm, p0, flags, ok);
+}
+
+GS_DEV void part_ids(bool xdir, int nlines, int S, int &line, int &seg) {
+  if (xdir) {
+    seg = blockIdx.x * blockDim.x + threadIdx.x;
+    line = blockIdx.y;
+  } else {
+    line = blockIdx.x * blockDim.x + threadIdx.x;
+    seg = blockIdx.y;
+  }
+}
+GS_DEV size_t iface_idx(bool xdir, int nlines, int S, int line, int seg) {
+  return xdir ? (size_t)line * S + seg : (size_t)seg * nlines + line;
+}
+
+template <bool XDIR, bool SINGLE, bool FAST>
+GS_DEV bool part_A_body(const PartParams &q, const CoefSel<SINGLE> &sel, const SweepConsts &k, int line, int seg,
+                        double *out6, unsigned &flags) {
+  const Sweep2dParams &p = q.sw;
+  LineAcc<XDIR> A(p, line);
+  const int n = A.n();
+  const int s = seg * q.m, e = min(n, s + q.m) - 1;
+  bool ok = true;
+  double delta = 0.0, lambda = 0.0, omega = 0.0;
+  double P = 1.0, Q = 0.0, R = 0.0;
+  double p0 = A.pred(s), pnext = 0.0, face = 0.0;
+  if (s > 0) face = face_before<XDIR, SINGLE, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
+  for (int i = s; i <= e; ++i) {
+    Row4 r = asm_node<XDIR, SINGLE, FAST>(A, sel, k, i, p0, pnext, face, flags, ok);
+    if (i > s) {  // the map x_s = P x_i + Q + R L gains node i-1's relation
+      Q = Q + P * lambda;
+      R = R + P * omega;
+      P = P * delta;
+    }
+    // assertion of forwardUnit (A/passion/package.scala:279-282): interior nodes of the line only
+    if (i > 0 && i < n - 1 && !(fabs(r.diag) >= fabs(r.sup) + fabs(r.sub))) flags |= GS_FLAG_NOT_DOMINANT;
+    if (i == s) {
+      GsRcp rd = gs_rcp<FAST>(r.diag, ok);
+      delta = gs_div<FAST>(-r.sup, rd, ok);
+      lambda = gs_div<FAST>(r.rhs, rd, ok);
+      omega = (s > 0) ? gs_div<FAST>(-r.sub, rd, ok) : 0.0;
+    } else {
+      double bigDelta = r.diag + r.sub * delta;
+      GsRcp rd = gs_rcp<FAST>(bigDelta, ok);
+      delta = gs_div<FAST>(-r.sup, rd, ok);
+      lambda = gs_div<FAST>(r.rhs - r.sub * lambda, rd, ok);
+      omega = (s > 0) ? gs_div<FAST>(-(r.sub * omega), rd, ok) : 0.0;
+    }
+    p0 = pnext;
+  }
+  out6[0] = delta;   // 0 on the line's last node (sup = 0)
+  out6[1] = lambda;
+  out6[2] = omega;
+  out6[3] = P;
+  out6[4] = Q;
+  out6[5] = R;
+  return ok;
+}
+
+template <bool XDIR, bool SINGLE>
+__global__ void __launch_bounds__(128) k_part_A(PartParams q) {
+  extern __shared__ double sm[];
+  const Sweep2dParams &p = q.sw;
+  const double *pool = stage_pool(p, sm);
+  const int nlines = XDIR ? p.rows : p.cols;
+  int line, seg;
+  part_ids(XDIR, nlines, q.S, line, seg);
+  if (line >= nlines || seg >= q.S) return;
+  CoefSel<SINGLE> sel(p.maps, pool, p.cols);
+  SweepConsts k;
+  k.fast_allowed = true;
+  k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
+  k.inv_time = 1.0 / p.time;
+  k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
+  unsigned flags = 0;
+  double o[6];
+  bool ok = k.fast_allowed && part_A_body<XDIR, SINGLE, true>(q, sel, k, line, seg, o, flags);
+  if (!ok) {
+    flags = 0;
+    part_A_body<XDIR, SINGLE, false>(q, sel, k, line, seg, o, flags);
+  }
+  const size_t N = (size_t)nlines * q.S, id = iface_idx(XDIR, nlines, q.S, line, seg);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) q.iface[j * N + id] = o[j];
+  gs_raise(p.status, flags);
+}
+
+// B: reduced tridiagonal system per line (Thomas); E_k overwrites slot 6, slots 3/4 hold the scratch
+template <bool XDIR>
+__global__ void k_part_B(PartParams q) {
+  const Sweep2dParams &p = q.sw;
+  const int nlines = XDIR ? p.rows : p.cols;
+  const int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= nlines) return;
+  const int S = q.S;
+  const size_t N = (size_t)nlines * S;
+  double *F = q.iface;
+  double cp = 0.0, dp = 0.0;
+  for (int k = 0; k < S; ++k) {
+    size_t id = iface_idx(XDIR, nlines, S, line, k);
+    double de = F[0 * N + id], la = F[1 * N + id], om = F[2 * N + id];
+    double pn = 0.0, qn = 0.0, rn = 0.0;
+    if (k + 1 < S) {
+      size_t idn = iface_idx(XDIR, nlines, S, line, k + 1);
+      pn = F[3 * N + idn];
+      qn = F[4 * N + idn];
+      rn = F[5 * N + idn];
+    }
+    double sub = -om, diag = 1.0 - de * rn, sup = -(de * pn), rhs = la + de * qn;
+    double den = diag - sub * cp;     // k = 0: sub = 0
+    cp = sup / den;
+    dp = (rhs - sub * dp) / den;
+    F[3 * N + id] = cp;               // p, q of segment k are no longer needed (k+1's were just read)
+    F[4 * N + id] = dp;
+  }
+  double x = 0.0;
+  for (int k = S - 1; k >= 0; --k) {
+    size_t id = iface_idx(XDIR, nlines, S, line, k);
+    x = F[4 * N + id] - F[3 * N + id] * x;
+    F[6 * N + id] = x;
+  }
+}
+
+template <bool XDIR, bool SINGLE, bool FAST, bool FUSE>
+GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const SweepConsts &k, int line, int seg,
+                        double2 *sc, int scs, unsigned &flags) {
+  const Sweep2dParams &p = q.sw;
+  LineAcc<XDIR> A(p, line);
+  const int n = A.n();
+  const int nlines = XDIR ? p.rows : p.cols;
+  const int s = seg * q.m, e = min(n, s + q.m) - 1;
+  const size_t N = (size_t)nlines * q.S;
+  const double xe = q.iface[6 * N + iface_idx(XDIR, nlines, q.S, line, seg)];
+  const double L = seg > 0 ? q.iface[6 * N + iface_idx(XDIR, nlines, q.S, line, seg - 1)] : 0.0;
+  bool ok = true;
+  double delta = 0.0, lambda = 0.0;
+  double p0 = A.pred(s), pnext = 0.0, face = 0.0;
+  if (s > 0) face = face_before<XDIR, SINGLE, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
+  for (int i = s; i < e; ++i) {   // node e's value is already known
+    Row4 r = asm_node<XDIR, SINGLE, FAST>(A, sel, k, i, p0, pnext, face, flags, ok);
+    if (i == s) {
+      GsRcp rd = gs_rcp<FAST>(r.diag, ok);
+      delta = gs_div<FAST>(-r.sup, rd, ok);
+      lambda = gs_div<FAST>(s > 0 ? r.rhs - r.sub * L : r.rhs, rd, ok);
+    } else {
+      double bigDelta = r.diag + r.sub * delta;
+      GsRcp rd = gs_rcp<FAST>(bigDelta, ok);
+      delta = gs_div<FAST>(-r.sup, rd, ok);
+      lambda = gs_div<FAST>(r.rhs - r.sub * lambda, rd, ok);
+    }
+    sc[(i - s) * scs] = make_double2(delta, lambda);
+    p0 = pnext;
+  }
+  if (FAST && !ok) return false;
+  double x = xe;
+  for (int i = e; i >= s; --i) {
+    if (i < e) {
+      double2 v = sc[(i - s) * scs];
+      x = v.x * x + v.y;
+    }
+    size_t id = A.idx(i);
+    if (FUSE) {
+      double g = p.grid_io[id];
+      q.predict_alt[id] = aval2d(g, x);
+      p.grid_io[id] = x;
+    } else {
+      p.out[id] = x;
+    }
+  }
+  if (!(fabs(x) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
+  return true;
+}
+
+template <bool XDIR, bool SINGLE, bool FUSE>
+__global__ void __launch_bounds__(128) k_part_C(PartParams q) {
+  extern __shared__ __align__(16) unsigned char smc[];
+  const Sweep2dParams &p = q.sw;
+  double2 *scratch = reinterpret_cast<double2 *>(smc);
+  double *pool_sm = reinterpret_cast<double *>(smc + (size_t)q.m * blockDim.x * sizeof(double2));
+  const double *pool = stage_pool(p, pool_sm);
+  const int nlines = XDIR ? p.rows : p.cols;
+  int line, seg;
+  part_ids(XDIR, nlines, q.S, line, seg);
+  if (line >= nlines || seg >= q.S) return;
+  CoefSel<SINGLE> sel(p.maps, pool, p.cols);
+  SweepConsts k;
+  k.fast_allowed = true;
+  k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
+  k.inv_time = 1.0 / p.time;
+  k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
+  unsigned flags = 0;
+  double2 *sc = scratch + threadIdx.x;
+  bool done = k.fast_allowed && part_C_body<XDIR, SINGLE, true, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
+  if (!done) {
+    flags = 0;
+    part_C_body<XDIR, SINGLE, false, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
+  }
+  gs_raise(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------------
 // small kernels: Grid.update, edges, reductions
 // ---------------------------------------------------------------------------------
 __global__ void k_update2d(double *grid, double *predict, const double *result, long long count) {
@@ -513,6 +884,8 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->grid); cudaFree(g->predict); cudaFree(g->result);
   for (int s = 0; s < 4; ++s) { cudaFree(g->b[s].values); cudaFree(g->map[s]); }
   cudaFree(g->scratch);
+  cudaFree(g->iface);
+  cudaFree(g->predict_alt);
   cudaFree(g->status);
   delete g;
   return GS_OK;
@@ -683,6 +1056,10 @@ static int launch_xsweep(gs_grid2d *g, double time) {
   p.kind_last = g->b[GS_RIGHT].kind;
   size_t smem = 4 * (size_t)XT * XTP * sizeof(double) + (p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0);
   int blocks = (g->rows + XT - 1) / XT;
+  if (smem > 48 * 1024) {
+    GS_CUDA(cudaFuncSetAttribute(k_xsweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GS_CUDA(cudaFuncSetAttribute(k_xsweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (single) k_xsweep<true><<<blocks, 32, smem, ctx->stream>>>(p);
   else k_xsweep<false><<<blocks, 32, smem, ctx->stream>>>(p);
   ctx->launches++;
@@ -733,17 +1110,103 @@ static int launch_ysweep(gs_grid2d *g, double time, bool fuse) {
   return GS_OK;
 }
 
+// ---- partitioned sweeps -------------------------------------------------------------------
+static int seg_len(gs_grid2d *g) { return (int)std::max<int64_t>(2, std::min<int64_t>(64, g->ctx->opt_seg_len)); }
+
+// which solver a direction of n nodes uses
+static bool use_partitioned(gs_grid2d *g, int n) {
+  if (g->solver == GS_SOLVER_THOMAS) return false;
+  int m = seg_len(g);
+  if (g->solver == GS_SOLVER_PARTITIONED) return n >= 2 * m;
+  return n >= 8 * m;  // AUTO: short lines stay on the bit-exact single chain
+}
+
+static int ensure_iface(gs_grid2d *g, size_t doubles) {
+  if (g->iface_len >= doubles) return GS_OK;
+  GS_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  cudaFree(g->iface);
+  g->iface = nullptr;
+  g->iface_len = 0;
+  GS_CUDA(cudaMalloc(&g->iface, doubles * sizeof(double)));
+  g->iface_len = doubles;
+  return GS_OK;
+}
+
+static int launch_part(gs_grid2d *g, double time, bool xdir, bool fuse) {
+  gs_ctx *ctx = g->ctx;
+  GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
+  GS_TRY(gs_ctx_sync_pool(ctx));
+  PartParams q;
+  bool single;
+  fill_common(g, q.sw, time, single);
+  Sweep2dParams &p = q.sw;
+  const gs_dim2d &d = xdir ? g->x : g->y;
+  const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
+  p.rhs = xdir ? g->grid : g->result;
+  p.coefs = d.coefs;
+  p.firstVol = d.hf[0]; p.fC = d.hf[1]; p.lastVol = d.hf[2]; p.lA = d.hf[3];
+  const int sf = xdir ? GS_LEFT : GS_UPP, sl = xdir ? GS_RIGHT : GS_LOW;
+  p.bound_first = g->b[sf].values;
+  p.bound_last = g->b[sl].values;
+  p.kind_first = g->b[sf].kind;
+  p.kind_last = g->b[sl].kind;
+  q.m = seg_len(g);
+  q.S = (n + q.m - 1) / q.m;
+  GS_REQUIRE(nlines <= 65535 && q.S <= 65535, "grid too large for the partitioned launch shape");
+  GS_TRY(ensure_iface(g, 7 * (size_t)nlines * q.S));
+  q.iface = g->iface;
+  q.predict_alt = nullptr;
+  if (fuse) {
+    if (!g->predict_alt) GS_CUDA(cudaMalloc(&g->predict_alt, (size_t)g->cols * g->rows * sizeof(double)));
+    p.grid_io = g->grid;
+    q.predict_alt = g->predict_alt;
+  }
+  const int bx = xdir ? std::min(128, (q.S + 31) / 32 * 32) : 128;
+  dim3 grid = xdir ? dim3((q.S + bx - 1) / bx, nlines) : dim3((nlines + bx - 1) / bx, q.S);
+  size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
+  size_t c_smem = (size_t)q.m * bx * sizeof(double2) + pool_smem;
+#define GS_PART(XD, SG)                                                                         \
+  do {                                                                                          \
+    k_part_A<XD, SG><<<grid, bx, pool_smem, ctx->stream>>>(q);                                  \
+    k_part_B<XD><<<(nlines + 63) / 64, 64, 0, ctx->stream>>>(q);                                \
+    if (fuse) {                                                                                 \
+      GS_CUDA(cudaFuncSetAttribute(k_part_C<XD, SG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem)); \
+      k_part_C<XD, SG, true><<<grid, bx, c_smem, ctx->stream>>>(q);                             \
+    } else {                                                                                    \
+      GS_CUDA(cudaFuncSetAttribute(k_part_C<XD, SG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem)); \
+      k_part_C<XD, SG, false><<<grid, bx, c_smem, ctx->stream>>>(q);                            \
+    }                                                                                           \
+  } while (0)
+  if (xdir) {
+    if (single) GS_PART(true, true); else GS_PART(true, false);
+  } else {
+    if (single) GS_PART(false, true); else GS_PART(false, false);
+  }
+#undef GS_PART
+  ctx->launches += 3;
+  GS_CUDA(cudaGetLastError());
+  if (fuse) std::swap(g->predict, g->predict_alt);  // predict' was written to the second buffer
+  return GS_OK;
+}
+
+static int sweep_x(gs_grid2d *g, double time) {
+  return use_partitioned(g, g->cols) ? launch_part(g, time, true, false) : launch_xsweep(g, time);
+}
+static int sweep_y(gs_grid2d *g, double time, bool fuse) {
+  return use_partitioned(g, g->rows) ? launch_part(g, time, false, fuse) : launch_ysweep(g, time, fuse);
+}
+
 extern "C" int gs_grid2d_xiter(gs_grid2d *g, double time) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   GS_TRY(gs_ctx_use(g->ctx));
   g->result_is_grid = false;  // xIter overwrites every element of result
-  return launch_xsweep(g, time);
+  return sweep_x(g, time);
 }
 extern "C" int gs_grid2d_yiter(gs_grid2d *g, double time) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   GS_TRY(gs_ctx_use(g->ctx));
   GS_TRY(materialise_result(g));
-  return launch_ysweep(g, time, false);
+  return sweep_y(g, time, false);
 }
 extern "C" int gs_grid2d_update(gs_grid2d *g) {
   GS_REQUIRE(g != nullptr, "NULL argument");
@@ -762,8 +1225,8 @@ extern "C" int gs_grid2d_iteration(gs_grid2d *g, double time, int nsteps) {
   GS_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
   GS_TRY(gs_ctx_use(g->ctx));
   for (int s = 0; s < nsteps; ++s) {
-    GS_TRY(launch_xsweep(g, time));
-    GS_TRY(launch_ysweep(g, time, true));
+    GS_TRY(sweep_x(g, time));
+    GS_TRY(sweep_y(g, time, true));
     g->result_is_grid = true;
   }
   return GS_OK;

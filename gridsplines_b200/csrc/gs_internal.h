@@ -58,6 +58,7 @@ struct gs_ctx {
   int64_t opt_smem_nodes = -1;
   int64_t opt_pipeline = 1;
   int64_t opt_pipe_cfg = 0;
+  int64_t opt_seg_len = 32;
 };
 
 int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice
@@ -110,6 +111,9 @@ struct gs_grid2d {
   std::vector<int> map_host[4];                         // ids as given
   double2 *scratch = nullptr;
   size_t scratch_elems = 0;
+  double *iface = nullptr;        // partitioned solver: interface coefficients / values
+  size_t iface_len = 0;
+  double *predict_alt = nullptr;  // partitioned fused y sweep writes predict' here, then the two swap
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };

@@ -155,6 +155,7 @@ def test_medium_grid_properties(O, gs):
     is uniform along x with x-independent BCs stays uniform along x (every column solve is identical)."""
     p = cases.bc_problem("TTFF", cols=512, rows=384)
     g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_THOMAS)
     g.iteration(900.0, nsteps=2)
     o.iteration(900.0); o.iteration(900.0)
     for k, v in cases.snapshot(o).items():
@@ -170,6 +171,7 @@ def test_medium_grid_properties(O, gs):
         tile = (lambda v: np.tile(v[None, :], (n, 1))) if sweep == "x" else (lambda v: np.tile(v[:, None], (1, n)))
         big = cases.Problem2D(xv, yv, 1, 0, bx, coefs="const", init=(tile(line_g), tile(line_p)))
         g = big.build_gs(gs)
+        g.set_solver(gs.SOLVER_THOMAS)
         if sweep == "x":
             small = cases.Problem2D(xv, yv[:4], 1, 0, {k: (v[0], v[1], v[2][:2] if len(v[2]) > 1 else v[2]) for k, v in bx.items()},
                                     coefs="const", init=(tile(line_g)[:2], tile(line_p)[:2]))
@@ -182,6 +184,7 @@ def test_medium_grid_properties(O, gs):
             by = {0: (0, 0, [20.0]), 1: (0, 0, [4.0]), 2: (0, 0, [1.0]), 3: (0, 0, [1.0])}
             big.bounds = by
             g = big.build_gs(gs)
+            g.set_solver(gs.SOLVER_THOMAS)
             g.grid.result = tile(line_g)
             small = cases.Problem2D(xv[:4], yv, 1, 0, by, coefs="const", init=(tile(line_g)[:, :2], tile(line_p)[:, :2]))
             o = small.build_oracle(O)
@@ -191,3 +194,94 @@ def test_medium_grid_properties(O, gs):
             assert np.all(res.view(np.uint64) == res[:, :1].view(np.uint64))
             assert_bit_equal(res[:, 0], o.result[:, 0], "2048^2 yIter column")
         assert g.status == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GS_SOLVER_PARTITIONED: segments + reduced system.  Operation order differs from the reference's single
+# chain, so the bar is the north star's tolerance: <= 1e-12 max relative error per field.
+# ---------------------------------------------------------------------------------------------
+TOL = 1e-12
+
+
+@pytest.fixture
+def seg_len(ctx):
+    def set_(m):
+        ctx.set_option("seg_len", m)
+
+    yield set_
+    ctx.set_option("seg_len", 32)
+
+
+def _compare_tol(got, want, what):
+    for k, v in want.items():
+        err = max_rel_err(got[k], v)
+        assert err <= TOL, f"{what} {k}: max relative error per field {err:.3e}"
+
+
+@pytest.mark.parametrize("combo", ["".join(c) for c in itertools.product("TF", repeat=4)])
+@pytest.mark.parametrize("m", [2, 5, 8])
+def test_partitioned_all_boundary_kinds(O, gs, seg_len, combo, m):
+    seg_len(m)
+    xdir = 1 if combo.count("F") % 2 else 0
+    p = cases.bc_problem(combo, xdir=xdir, ydir=0, cols=41, rows=35, dense=True)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.xIter(900.0); o.xIter(900.0)
+    assert max_rel_err(g.grid.result, o.result) <= TOL, "xIter"
+    g.yIter(900.0); o.yIter(900.0)
+    assert max_rel_err(g.grid.result, o.result) <= TOL, "yIter"
+    g.grid.update(); o.update()
+    g.iteration(900.0, nsteps=3)
+    for _ in range(3):
+        o.iteration(900.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"{combo} m={m}")
+    assert g.status == 0
+
+
+@pytest.mark.parametrize("cols,rows,m", [(4, 4, 2), (5, 9, 2), (33, 31, 4), (64, 65, 32), (130, 97, 7), (300, 270, 32)])
+@pytest.mark.parametrize("combo", ["TTTT", "FFFF", "TFTF"])
+def test_partitioned_ragged_sizes(O, gs, seg_len, cols, rows, m, combo):
+    seg_len(m)
+    p = cases.bc_problem(combo, xdir=1, ydir=1, cols=cols, rows=rows)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.iteration(900.0, nsteps=2)
+    o.iteration(900.0); o.iteration(900.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"{cols}x{rows} m={m} {combo}")
+
+
+@pytest.mark.parametrize("coefs", ["hermite", "per_row", "per_col", "dense"])
+def test_partitioned_coefficient_maps_and_tables(O, gs, seg_len, coefs):
+    seg_len(6)
+    p = cases.bc_problem("TTFT", xdir=1, cols=37, rows=29, coefs=coefs)
+    r = np.random.default_rng(4)
+    p.grid0 = r.uniform(-15.0, 70.0, p.grid0.shape)
+    p.predict0 = p.grid0 + r.uniform(-12.0, 12.0, p.grid0.shape)
+    g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.iteration(900.0, nsteps=3)
+    for _ in range(3):
+        o.iteration(900.0)
+    O.set_ascending_fold(True)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), coefs)
+
+
+def test_partitioned_gridtest_and_medium(O, gs, seg_len):
+    """AT/GridTest.scala with the partitioned solver: wall temperature within 1e-12 of KAT R1; then 512 x 384
+    (the AUTO solver's choice at that size) against the oracle."""
+    seg_len(8)
+    p = cases.gridtest_problem()
+    g = p.build_gs(gs)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.fill(7.0)
+    got = cases.run_gridtest(g, True)
+    want = np.load(os.path.join(GOLDEN, "gridtest_137x45x195.npz"))
+    _compare_tol(got, {k: want[k] for k in want.files}, "GridTest")
+    assert abs(got["grid"][0, 0] - 54.44328715390563) <= 1e-12 * 54.44328715390563
+    seg_len(32)
+    p = cases.bc_problem("TTFF", cols=512, rows=384)
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.iteration(900.0, nsteps=3)   # AUTO
+    for _ in range(3):
+        o.iteration(900.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), "512x384 auto")
