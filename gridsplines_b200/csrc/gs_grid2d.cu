@@ -64,6 +64,7 @@ GS_DEV int map_off(const Maps2d &m, int sel, int col, int row, int cols) {
 // Coefficients.{apply, thermConductivity, capacity, tempConductivity}(col, row), indices from -1
 template <bool SINGLE>
 struct CoefSel {
+  typedef GsSpline Z;
   const Maps2d &m;
   const double *pool;
   int cols;
@@ -78,6 +79,16 @@ struct CoefSel {
     if (SINGLE) return z[sel];
     return gs_spline_view(pool, map_off(m, sel, col, row, cols));
   }
+};
+// every selector is SINGLE and a literal Spline.const (ConstantCoef over Spline.const values)
+struct CoefSelLit {
+  typedef GsLitConst Z;
+  GsLitConst z[4];
+  GS_DEV CoefSelLit(const Maps2d &maps, const double *pool, int) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) z[s].v = pool[maps.single_off[s] + GS_HDR + 3];
+  }
+  GS_DEV GsLitConst get(int sel, int, int) const { return z[sel]; }
 };
 
 // one line's forward elimination state
@@ -426,9 +437,9 @@ struct PartParams {
 };
 
 // Dim.general :67-83 up to the elimination: (sub, diag, sup, rhs) of an interior node
-template <bool FAST>
+template <bool FAST, class Z>
 GS_DEV Row4 asm_general(const SweepConsts &k, double cf0, double cf1, double face_left, double p0, double p1,
-                        double t, const GsSpline &z, double &face_right, unsigned &flags, bool &ok) {
+                        double t, const Z &z, double &face_right, unsigned &flags, bool &ok) {
   double co = gs_take_average<FAST>(z, p0, p1, flags, ok);
   Row4 r;
   r.sub = cf0 * face_left;
@@ -439,9 +450,9 @@ GS_DEV Row4 asm_general(const SweepConsts &k, double cf0, double cf1, double fac
   return r;
 }
 // Dim.first :28-43
-template <bool FAST>
+template <bool FAST, class Z>
 GS_DEV Row4 asm_first_temp(const SweepConsts &k, double cf0, double cf1, double t1, double p0, double p1, double t,
-                           const GsSpline &z0, const GsSpline &z, double &face_right, unsigned &flags, bool &ok) {
+                           const Z &z0, const Z &z, double &face_right, unsigned &flags, bool &ok) {
   double co0 = gs_take_average<FAST>(z0, t1, p0, flags, ok);
   double co = gs_take_average<FAST>(z, p0, p1, flags, ok);
   double a = cf0 * co0;
@@ -454,9 +465,9 @@ GS_DEV Row4 asm_first_temp(const SweepConsts &k, double cf0, double cf1, double 
   return r;
 }
 // Dim.firstHeatFlow :46-64
-template <bool FAST>
+template <bool FAST, class Z>
 GS_DEV Row4 asm_first_flow(const SweepConsts &k, double heatFlow, double p0, double p1, double t,
-                           const GsSpline &conductivity, const GsSpline &capacity, double &face_right,
+                           const Z &conductivity, const Z &capacity, double &face_right,
                            unsigned &flags, bool &ok) {
   double cap = gs_ads_apply(capacity, t, flags);
   double cond = gs_ads_average<FAST>(conductivity, p0, p1, flags, ok);
@@ -470,9 +481,9 @@ GS_DEV Row4 asm_first_flow(const SweepConsts &k, double heatFlow, double p0, dou
   return r;
 }
 // Dim.last :86-103
-template <bool FAST>
+template <bool FAST, class Z>
 GS_DEV Row4 asm_last_temp(const SweepConsts &k, double cf0, double cf1, double face_left, double p0, double t3,
-                          double t, const GsSpline &z, unsigned &flags, bool &ok) {
+                          double t, const Z &z, unsigned &flags, bool &ok) {
   double co = gs_take_average<FAST>(z, p0, t3, flags, ok);
   Row4 r;
   r.sub = cf0 * face_left;
@@ -483,9 +494,9 @@ GS_DEV Row4 asm_last_temp(const SweepConsts &k, double cf0, double cf1, double f
   return r;
 }
 // Dim.lastHeatFlow :106-128
-template <bool FAST>
+template <bool FAST, class Z>
 GS_DEV Row4 asm_last_flow(const SweepConsts &k, double heatFlow, double t1, double t2, double t,
-                          const GsSpline &conductivity, const GsSpline &capacity, unsigned &flags, bool &ok) {
+                          const Z &conductivity, const Z &capacity, unsigned &flags, bool &ok) {
   double cap = gs_ads_apply(capacity, t, flags);
   double cond = gs_ads_average<FAST>(conductivity, t1, t2, flags, ok);
   double vol = gs_div<FAST>(cap * k.lastVol, k.rt, ok);
@@ -517,14 +528,12 @@ struct LineAcc {
 
 // assembles node i of the line (any position) from the reference's formulas; `face` is the carried face value
 // (Dim's co0), `pm`, `p0` the predict values of nodes i-1 and i (pm unused at i = 0)
-template <bool XDIR, bool SINGLE, bool FAST>
-GS_DEV Row4 asm_node(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, const SweepConsts &k, int i, double p0,
-                     double &pnext, double &face, unsigned &flags, bool &ok) {
+template <bool XDIR, class SEL, bool FAST>
+GS_DEV Row4 asm_node(const LineAcc<XDIR> &A, const SEL &sel, const SweepConsts &k, int i, double p0,
+                     double pnext, double t, double &face, unsigned &flags, bool &ok) {
   const Sweep2dParams &p = A.p;
   const int n = A.n();
-  const double t = A.rhs(i);
   if (i == 0) {
-    pnext = A.pred(1);
     if (p.kind_first == GS_TEMP) {
       return asm_first_temp<FAST>(k, p.coefs[0], p.coefs[1], p.bound_first[A.line], p0, pnext, t,
                                   XDIR ? sel.get(GS_SEL_APPLY, -1, A.line) : sel.get(GS_SEL_APPLY, A.line, -1),
@@ -545,14 +554,13 @@ GS_DEV Row4 asm_node(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, const S
     return asm_last_flow<FAST>(k, p.bound_last[A.line], t1, p0, t, sel.get(GS_SEL_TEMPCOND, A.col(i), A.row(i)),
                                sel.get(GS_SEL_CAP, A.col(i), A.row(i)), flags, ok);
   }
-  pnext = A.pred(i + 1);
   return asm_general<FAST>(k, p.coefs[2 * i], p.coefs[2 * i + 1], face, p0, pnext, t,
                            sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), face, flags, ok);
 }
 
 // face value between nodes s-1 and s as node s-1 would have carried it (Dim.general's `co`)
-template <bool XDIR, bool SINGLE, bool FAST>
-GS_DEV double face_before(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, const SweepConsts &k, int s, double pm,
+template <bool XDIR, class SEL, bool FAST>
+GS_DEV double face_before(const LineAcc<XDIR> &A, const SEL &sel, const SweepConsts &k, int s, double pm,
                           double p0, unsigned &flags, bool &ok) {
   const Sweep2dParams &p = A.p;
   if (s - 1 == 0 && p.kind_first == GS_FLOW) {
@@ -565,6 +573,30 @@ GS_DEV double face_before(const LineAcc<XDIR> &A, const CoefSel<SINGLE> &sel, co
   }
   return gs_take_average<FAST>(sel.get(GS_SEL_APPLY, A.col(s - 1), A.row(s - 1)), pm, p0, flags, ok);
 }
+
+// Inputs of a segment, fetched two nodes ahead of their use so that the global-load latency overlaps the
+// (long, dependent) FP64 work of the node being eliminated.
+template <bool XDIR>
+struct SegStream {
+  const LineAcc<XDIR> &A;
+  int n;
+  double pA, pB, tA, tB;   // predict[i+1], predict[i+2], rhs[i], rhs[i+1] for the current i
+  GS_DEV SegStream(const LineAcc<XDIR> &A_, int s) : A(A_), n(A_.n()) {
+    pA = (s + 1 < n) ? A.pred(s + 1) : 0.0;
+    pB = (s + 2 < n) ? A.pred(s + 2) : 0.0;
+    tA = A.rhs(s);
+    tB = (s + 1 < n) ? A.rhs(s + 1) : 0.0;
+  }
+  // returns (pnext, t) of node i and issues the loads node i + 2 will need
+  GS_DEV void next(int i, double &pnext, double &t) {
+    pnext = pA;
+    t = tA;
+    pA = pB;
+    tA = tB;
+    pB = (i + 3 < n) ? A.pred(i + 3) : 0.0;
+    tB = (i + 2 < n) ? A.rhs(i + 2) : 0.0;
+  }
+};
 
 GS_DEV void part_ids(bool xdir, int nlines, int S, int &line, int &seg) {
   if (xdir) {
@@ -579,8 +611,8 @@ GS_DEV size_t iface_idx(bool xdir, int nlines, int S, int line, int seg) {
   return xdir ? (size_t)line * S + seg : (size_t)seg * nlines + line;
 }
 
-template <bool XDIR, bool SINGLE, bool FAST>
-GS_DEV bool part_A_body(const PartParams &q, const CoefSel<SINGLE> &sel, const SweepConsts &k, int line, int seg,
+template <bool XDIR, class SEL, bool FAST>
+GS_DEV bool part_A_body(const PartParams &q, const SEL &sel, const SweepConsts &k, int line, int seg,
                         double *out6, unsigned &flags) {
   const Sweep2dParams &p = q.sw;
   LineAcc<XDIR> A(p, line);
@@ -589,10 +621,12 @@ GS_DEV bool part_A_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
   bool ok = true;
   double delta = 0.0, lambda = 0.0, omega = 0.0;
   double P = 1.0, Q = 0.0, R = 0.0;
-  double p0 = A.pred(s), pnext = 0.0, face = 0.0;
-  if (s > 0) face = face_before<XDIR, SINGLE, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
+  double p0 = A.pred(s), pnext = 0.0, t = 0.0, face = 0.0;
+  SegStream<XDIR> in(A, s);
+  if (s > 0) face = face_before<XDIR, SEL, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
   for (int i = s; i <= e; ++i) {
-    Row4 r = asm_node<XDIR, SINGLE, FAST>(A, sel, k, i, p0, pnext, face, flags, ok);
+    in.next(i, pnext, t);
+    Row4 r = asm_node<XDIR, SEL, FAST>(A, sel, k, i, p0, pnext, t, face, flags, ok);
     if (i > s) {  // the map x_s = P x_i + Q + R L gains node i-1's relation
       Q = Q + P * lambda;
       R = R + P * omega;
@@ -623,8 +657,8 @@ GS_DEV bool part_A_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
   return ok;
 }
 
-template <bool XDIR, bool SINGLE>
-__global__ void __launch_bounds__(128) k_part_A(PartParams q) {
+template <bool XDIR, class SEL>
+__global__ void __launch_bounds__(128, 5) k_part_A(PartParams q) {
   extern __shared__ double sm[];
   const Sweep2dParams &p = q.sw;
   const double *pool = stage_pool(p, sm);
@@ -632,7 +666,7 @@ __global__ void __launch_bounds__(128) k_part_A(PartParams q) {
   int line, seg;
   part_ids(XDIR, nlines, q.S, line, seg);
   if (line >= nlines || seg >= q.S) return;
-  CoefSel<SINGLE> sel(p.maps, pool, p.cols);
+  SEL sel(p.maps, pool, p.cols);
   SweepConsts k;
   k.fast_allowed = true;
   k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
@@ -640,10 +674,10 @@ __global__ void __launch_bounds__(128) k_part_A(PartParams q) {
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
   double o[6];
-  bool ok = k.fast_allowed && part_A_body<XDIR, SINGLE, true>(q, sel, k, line, seg, o, flags);
+  bool ok = k.fast_allowed && part_A_body<XDIR, SEL, true>(q, sel, k, line, seg, o, flags);
   if (!ok) {
     flags = 0;
-    part_A_body<XDIR, SINGLE, false>(q, sel, k, line, seg, o, flags);
+    part_A_body<XDIR, SEL, false>(q, sel, k, line, seg, o, flags);
   }
   const size_t N = (size_t)nlines * q.S, id = iface_idx(XDIR, nlines, q.S, line, seg);
 #pragma unroll
@@ -687,8 +721,8 @@ __global__ void k_part_B(PartParams q) {
   }
 }
 
-template <bool XDIR, bool SINGLE, bool FAST, bool FUSE>
-GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const SweepConsts &k, int line, int seg,
+template <bool XDIR, class SEL, bool FAST, bool FUSE>
+GS_DEV bool part_C_body(const PartParams &q, const SEL &sel, const SweepConsts &k, int line, int seg,
                         double2 *sc, int scs, unsigned &flags) {
   const Sweep2dParams &p = q.sw;
   LineAcc<XDIR> A(p, line);
@@ -700,10 +734,12 @@ GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
   const double L = seg > 0 ? q.iface[6 * N + iface_idx(XDIR, nlines, q.S, line, seg - 1)] : 0.0;
   bool ok = true;
   double delta = 0.0, lambda = 0.0;
-  double p0 = A.pred(s), pnext = 0.0, face = 0.0;
-  if (s > 0) face = face_before<XDIR, SINGLE, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
+  double p0 = A.pred(s), pnext = 0.0, t = 0.0, face = 0.0;
+  SegStream<XDIR> in(A, s);
+  if (s > 0) face = face_before<XDIR, SEL, FAST>(A, sel, k, s, A.pred(s - 1), p0, flags, ok);
   for (int i = s; i < e; ++i) {   // node e's value is already known
-    Row4 r = asm_node<XDIR, SINGLE, FAST>(A, sel, k, i, p0, pnext, face, flags, ok);
+    in.next(i, pnext, t);
+    Row4 r = asm_node<XDIR, SEL, FAST>(A, sel, k, i, p0, pnext, t, face, flags, ok);
     if (i == s) {
       GsRcp rd = gs_rcp<FAST>(r.diag, ok);
       delta = gs_div<FAST>(-r.sup, rd, ok);
@@ -719,6 +755,11 @@ GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
   }
   if (FAST && !ok) return false;
   double x = xe;
+  double gA = 0.0, gB = 0.0;
+  if (FUSE) {
+    gA = p.grid_io[A.idx(e)];
+    gB = (e - 1 >= s) ? p.grid_io[A.idx(e - 1)] : 0.0;
+  }
   for (int i = e; i >= s; --i) {
     if (i < e) {
       double2 v = sc[(i - s) * scs];
@@ -726,7 +767,9 @@ GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
     }
     size_t id = A.idx(i);
     if (FUSE) {
-      double g = p.grid_io[id];
+      double g = gA;
+      gA = gB;
+      gB = (i - 2 >= s) ? p.grid_io[A.idx(i - 2)] : 0.0;   // two nodes ahead (own nodes only: no aliasing with the stores below)
       q.predict_alt[id] = aval2d(g, x);
       p.grid_io[id] = x;
     } else {
@@ -737,8 +780,8 @@ GS_DEV bool part_C_body(const PartParams &q, const CoefSel<SINGLE> &sel, const S
   return true;
 }
 
-template <bool XDIR, bool SINGLE, bool FUSE>
-__global__ void __launch_bounds__(128) k_part_C(PartParams q) {
+template <bool XDIR, class SEL, bool FUSE>
+__global__ void __launch_bounds__(128, 5) k_part_C(PartParams q) {
   extern __shared__ __align__(16) unsigned char smc[];
   const Sweep2dParams &p = q.sw;
   double2 *scratch = reinterpret_cast<double2 *>(smc);
@@ -748,7 +791,7 @@ __global__ void __launch_bounds__(128) k_part_C(PartParams q) {
   int line, seg;
   part_ids(XDIR, nlines, q.S, line, seg);
   if (line >= nlines || seg >= q.S) return;
-  CoefSel<SINGLE> sel(p.maps, pool, p.cols);
+  SEL sel(p.maps, pool, p.cols);
   SweepConsts k;
   k.fast_allowed = true;
   k.rt = gs_rcp_invariant(p.time, k.fast_allowed);
@@ -756,10 +799,10 @@ __global__ void __launch_bounds__(128) k_part_C(PartParams q) {
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
   double2 *sc = scratch + threadIdx.x;
-  bool done = k.fast_allowed && part_C_body<XDIR, SINGLE, true, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
+  bool done = k.fast_allowed && part_C_body<XDIR, SEL, true, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
   if (!done) {
     flags = 0;
-    part_C_body<XDIR, SINGLE, false, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
+    part_C_body<XDIR, SEL, false, FUSE>(q, sel, k, line, seg, sc, blockDim.x, flags);
   }
   gs_raise(p.status, flags);
 }
@@ -1177,10 +1220,16 @@ static int launch_part(gs_grid2d *g, double time, bool xdir, bool fuse) {
       k_part_C<XD, SG, false><<<grid, bx, c_smem, ctx->stream>>>(q);                            \
     }                                                                                           \
   } while (0)
+  bool lit = single;
+  for (int sl4 = 0; sl4 < 4 && lit; ++sl4) {
+    const double *h = ctx->pool.data() + p.maps.single_off[sl4];
+    lit = (int)h[0] == GS_CONST && (int)h[1] == 1 && h[2] == -1.7976931348623157e308 && h[3] == h[2] &&
+          h[4] == h[GS_HDR + 3] && h[5] == h[GS_HDR + 3] && h[GS_HDR] == h[2] && h[GS_HDR + 1] == -h[2];
+  }
   if (xdir) {
-    if (single) GS_PART(true, true); else GS_PART(true, false);
+    if (lit) GS_PART(true, CoefSelLit); else if (single) GS_PART(true, CoefSel<true>); else GS_PART(true, CoefSel<false>);
   } else {
-    if (single) GS_PART(false, true); else GS_PART(false, false);
+    if (lit) GS_PART(false, CoefSelLit); else if (single) GS_PART(false, CoefSel<true>); else GS_PART(false, CoefSel<false>);
   }
 #undef GS_PART
   ctx->launches += 3;
