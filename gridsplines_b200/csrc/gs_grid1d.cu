@@ -776,6 +776,248 @@ __global__ void __launch_bounds__(256) k_step1d_hoist(Step1dParams p, const doub
 }
 
 // ---------------------------------------------------------------------------------
+// K2c: hoisted coefficients + checkpoint/recompute -- no scratch traffic at all.
+//
+// K2h's remaining excess traffic is the lambda round trip (8 B written + 8 B read per node, all of it
+// reaching DRAM: profiles/r1_k_step1d_hoist_bench.txt).  The hoisted forward recurrence is only 8 FP64
+// instructions per node, so it is cheaper to run it twice than to store it:
+//   pass 1  streams grid once and keeps lambda only at the end of every K-node block (a checkpoint per
+//           block and lane, in shared memory);
+//   pass 2  walks the blocks from the last to the first: reloads the block's grid values (L2: pass 1 asked
+//           for evict_last), recomputes its lambdas from the checkpoint with the very same operations,
+//           back-substitutes, applies the predictor and stores grid' / predict' in place of the two
+//           shared-memory buffers (grid -> grid', lambda -> predict').
+// Same operations on the same inputs => same bits as K2h and as the general path.  DRAM traffic: read grid
+// (8) + write grid', predict' (16) = 24 B/node when the re-read hits L2.
+// ---------------------------------------------------------------------------------
+template <int K>
+struct PipeC {
+  static constexpr int kBufBytes = K * 256;
+  static constexpr int kFixedBytes = 3 * kBufBytes + 128;  // 3 buffers + mbarriers (checkpoints follow)
+};
+
+template <bool FAST, int K>
+GS_DEV bool ck_pass1(const LineH &L, char *wsm, uint64_t *full, uint32_t &phase, double *ckpt, const double *Gblk,
+                     int lane, double firstT, double lastT, double &lambda, uint64_t pol_keep) {
+  typedef PipeC<K> PP;
+  const int n = L.n;
+  const int NB = (n + K - 1) / K;
+  bool ok = true;
+  auto issue = [&](int c) {
+    int len = min(K, n - c * K);
+    int s = c % 3;
+    gs_mbar_expect_tx(&full[s], (uint32_t)len * 256u);
+    gs_bulk_g2s_hint(wsm + s * PP::kBufBytes, Gblk + (size_t)c * K * GS_LB, (uint32_t)len * 256u, &full[s], pol_keep);
+  };
+  if (lane == 0) {
+    for (int c = 0; c < min(3, NB); ++c) issue(c);
+  }
+  const double c_last = L.tab[4 * (size_t)n];
+  int s = 0;
+  for (int c = 0; c < NB; ++c, s = (s == 2 ? 0 : s + 1)) {
+    gs_mbar_wait(&full[s], (phase >> s) & 1u);
+    phase ^= 1u << s;
+    const double *sG = reinterpret_cast<const double *>(wsm + s * PP::kBufBytes) + lane;
+    const int len = min(K, n - c * K);
+    const double *t = L.tab + 4 * (size_t)c * K;
+    if (c != 0 && c != NB - 1) {
+#pragma unroll
+      for (int m = 0; m < K; ++m) hoist_fwd_node<FAST>(sG[m * GS_LB], t + 4 * m, L.rt, lambda, ok);
+    } else {
+      for (int m = 0; m < len; ++m) {
+        const int i = c * K + m;
+        const double *ti = t + 4 * m;
+        GsRcp rd;
+        rd.b = ti[1];
+        rd.y = ti[2];
+        double vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok);
+        if (i == 0) {
+          lambda = gs_div<FAST>(vect - ti[0] * firstT, rd, ok);       // :65, forwardFirst :245-248
+        } else {
+          if (i == n - 1) vect = vect - c_last * lastT;               // :89
+          lambda = gs_div<FAST>(vect - ti[0] * lambda, rd, ok);       // lam :234
+        }
+      }
+    }
+    ckpt[c * GS_LB + lane] = lambda;
+    __syncwarp();
+    if (lane == 0 && c + 3 < NB) issue(c + 3);
+  }
+  return ok;
+}
+
+template <int K, bool TABSM>
+__global__ void __launch_bounds__(128, 3) k_step1d_hoist_ck(Step1dParams p, const double *table, int ckpt_rows) {
+  typedef PipeC<K> PP;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = p.n;
+  const int nw = blockDim.x >> 5;
+  const size_t warp_bytes = (size_t)PP::kFixedBytes + (size_t)ckpt_rows * 256;
+  LineH L;
+  L.n = n;
+  if (TABSM) {
+    double *smd = reinterpret_cast<double *>(smraw + (size_t)nw * warp_bytes);
+    for (int i = threadIdx.x; i < 4 * n + 2; i += blockDim.x) smd[i] = table[i];
+    L.tab = smd;
+  } else {
+    L.tab = table;
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  char *wsm = reinterpret_cast<char *>(smraw) + (size_t)wib * warp_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(wsm + 3 * PP::kBufBytes);
+  double *ckpt = reinterpret_cast<double *>(wsm + PP::kFixedBytes);
+  if (lane == 0) {
+    for (int s = 0; s < 3; ++s) gs_mbar_init(&full[s], 1);
+    gs_mbar_init_fence();
+  }
+  gs_fence_proxy_async();
+  __syncthreads();
+  const long long warp = (long long)blockIdx.x * nw + wib;
+  if (warp >= p.nwarps) return;
+  bool fast_allowed = p.allow_fast != 0 && L.tab[4 * (size_t)n + 1] != 0.0;
+  L.rt = gs_rcp_invariant(p.time, fast_allowed);
+  GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
+  const uint64_t pol_keep = gs_policy_evict_last(), pol_stream = gs_policy_evict_first();
+  unsigned flags = 0;
+  const size_t block_elems = (size_t)n * GS_LB;
+  uint32_t phase = 0;   // bit s = parity the next wait on buffer s expects
+  const int NB = (n + K - 1) / K;
+  const double c_last = L.tab[4 * (size_t)n];
+
+  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+    const long long line = blk * GS_LB + lane;
+    const bool valid = line < p.nlines;
+    const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
+    double *Gblk = p.grid + (size_t)blk * block_elems;
+    double *Pblk = p.predict + (size_t)blk * block_elems;
+    const double firstT = p.leftT[bcl], lastT = p.rightT[bcl];
+    bool try_fast = fast_allowed;
+    for (int step = 0; step < p.nsteps; ++step) {
+      double lambda = 0.0;
+      unsigned lf = 0;
+      // ---- pass 1: forward recurrence, checkpoints only ----
+      bool ok = false;
+      if (try_fast) {
+        ok = ck_pass1<true, K>(L, wsm, full, phase, ckpt, Gblk, lane, firstT, lastT, lambda, pol_keep);
+        ok = __all_sync(0xffffffffu, ok);
+      }
+      if (!ok) {
+        try_fast = false;
+        ck_pass1<false, K>(L, wsm, full, phase, ckpt, Gblk, lane, firstT, lastT, lambda, pol_keep);
+      }
+      __syncwarp();
+      // ---- pass 2: per block, recompute lambda, back-substitute, predictor, store ----
+      // buffers 0/1 alternate as bufA (grid -> grid'), buffer 2 is bufB (lambda -> predict')
+      auto load_block = [&](int b) {
+        int len = min(K, n - b * K);
+        int pr = (NB - 1 - b) & 1;
+        gs_mbar_expect_tx(&full[pr], (uint32_t)len * 256u);
+        gs_bulk_g2s_hint(wsm + pr * PP::kBufBytes, Gblk + (size_t)b * K * GS_LB, (uint32_t)len * 256u, &full[pr],
+                         pol_stream);
+      };
+      if (lane == 0) load_block(NB - 1);
+      double u = 0.0;
+      for (int b = NB - 1; b >= 0; --b) {
+        const int pr = (NB - 1 - b) & 1;
+        if (lane == 0) {
+          // block b+1's stores must have read bufB and the other bufA before they are written again
+          gs_bulk_wait_read<0>();
+          if (b >= 1) load_block(b - 1);
+        }
+        __syncwarp();
+        gs_mbar_wait(&full[pr], (phase >> pr) & 1u);
+        phase ^= 1u << pr;
+        double *bA = reinterpret_cast<double *>(wsm + pr * PP::kBufBytes) + lane;      // grid -> grid'
+        double *bB = reinterpret_cast<double *>(wsm + 2 * PP::kBufBytes) + lane;       // lambda -> predict'
+        const int len = min(K, n - b * K);
+        const double *t = L.tab + 4 * (size_t)b * K;
+        // recompute this block's lambdas (same operations as pass 1)
+        bool ok2 = true;
+        double lam = (b > 0) ? ckpt[(b - 1) * GS_LB + lane] : 0.0;
+        if (b != 0 && b != NB - 1) {
+          if (try_fast) {
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+              hoist_fwd_node<true>(bA[m * GS_LB], t + 4 * m, L.rt, lam, ok2);
+              bB[m * GS_LB] = lam;
+            }
+          } else {
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+              hoist_fwd_node<false>(bA[m * GS_LB], t + 4 * m, L.rt, lam, ok2);
+              bB[m * GS_LB] = lam;
+            }
+          }
+        } else {
+          for (int m = 0; m < len; ++m) {
+            const int i = b * K + m;
+            const double *ti = t + 4 * m;
+            double g = bA[m * GS_LB];
+            if (try_fast) {
+              GsRcp rd;
+              rd.b = ti[1];
+              rd.y = ti[2];
+              double vect = gs_div<true>(-g, L.rt, ok2);
+              if (i == 0) lam = gs_div<true>(vect - ti[0] * firstT, rd, ok2);
+              else {
+                if (i == n - 1) vect = vect - c_last * lastT;
+                lam = gs_div<true>(vect - ti[0] * lam, rd, ok2);
+              }
+            } else {
+              double vect = -g / p.time;
+              if (i == 0) lam = (vect - ti[0] * firstT) / ti[1];
+              else {
+                if (i == n - 1) vect = vect - c_last * lastT;
+                lam = (vect - ti[0] * lam) / ti[1];
+              }
+            }
+            bB[m * GS_LB] = lam;
+          }
+        }
+        // back-substitution (backwardPassion :345-365) + predictor (arraygrid.aVal :85-87) + grid <- result
+        bool okb = fast_allowed;
+        if (len == K) {
+          double uu[K];
+#pragma unroll
+          for (int m = K - 1; m >= 0; --m) {
+            u = t[4 * m + 3] * u + bB[m * GS_LB];
+            uu[m] = u;
+            bB[m * GS_LB] = u + gs_div<true>(u - bA[m * GS_LB], r3, okb);
+          }
+          if (!__all_sync(0xffffffffu, okb)) {
+            // some (u - t) was zero / out of range for the shared-reciprocal division: plain division
+#pragma unroll
+            for (int m = 0; m < K; ++m) bB[m * GS_LB] = uu[m] + (uu[m] - bA[m * GS_LB]) / 3.0;
+          }
+#pragma unroll
+          for (int m = 0; m < K; ++m) bA[m * GS_LB] = uu[m];
+        } else {
+          for (int m = len - 1; m >= 0; --m) {
+            u = t[4 * m + 3] * u + bB[m * GS_LB];
+            double d = u - bA[m * GS_LB];
+            bB[m * GS_LB] = u + d / 3.0;
+            bA[m * GS_LB] = u;
+          }
+        }
+        gs_fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          gs_bulk_s2g_hint(Gblk + (size_t)b * K * GS_LB, wsm + pr * PP::kBufBytes, (uint32_t)len * 256u, pol_stream);
+          gs_bulk_s2g_hint(Pblk + (size_t)b * K * GS_LB, wsm + 2 * PP::kBufBytes, (uint32_t)len * 256u, pol_stream);
+          gs_bulk_commit();
+        }
+      }
+      // grid' / predict' complete before the next step (or the next block's pass 1) reuses buffers / data
+      if (lane == 0) gs_bulk_wait<0>();
+      __syncwarp();
+      if (!(fabs(u) <= 1.7976931348623157e308)) lf |= GS_FLAG_NONFINITE;
+      if (valid) flags |= lf;
+    }
+  }
+  gs_raise(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------
 // device index of (line, node) in the blocked layout [line / 32][node][line % 32]
@@ -1059,7 +1301,7 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   // resident line threads per SM: measured optimum per path on B200 (profiles/): the hoisted kernel is
   // DRAM-bound from 7 warps/SM on, the general one wants every warp its shared-memory ring allows
   const bool hoist_path = g->all_const && ctx->opt_const_hoist && ctx->opt_pipeline;
-  int64_t tps = ctx->opt_threads_per_sm_1d > 0 ? ctx->opt_threads_per_sm_1d : (hoist_path ? 224 : 384);
+  int64_t tps = ctx->opt_threads_per_sm_1d > 0 ? ctx->opt_threads_per_sm_1d : 384;
   long long want_warps = (long long)ctx->sm_count * std::max<int64_t>(32, tps) / 32;
   long long nwarps = std::min<long long>(nblocks, want_warps);
   size_t need = (size_t)nwarps * (size_t)g->n * GS_LB;
@@ -1115,6 +1357,28 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
     int blocks = (int)((nwarps + pblock / 32 - 1) / (pblock / 32));
     size_t tab_bytes = (4 * (size_t)g->n + 2) * sizeof(double);
     int smem_table = tab_bytes <= 24 * 1024 ? 1 : 0;
+    // K2c (checkpoint + recompute) when the per-block checkpoints fit in shared memory
+    {
+      const int K = ctx->opt_ck_block == 32 ? 32 : 16;
+      const int ckpt_rows = (g->n + K - 1) / K;
+      const size_t wbytes = (K == 32 ? PipeC<32>::kFixedBytes : PipeC<16>::kFixedBytes) + (size_t)ckpt_rows * 256;
+      if (ctx->opt_hoist_ck && wbytes <= 28 * 1024) {
+        size_t psmem = (smem_table ? tab_bytes : 0) + (size_t)(pblock / 32) * wbytes;
+        void (*kern)(Step1dParams, const double *, int) =
+            K == 32 ? (smem_table ? k_step1d_hoist_ck<32, true> : k_step1d_hoist_ck<32, false>)
+                    : (smem_table ? k_step1d_hoist_ck<16, true> : k_step1d_hoist_ck<16, false>);
+        GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        int per_sm = 0;
+        GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pblock, psmem));
+        GS_REQUIRE(per_sm >= 1, "line kernel does not fit on an SM");
+        p.nwarps = std::min<long long>(nwarps, (long long)per_sm * ctx->sm_count * (pblock / 32));
+        blocks = (int)((p.nwarps + pblock / 32 - 1) / (pblock / 32));
+        kern<<<blocks, pblock, psmem, ctx->stream>>>(p, g->hoist_table, ckpt_rows);
+        ctx->launches++;
+        GS_CUDA(cudaGetLastError());
+        return GS_OK;
+      }
+    }
 #define GS_LAUNCH_HOIST(CH, NSI)                                                                   \
   do {                                                                                             \
     size_t psmem = (smem_table ? tab_bytes : 0) + (size_t)(pblock / 32) * PipeH<CH, NSI>::kWarpBytes; \

@@ -59,6 +59,8 @@ struct gs_ctx {
   int64_t opt_pipeline = 1;
   int64_t opt_pipe_cfg = 0;
   int64_t opt_seg_len = 32;
+  int64_t opt_hoist_ck = 1;
+  int64_t opt_ck_block = 16;
 };
 
 int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice

@@ -48,7 +48,8 @@ def test_batch_vs_golden(gs, name, args):
 @pytest.fixture
 def options(ctx):
     """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
-    defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0}
+    defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0,
+                "hoist_ck": 1, "ck_block": 16}
 
     def set_(**kw):
         for k, v in kw.items():
@@ -63,11 +64,14 @@ def options(ctx):
 # plain IEEE division instead of the shared-reciprocal one, other ring shapes
 PATHS = {
     "default": {},
+    "hoist_scratch": {"hoist_ck": 0},
+    "hoist_ck32": {"ck_block": 32},
+    "hoist_ck_native": {"native_div": 1},
     "general": {"const_hoist": 0},
     "direct": {"const_hoist": 0, "pipeline": 0},
-    "native_div": {"native_div": 1},
+    "native_div": {"native_div": 1, "hoist_ck": 0},
     "general_native_div": {"const_hoist": 0, "native_div": 1},
-    "ring1": {"pipe_cfg": 1},
+    "ring1": {"pipe_cfg": 1, "hoist_ck": 0},
     "general_ring2": {"const_hoist": 0, "pipe_cfg": 2},
     "few_warps": {"threads_per_sm_1d": 32},
 }
