@@ -49,6 +49,7 @@ SIGNATURES = {
     "gs_grid1d_fill": (_vp, C.c_int, C.c_double),
     "gs_grid1d_set_bc": (_vp, _dp, _dp, C.c_int),
     "gs_grid1d_step": (_vp, C.c_double, C.c_int),
+    "gs_grid1d_step_host": (_vp, C.c_double, C.c_int, _vp, _dp, _dp, C.c_int),
     "gs_grid1d_set_solver": (_vp, C.c_int),
     "gs_grid1d_status": (_vp, C.POINTER(C.c_uint32)),
     "gs_grid1d_clear_status": (_vp,),

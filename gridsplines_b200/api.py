@@ -363,6 +363,17 @@ class BatchedOneDGrid:
             self.set_bc(leftT, rightT)
         L.check(L.lib().gs_grid1d_step(self._h, time, nsteps))
 
+    def step_host(self, time: float, host_grid, leftT, rightT, nsteps: int = 1):
+        """OneDGrid.step with the state in a HOST array (numpy, or an int pointer to pinned memory): upload grid,
+        step, download grid, pipelined over line chunks.  `host_grid` [nlines, n] is updated in place."""
+        lt, rt = np.atleast_1d(_d(leftT)), np.atleast_1d(_d(rightT))
+        stride = 0 if (lt.size == 1 and rt.size == 1) else 1
+        if stride:
+            lt = np.ascontiguousarray(np.broadcast_to(lt, (self.nlines,)))
+            rt = np.ascontiguousarray(np.broadcast_to(rt, (self.nlines,)))
+        ptr = host_grid if isinstance(host_grid, int) else host_grid.ctypes.data
+        L.check(L.lib().gs_grid1d_step_host(self._h, time, nsteps, ptr, _p(lt), _p(rt), stride))
+
     def set_solver(self, solver: int):
         L.check(L.lib().gs_grid1d_set_solver(self._h, solver))
 

@@ -23,7 +23,7 @@ int gs_launch_predef(gs_ctx *ctx, int dir, const double *values_dev, int n, doub
 
 struct Step1dParams {
   int n;
-  long long nlines, nblocks, nwarps;
+  long long nlines, blk0, nblocks, nwarps;   // line blocks [blk0, nblocks) are stepped
   double *grid, *predict;
   double2 *scratch;
   const double *predef;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_step1d(Step1dParams p) {
   const size_t block_elems = (size_t)n * GS_LB;
   double2 *sc = p.scratch + (size_t)warp * block_elems + lane;
 
-  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+  for (long long blk = p.blk0 + warp; blk < p.nblocks; blk += p.nwarps) {
     const long long line = blk * GS_LB + lane;
     const bool valid = line < p.nlines;  // padding lanes compute on the padding lines (kept finite)
     const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) k_step1d_tma(Step1dParams p) {
   uint32_t seq = 0, oseq = 0;
   const int NC = (n + CH - 1) / CH;
 
-  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+  for (long long blk = p.blk0 + warp; blk < p.nblocks; blk += p.nwarps) {
     const long long line = blk * GS_LB + lane;
     const bool valid = line < p.nlines;  // padding lanes compute on the padding lines (kept finite)
     const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256) k_step1d_hoist(Step1dParams p, const doub
   uint32_t seq = 0, oseq = 0;
   const int NC = (n + CH - 1) / CH;
 
-  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+  for (long long blk = p.blk0 + warp; blk < p.nblocks; blk += p.nwarps) {
     const long long line = blk * GS_LB + lane;
     const bool valid = line < p.nlines;
     const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(128, 3) k_step1d_hoist_ck(Step1dParams p, cons
   const int NB = (n + K - 1) / K;
   const double c_last = L.tab[4 * (size_t)n];
 
-  for (long long blk = warp; blk < p.nblocks; blk += p.nwarps) {
+  for (long long blk = p.blk0 + warp; blk < p.nblocks; blk += p.nwarps) {
     const long long line = blk * GS_LB + lane;
     const bool valid = line < p.nlines;
     const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
@@ -1180,6 +1180,14 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
   cudaFree(g->rightT);
   cudaFree(g->scratch);
   cudaFree(g->hoist_table);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(g->hs_stage_in[i]);
+    cudaFree(g->hs_stage_out[i]);
+  }
+  if (g->hs_init) {
+    cudaStreamDestroy(g->hs_in);
+    cudaStreamDestroy(g->hs_out);
+  }
   cudaFree(g->status);
   delete g;
   return GS_OK;
@@ -1287,17 +1295,11 @@ extern "C" int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double 
   return GS_OK;
 }
 
-extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
-  GS_REQUIRE(g != nullptr, "NULL argument");
-  GS_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
-  GS_REQUIRE(g->bc_set, "gs_grid1d_set_bc has not been called");
-  if (nsteps == 0) return GS_OK;
+// steps the line blocks [blk0, blk1) (all of them for the public entry point)
+static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, long long blk1) {
   gs_ctx *ctx = g->ctx;
-  GS_TRY(gs_ctx_use(ctx));
-  GS_TRY(gs_ctx_sync_pool(ctx));
-
   int block = (int)std::max<int64_t>(32, std::min<int64_t>(256, ctx->opt_block_1d / 32 * 32));
-  long long nblocks = g->pitch / GS_LB;
+  long long nblocks = blk1 - blk0;
   // resident line threads per SM: measured optimum per path on B200 (profiles/): the hoisted kernel is
   // DRAM-bound from 7 warps/SM on, the general one wants every warp its shared-memory ring allows
   const bool hoist_path = g->all_const && ctx->opt_const_hoist && ctx->opt_pipeline;
@@ -1316,7 +1318,8 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   Step1dParams p;
   p.n = g->n;
   p.nlines = g->nlines;
-  p.nblocks = nblocks;
+  p.blk0 = blk0;
+  p.nblocks = blk1;
   p.nwarps = nwarps;
   p.allow_fast = ctx->opt_native_div ? 0 : 1;
   p.grid = g->grid;
@@ -1427,6 +1430,91 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   }
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
+extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
+  GS_REQUIRE(g != nullptr, "NULL argument");
+  GS_REQUIRE(nsteps >= 0, "nsteps must be >= 0");
+  GS_REQUIRE(g->bc_set, "gs_grid1d_set_bc has not been called");
+  if (nsteps == 0) return GS_OK;
+  GS_TRY(gs_ctx_use(g->ctx));
+  GS_TRY(gs_ctx_sync_pool(g->ctx));
+  return step_blocks(g, time, nsteps, 0, g->pitch / GS_LB);
+}
+
+// The reference-facing call with HOST state: what a drop-in OneDGrid.step does when user code owns the public
+// `grid` array: upload grid, step, download grid.  `predict` is private to the grid object
+// and stays on the device.  Lines are independent, so the batch is cut into chunks of whole line blocks and
+// pipelined over three streams: H2D of chunk k+1, transposes + step of chunk k and D2H of chunk k-1 overlap
+// (PCIe is full duplex).  host_grid is LINE_MAJOR, updated in place; pinned memory is needed for real overlap.
+extern "C" int gs_grid1d_step_host(gs_grid1d *g, double time, int nsteps, double *host_grid, const double *leftT,
+                                   const double *rightT, int bc_stride) {
+  GS_REQUIRE(g && host_grid && leftT && rightT, "NULL argument");
+  GS_REQUIRE(nsteps >= 1, "nsteps must be >= 1");
+  gs_ctx *ctx = g->ctx;
+  GS_TRY(gs_ctx_use(ctx));
+  GS_TRY(gs_ctx_sync_pool(ctx));
+  GS_TRY(gs_grid1d_set_bc(g, leftT, rightT, bc_stride));
+  const size_t line_bytes = (size_t)g->n * sizeof(double);
+  long long chunk = std::max<long long>(GS_LB, (long long)(ctx->opt_host_chunk_mb << 20) / (long long)line_bytes / GS_LB * GS_LB);
+  chunk = std::min<long long>(chunk, g->pitch);
+  const size_t cbytes = (size_t)chunk * line_bytes;
+  if (!g->hs_init) {
+    GS_CUDA(cudaStreamCreateWithFlags(&g->hs_in, cudaStreamNonBlocking));
+    GS_CUDA(cudaStreamCreateWithFlags(&g->hs_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      GS_CUDA(cudaEventCreateWithFlags(&g->hs_in_done[i], cudaEventDisableTiming));
+      GS_CUDA(cudaEventCreateWithFlags(&g->hs_in_free[i], cudaEventDisableTiming));
+      GS_CUDA(cudaEventCreateWithFlags(&g->hs_out_ready[i], cudaEventDisableTiming));
+      GS_CUDA(cudaEventCreateWithFlags(&g->hs_out_free[i], cudaEventDisableTiming));
+    }
+    GS_CUDA(cudaEventCreateWithFlags(&g->hs_start, cudaEventDisableTiming));
+    g->hs_init = true;
+  }
+  if (g->hs_bytes < cbytes) {
+    GS_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(g->hs_stage_in[i]);
+      cudaFree(g->hs_stage_out[i]);
+      GS_CUDA(cudaMalloc(&g->hs_stage_in[i], cbytes));
+      GS_CUDA(cudaMalloc(&g->hs_stage_out[i], cbytes));
+    }
+    g->hs_bytes = cbytes;
+  }
+  // the side streams start after everything already queued on the context stream
+  GS_CUDA(cudaEventRecord(g->hs_start, ctx->stream));
+  GS_CUDA(cudaStreamWaitEvent(g->hs_in, g->hs_start, 0));
+  GS_CUDA(cudaStreamWaitEvent(g->hs_out, g->hs_start, 0));
+  long long k = 0;
+  for (long long l0 = 0; l0 < g->nlines; l0 += chunk, ++k) {
+    const int L = (int)std::min<long long>(chunk, g->nlines - l0);
+    const int sl = (int)(k & 1);
+    // H2D (stream in)
+    if (k >= 2) GS_CUDA(cudaStreamWaitEvent(g->hs_in, g->hs_in_free[sl], 0));
+    GS_CUDA(cudaMemcpyAsync(g->hs_stage_in[sl], host_grid + (size_t)l0 * g->n, (size_t)L * line_bytes,
+                            cudaMemcpyHostToDevice, g->hs_in));
+    GS_CUDA(cudaEventRecord(g->hs_in_done[sl], g->hs_in));
+    // transposes + step (context stream)
+    GS_CUDA(cudaStreamWaitEvent(ctx->stream, g->hs_in_done[sl], 0));
+    dim3 blk(32, 8), grd((g->n + 31) / 32, (L + 31) / 32);
+    k_lines_to_interleaved<<<grd, blk, 0, ctx->stream>>>(g->hs_stage_in[sl], g->grid, L, g->n, g->pitch, l0);
+    GS_CUDA(cudaEventRecord(g->hs_in_free[sl], ctx->stream));
+    GS_TRY(step_blocks(g, time, nsteps, l0 / GS_LB, (l0 + L + GS_LB - 1) / GS_LB));
+    if (k >= 2) GS_CUDA(cudaStreamWaitEvent(ctx->stream, g->hs_out_free[sl], 0));
+    k_interleaved_to_lines<<<grd, blk, 0, ctx->stream>>>(g->grid, g->hs_stage_out[sl], L, g->n, g->pitch, l0);
+    ctx->launches += 2;
+    GS_CUDA(cudaGetLastError());
+    GS_CUDA(cudaEventRecord(g->hs_out_ready[sl], ctx->stream));
+    // D2H (stream out)
+    GS_CUDA(cudaStreamWaitEvent(g->hs_out, g->hs_out_ready[sl], 0));
+    GS_CUDA(cudaMemcpyAsync(host_grid + (size_t)l0 * g->n, g->hs_stage_out[sl], (size_t)L * line_bytes,
+                            cudaMemcpyDeviceToHost, g->hs_out));
+    GS_CUDA(cudaEventRecord(g->hs_out_free[sl], g->hs_out));
+  }
+  // the context stream (and therefore the caller) sees the last download
+  for (int i = 0; i < 2 && i < k; ++i) GS_CUDA(cudaStreamWaitEvent(ctx->stream, g->hs_out_free[i], 0));
+  GS_CUDA(cudaStreamSynchronize(ctx->stream));
   return GS_OK;
 }
 

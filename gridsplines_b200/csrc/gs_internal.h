@@ -60,6 +60,7 @@ struct gs_ctx {
   int64_t opt_pipe_cfg = 0;
   int64_t opt_seg_len = 32;
   int64_t opt_hoist_ck = 1;
+  int64_t opt_host_chunk_mb = 128;
   int64_t opt_ck_block = 16;
 };
 
@@ -82,6 +83,12 @@ struct gs_grid1d {
   bool bc_set = false;
   double2 *scratch = nullptr;
   size_t scratch_elems = 0;
+  // gs_grid1d_step_host pipeline (H2D / compute / D2H on three streams)
+  bool hs_init = false;
+  cudaStream_t hs_in = nullptr, hs_out = nullptr;
+  cudaEvent_t hs_in_done[2], hs_in_free[2], hs_out_ready[2], hs_out_free[2], hs_start;
+  double *hs_stage_in[2] = {nullptr, nullptr}, *hs_stage_out[2] = {nullptr, nullptr};
+  size_t hs_bytes = 0;
   double *hoist_table = nullptr;  // K2h coefficients for hoist_time
   bool hoist_valid = false;
   double hoist_time = 0.0;

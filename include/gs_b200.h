@@ -138,6 +138,11 @@ int gs_grid1d_fill(gs_grid1d *g, int which, double value);
 int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double *rightT, int stride);
 /* nsteps x OneDGrid.step(time, leftT, rightT) (A/OneDGrid.scala:26-34) for every line */
 int gs_grid1d_step(gs_grid1d *g, double time, int nsteps);
+/* The drop-in OneDGrid.step with HOST state (the public `grid` array, A/OneDGrid.scala:20): upload grid, nsteps
+ * steps, download grid -- chunked over line blocks and pipelined (H2D / compute / D2H overlap).  host_grid is
+ * LINE_MAJOR [nlines][n], updated in place; `predict` (private in the reference) stays on the device. */
+int gs_grid1d_step_host(gs_grid1d *g, double time, int nsteps, double *host_grid, const double *leftT,
+                        const double *rightT, int bc_stride);
 int gs_grid1d_set_solver(gs_grid1d *g, int solver);
 int gs_grid1d_status(gs_grid1d *g, uint32_t *flags);
 int gs_grid1d_clear_status(gs_grid1d *g);

@@ -171,3 +171,27 @@ def test_large_batch_properties(gs):
     assert np.all(out.view(np.uint64) == out[0].view(np.uint64)[None, :])
     assert out.min() >= 0.0 and out.max() <= 30.0
     assert g.status == 0
+
+
+@pytest.mark.parametrize("chunk_mb,spline", [(128, "const"), (1, "const"), (1, "hermite")])
+def test_step_host_pipeline(O, gs, ctx, chunk_mb, spline):
+    """gs_grid1d_step_host = the drop-in OneDGrid.step with the public `grid` array on the host: upload, step,
+    download, pipelined over line chunks.  Two calls in a row (state: host grid + device-private predict)."""
+    ctx.set_option("host_chunk_mb", chunk_mb)
+    try:
+        nlines, n = 3000, 64
+        s = cases.batch_setup(nlines, n, random_grid=True)
+        mk = (lambda m: m.Spline.const(1e-6)) if spline == "const" else (
+            lambda m: m.Spline.m1Hermite3([(-20.0 + 10.0 * i, 1e-6 * (1.0 + 0.1 * (i + 1))) for i in range(11)]))
+        g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], mk(gs), 1.0, nlines=nlines)
+        host = s["grid0"].copy()
+        og, op = s["grid0"].copy(), np.full((nlines, n), 4.0)
+        for _ in range(2):
+            g.step_host(900.0, host, s["leftT"], s["rightT"], nsteps=2)
+            O.batch1d_step(0, s["leftX"], s["rangeX"], s["rightX"], mk(O), 1.0, og, op, s["leftT"], s["rightT"], 900.0,
+                           nsteps=2)
+            assert_bit_equal(host, og, "step_host grid")
+        assert_bit_equal(g.download(gs.PREDICT), op, "device-private predict")
+        assert g.status == 0
+    finally:
+        ctx.set_option("host_chunk_mb", 128)
