@@ -60,7 +60,19 @@ def test_spline_undefined_is_flagged(gs, ctx):
     g.grid = [1.0, float("nan"), 2.0]
     g.step(900.0, 1.0, 2.0)
     assert g.status & gs.FLAG_NONFINITE
-    g2 = gs.OneDGrid(0.0, [0.1, 0.2, 0.3], 0.4, gs.Spline.const(1e-6), 1.0)
+    # a NaN temperature reaches Spline.apply: RuntimeException in the reference (AbsITree.scala:475-479)
+    lin = gs.Spline.lines([(-50.0, 1e-6), (50.0, 2e-6), (150.0, 3e-6)])
+    g2 = gs.OneDGrid(0.0, [0.1, 0.2, 0.3], 0.4, lin, 1.0)
     g2.upload(gs.PREDICT, np.array([[1.0, float("nan"), 2.0]]))
     g2.step(900.0, 1.0, 2.0)
-    assert g2.status & gs.FLAG_SPLINE_UNDEFINED  # RuntimeException in the reference (AbsITree.scala:475-479)
+    assert g2.status & gs.FLAG_SPLINE_UNDEFINED
+    # same with a constant spline on the general path; the hoisted path (default for constant properties) never
+    # reads predict, so it cannot see that NaN (documented in DESIGN.md section 4)
+    ctx.set_option("const_hoist", 0)
+    try:
+        g3 = gs.OneDGrid(0.0, [0.1, 0.2, 0.3], 0.4, gs.Spline.const(1e-6), 1.0)
+        g3.upload(gs.PREDICT, np.array([[1.0, float("nan"), 2.0]]))
+        g3.step(900.0, 1.0, 2.0)
+        assert g3.status & gs.FLAG_SPLINE_UNDEFINED
+    finally:
+        ctx.set_option("const_hoist", 1)
