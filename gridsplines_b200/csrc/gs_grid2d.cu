@@ -21,6 +21,7 @@
 
 #include "gs_device.cuh"
 #include "gs_internal.h"
+#include "gs_grid2d_k5.cuh"
 
 int gs_launch_predef(gs_ctx *ctx, int dir, const double *values_dev, int n, double sigma, double *coefs_dev);
 int gs_launch_heatflow(gs_ctx *ctx, int dir, const double *values_dev, int n, double *out4_dev);
@@ -929,6 +930,12 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->scratch);
   cudaFree(g->iface);
   cudaFree(g->predict_alt);
+  for (gs_k5dir *kd : {&g->k5x, &g->k5y}) {
+    cudaFree(kd->tab);
+    cudaFree(kd->omega_end);
+    cudaFree(kd->seg);
+    cudaFree(kd->ends);
+  }
   cudaFree(g->status);
   delete g;
   return GS_OK;
@@ -1238,10 +1245,120 @@ static int launch_part(gs_grid2d *g, double time, bool xdir, bool fuse) {
   return GS_OK;
 }
 
+// ---- K5: hoisted sweeps for literal-constant coefficients --------------------------------------------------
+static bool literal_const(gs_ctx *ctx, int off, double *value) {
+  const double *h = ctx->pool.data() + off;
+  bool lit = (int)h[0] == GS_CONST && (int)h[1] == 1 && h[2] == -1.7976931348623157e308 && h[3] == h[2] &&
+             h[4] == h[GS_HDR + 3] && h[5] == h[GS_HDR + 3] && h[GS_HDR] == h[2] && h[GS_HDR + 1] == -h[2];
+  if (lit && value) *value = h[GS_HDR + 3];
+  return lit;
+}
+
+static void k5_shape(int n, int *m, int *S) {
+  int s = std::max(2, std::min(16, n / 256));
+  int mm = ((n + s - 1) / s + K5_CH - 1) / K5_CH * K5_CH;
+  *m = mm;
+  *S = (n + mm - 1) / mm;
+}
+static size_t k5_smem(bool xdir, int m, int S) {
+  size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
+  return ((size_t)3 * S * 32 + (size_t)S * (tile + (size_t)(m / K5_CH) * 32)) * sizeof(double);
+}
+
+static bool use_k5(gs_grid2d *g, bool xdir) {
+  gs_ctx *ctx = g->ctx;
+  if (g->solver == GS_SOLVER_THOMAS || !ctx->opt_k5) return false;
+  const int n = xdir ? g->cols : g->rows;
+  if (n < (g->solver == GS_SOLVER_PARTITIONED ? 128 : 256)) return false;  // AUTO keeps short lines bit-exact
+  for (int s = 0; s < 4; ++s) {
+    if (g->map_mode[s] != GS_MAP_SINGLE) return false;
+    if (!literal_const(ctx, ctx->spline_off[g->map_host[s][0]], nullptr)) return false;
+  }
+  int m, S;
+  k5_shape(n, &m, &S);
+  return S >= 2 && k5_smem(xdir, m, S) <= ctx->smem_optin;
+}
+
+static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
+  gs_ctx *ctx = g->ctx;
+  gs_k5dir &kd = xdir ? g->k5x : g->k5y;
+  const gs_dim2d &d = xdir ? g->x : g->y;
+  const int n = d.n;
+  const int sf = xdir ? GS_LEFT : GS_UPP, sl = xdir ? GS_RIGHT : GS_LOW;
+  if (kd.valid && kd.time == time && kd.kind_first == g->b[sf].kind && kd.kind_last == g->b[sl].kind &&
+      kd.pool_gen == ctx->spline_off.size())
+    return GS_OK;
+  k5_shape(n, &kd.m, &kd.S);
+  if (!kd.tab) {
+    GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
+    GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
+    GS_CUDA(cudaMalloc(&kd.seg, 64 * sizeof(double4)));
+    GS_CUDA(cudaMalloc(&kd.ends, 4 * sizeof(double)));
+  }
+  K5Setup q;
+  q.n = n; q.m = kd.m; q.S = kd.S; q.dir_x = xdir ? 1 : 0;
+  q.coefs = d.coefs;
+  q.firstVol = d.hf[0]; q.fC = d.hf[1]; q.lastVol = d.hf[2]; q.lA = d.hf[3];
+  q.kind_first = g->b[sf].kind; q.kind_last = g->b[sl].kind;
+  double va, vth, vc, vt;
+  literal_const(ctx, ctx->spline_off[g->map_host[GS_SEL_APPLY][0]], &va);
+  literal_const(ctx, ctx->spline_off[g->map_host[GS_SEL_THERM][0]], &vth);
+  literal_const(ctx, ctx->spline_off[g->map_host[GS_SEL_CAP][0]], &vc);
+  literal_const(ctx, ctx->spline_off[g->map_host[GS_SEL_TEMPCOND][0]], &vt);
+  q.v_apply = va; q.v_first_cond = xdir ? vth : vt; q.v_cap = vc; q.v_tempcond = vt;
+  q.time = time;
+  q.tab = kd.tab; q.omega_end = kd.omega_end; q.seg = kd.seg; q.ends = kd.ends; q.status = g->status;
+  k5_setup<<<1, 32, 0, ctx->stream>>>(q);
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  GS_CUDA(cudaMemcpyAsync(kd.ends_host, kd.ends, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GS_CUDA(cudaStreamSynchronize(ctx->stream));
+  kd.valid = true;
+  kd.time = time;
+  kd.kind_first = q.kind_first;
+  kd.kind_last = q.kind_last;
+  kd.pool_gen = ctx->spline_off.size();
+  return GS_OK;
+}
+
+static int launch_k5(gs_grid2d *g, double time, bool xdir) {
+  gs_ctx *ctx = g->ctx;
+  GS_TRY(k5_prepare(g, xdir, time));
+  gs_k5dir &kd = xdir ? g->k5x : g->k5y;
+  K5Params q;
+  q.d.n = xdir ? g->cols : g->rows;
+  q.d.nlines = xdir ? g->rows : g->cols;
+  q.d.m = kd.m; q.d.S = kd.S;
+  q.d.tab = kd.tab; q.d.omega_end = kd.omega_end; q.d.seg = kd.seg;
+  q.d.e0a = kd.ends_host[0]; q.d.e0b = kd.ends_host[1]; q.d.e1a = kd.ends_host[2]; q.d.e1b = kd.ends_host[3];
+  q.d.bound_first = g->b[xdir ? GS_LEFT : GS_UPP].values;
+  q.d.bound_last = g->b[xdir ? GS_RIGHT : GS_LOW].values;
+  q.cols = g->cols; q.rows = g->rows;
+  q.rhs = xdir ? g->grid : g->result;
+  q.out = g->result;
+  q.grid_io = g->grid;
+  q.predict_out = g->predict;
+  q.status = g->status;
+  size_t smem = k5_smem(xdir, kd.m, kd.S);
+  int blocks = (q.d.nlines + 31) / 32, threads = 32 * kd.S;
+  if (xdir) {
+    GS_CUDA(cudaFuncSetAttribute(k5_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_sweep<true><<<blocks, threads, smem, ctx->stream>>>(q);
+  } else {
+    GS_CUDA(cudaFuncSetAttribute(k5_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_sweep<false><<<blocks, threads, smem, ctx->stream>>>(q);
+  }
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
 static int sweep_x(gs_grid2d *g, double time) {
+  if (use_k5(g, true)) return launch_k5(g, time, true);
   return use_partitioned(g, g->cols) ? launch_part(g, time, true, false) : launch_xsweep(g, time);
 }
 static int sweep_y(gs_grid2d *g, double time, bool fuse) {
+  if (fuse && use_k5(g, false)) return launch_k5(g, time, false);   // K5's y sweep is always fused with Grid.update
   return use_partitioned(g, g->rows) ? launch_part(g, time, false, fuse) : launch_ysweep(g, time, fuse);
 }
 

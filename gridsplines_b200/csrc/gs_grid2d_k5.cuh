@@ -1,0 +1,301 @@
+// gs_grid2d_k5.cuh -- K5: 2-D sweeps for grids whose four coefficient selectors are one literal Spline.const each
+// (ConstantCoef over Spline.const values: config C3, AT/GridTest.scala).  Part of the tolerance solver family
+// (GS_SOLVER_PARTITIONED / AUTO): <= 1e-12 relative per field, not bit-exact.
+//
+// With constant properties the face value the reference computes, ((hi - lo) * v) / (hi - lo), equals v to one ulp,
+// so the tridiagonal matrix of a sweep is the same for every line: Row_i = (sub_i, diag_i, sup_i) depends on the node
+// only.  k5_setup eliminates it once per (grid, direction, time step) -- per segment of m nodes, restarting at every
+// segment start -- and stores per node
+//     alpha_i = kappa_i / Delta_i   beta_i = -sub_i / Delta_i   delta_i = -sup_i / Delta_i   p_i = prod delta
+// so that a line only runs  lambda_i = t_i * alpha_i + lambda_{i-1} * beta_i  (2 FP64 instructions per node),
+// Q = sum p_i lambda_i, and the back-substitution x_i = delta_i x_{i+1} + lambda_i.  The S x S reduced system that
+// stitches the segments has a line-independent matrix too; its factorisation is a table.
+//
+// One CTA owns 32 lines, one warp per segment:  phase A (lambda_e, Q per segment, lambda checkpoints per 32-node
+// chunk) -> __syncthreads -> reduced solve (warp 0, lane = line) -> __syncthreads -> phase C (per chunk, last to
+// first: re-read the chunk, recompute its lambdas from the checkpoint, back-substitute, store).  The y sweep applies
+// Grid.update on the way out (grid', predict'); predict is never read (coefficients do not depend on it).
+//   y sweep: lane <-> column, every node row of the strip is one coalesced 256 B access;
+//   x sweep: lane <-> row; 32 x 32 tiles are transposed through shared memory (coalesced 256 B row pieces both ways,
+//            33-double pitch = conflict-free).
+// DRAM traffic: x: read grid (A) + re-read (C, L2) + write result; y: read result (A) + re-read (C) + read grid +
+// write grid', predict'  =>  48 B/node when the re-reads hit L2, against 64 algorithmic bytes.
+#pragma once
+
+#define K5_CH 32  // nodes per chunk
+
+struct K5Dir {
+  int n, nlines, m, S;          // nodes per line, lines, segment length (multiple of K5_CH), segments
+  const double4 *tab;           // [n]  alpha, beta, delta, p
+  const double *omega_end;      // [n / K5_CH rounded up] omega at the last node of every chunk
+  const double4 *seg;           // [S]  delta_e, sub_r, 1/den, cp of the reduced system
+  double e0a, e0b, e1a, e1b;    // end-node terms: lambda_0 += (e0a * bound_first + e0b), lambda_{n-1} += (e1a * bound_last + e1b)
+  const double *bound_first, *bound_last;
+};
+
+struct K5Params {
+  K5Dir d;
+  int cols, rows;
+  const double *rhs;     // x: grid, y: result
+  double *out;           // x: result
+  double *grid_io;       // y: old grid in / new grid out
+  double *predict_out;   // y: new predict
+  unsigned *status;
+};
+
+// ---- setup: line-independent elimination ------------------------------------------------------------------
+struct K5Setup {
+  int n, m, S, dir_x;
+  const double *coefs;                    // Dim.coefs [2n]
+  double firstVol, fC, lastVol, lA;
+  int kind_first, kind_last;
+  double v_apply, v_first_cond, v_cap, v_tempcond;  // literal constants (first_cond: THERM for x, TEMPCOND for y)
+  double time;
+  double4 *tab;
+  double *omega_end;
+  double4 *seg;
+  double *ends;                           // e0a, e0b, e1a, e1b
+  unsigned *status;
+};
+
+__global__ void k5_setup(K5Setup q) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = q.n;
+  const double inv_time = 1.0 / q.time;
+  unsigned flags = 0;
+  double face = q.v_apply;   // value carried from node i-1's right face
+  // per-segment results needed by the reduced system
+  double prevP = 0.0, prevR = 0.0;  // of segment k+1 while walking k downwards: do two passes instead
+  // pass 1: rows, local elimination, tables; keep (delta_e, omega_e, P, R) per segment in q.seg temporarily
+  double delta = 0.0, omega = 0.0, p = 1.0, R = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int s = (i / q.m) * q.m, e = min(n, s + q.m) - 1;
+    double sub, diag, sup, kappa = -inv_time;
+    if (i == 0) {
+      if (q.kind_first == GS_TEMP) {           // Dim.first :28-43
+        double a = q.coefs[0] * q.v_apply;
+        sup = q.coefs[1] * q.v_apply;
+        sub = 0.0;
+        diag = -(a + sup) - inv_time;
+        q.ends[0] = -a;                        // rhs_0 = -t/tau - a * t1
+        q.ends[1] = 0.0;
+        face = q.v_apply;
+      } else {                                 // Dim.firstHeatFlow :46-64
+        double vol = q.firstVol * q.v_cap / q.time;
+        sup = -q.v_first_cond * q.fC;
+        sub = 0.0;
+        diag = vol - sup;
+        kappa = 0.0;                           // rhs_0 = vol + q
+        q.ends[0] = 1.0;
+        q.ends[1] = vol;
+        face = q.v_first_cond / q.v_cap;
+      }
+    } else if (i == n - 1) {
+      if (q.kind_last == GS_TEMP) {            // Dim.last :86-103
+        sub = q.coefs[2 * i] * face;
+        double c = q.coefs[2 * i + 1] * q.v_apply;
+        sup = 0.0;
+        diag = -(sub + c) - inv_time;
+        q.ends[2] = -c;                        // rhs = -t/tau - c * t3
+        q.ends[3] = 0.0;
+      } else {                                 // Dim.lastHeatFlow :106-128
+        double vol = q.v_cap * q.lastVol / q.time;
+        sub = -q.v_tempcond * q.lA;
+        sup = 0.0;
+        diag = vol - sub;
+        kappa = 0.0;                           // rhs = vol - q
+        q.ends[2] = -1.0;
+        q.ends[3] = vol;
+      }
+    } else {                                   // Dim.general :67-83
+      sub = q.coefs[2 * i] * face;
+      sup = q.coefs[2 * i + 1] * q.v_apply;
+      diag = -(sub + sup) - inv_time;
+      if (!(fabs(diag) >= fabs(sup) + fabs(sub))) flags |= GS_FLAG_NOT_DOMINANT;
+      face = q.v_apply;
+    }
+    if (i == s) {
+      delta = 0.0;
+      omega = 1.0;   // so that omega_s = -sub_s / Delta_s below
+      p = 1.0;
+      R = 0.0;
+    }
+    const double bigDelta = diag + sub * delta;   // Delta_s = diag_s (delta = 0 at a segment start)
+    const double inv = 1.0 / bigDelta;
+    const double beta = -sub * inv;
+    const double om = (s > 0) ? beta * omega : 0.0;   // omega_i = -(sub_i omega_{i-1}) / Delta_i
+    const double dl = -sup * inv;
+    q.tab[i] = make_double4(kappa * inv, beta, dl, p);
+    // end-node terms are multiplied by 1/Delta of their node
+    if (i == 0) { q.ends[0] *= inv; q.ends[1] *= inv; }
+    if (i == n - 1) { q.ends[2] *= inv; q.ends[3] *= inv; }
+    if (i < e) {          // the map x_s = P x_e + Q + R L gathers nodes s .. e-1
+      R = R + p * om;
+      p = p * dl;
+    }
+    delta = dl;
+    omega = om;
+    if ((i % K5_CH) == K5_CH - 1 || i == n - 1 || i == e) q.omega_end[i / K5_CH] = om;
+    if (i == e) q.seg[i / q.m] = make_double4(dl, om, p, R);   // delta_e, omega_e, P, R (temporary)
+  }
+  // pass 2: reduced system  sub_k E_{k-1} + diag_k E_k + sup_k E_{k+1} = lambda_e^k + delta_e^k Q^{k+1}
+  double cp = 0.0;
+  for (int k = 0; k < q.S; ++k) {
+    double4 me = q.seg[k];
+    double Pn = 0.0, Rn = 0.0;
+    if (k + 1 < q.S) { Pn = q.seg[k + 1].z; Rn = q.seg[k + 1].w; }
+    double subr = -me.y, diagr = 1.0 - me.x * Rn, supr = -(me.x * Pn);
+    double den = diagr - subr * cp;
+    cp = supr / den;
+    // overwrite in place: segment k+1's (P, R) are still intact (different element)
+    q.seg[k] = make_double4(me.x, subr, 1.0 / den, cp);
+    // keep P, R of k+1 readable: they live in q.seg[k+1].z/.w until iteration k+1 rewrites that element
+  }
+  (void)prevP; (void)prevR;
+  if (flags) atomicOr(q.status, flags);
+}
+
+// ---- sweep ---------------------------------------------------------------------------------------------------
+template <bool XDIR>
+struct K5Tile {
+  static constexpr int PITCH = XDIR ? 33 : 32;
+  static constexpr int DOUBLES = K5_CH * PITCH;
+};
+
+// chunk [i0, i0 + len) of the warp's 32 lines -> tile[j * PITCH + lane]
+template <bool XDIR>
+__device__ __forceinline__ void k5_load(const K5Params &q, const double *src, int line0, int nl, int i0, int len,
+                                        double *tile, int lane) {
+  constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  if (XDIR) {
+    if (lane < len) {
+      const double *g = src + (size_t)line0 * q.cols + i0 + lane;
+#pragma unroll 8
+      for (int r = 0; r < nl; ++r) tile[lane * PITCH + r] = g[(size_t)r * q.cols];
+    }
+  } else {
+    if (lane < nl) {
+      const double *g = src + (size_t)i0 * q.cols + line0 + lane;
+#pragma unroll 8
+      for (int j = 0; j < len; ++j) tile[j * PITCH + lane] = g[(size_t)j * q.cols];
+    }
+  }
+}
+template <bool XDIR>
+__device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int line0, int nl, int i0, int len,
+                                           const double *tile, int lane) {
+  constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  if (lane < len) {
+    double *g = dst + (size_t)line0 * q.cols + i0 + lane;
+#pragma unroll 8
+    for (int r = 0; r < nl; ++r) g[(size_t)r * q.cols] = tile[lane * PITCH + r];
+  }
+}
+
+template <bool XDIR>
+__global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
+  extern __shared__ __align__(16) double k5sm[];
+  constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  const K5Dir &d = q.d;
+  const int S = d.S, m = d.m, n = d.n;
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment k
+  const int line0 = blockIdx.x * 32, nl = min(32, d.nlines - line0);
+  const int nch_max = m / K5_CH;
+  // shared memory: per CTA lamE[S][32], Q[S][32], E[S][32]; per warp tile[DOUBLES] + ckpt[nch_max][32]
+  double *lamE = k5sm, *Qs = lamE + S * 32, *Es = Qs + S * 32;
+  double *wbase = Es + S * 32 + (size_t)k * (K5Tile<XDIR>::DOUBLES + nch_max * 32);
+  double *tile = wbase, *ckpt = wbase + K5Tile<XDIR>::DOUBLES;
+  const int s = k * m, e = min(n, s + m) - 1;
+  const int nch = (e >= s) ? (e - s) / K5_CH + 1 : 0;
+  const bool act = lane < nl;
+  const int line = line0 + (act ? lane : 0);
+  // end-node terms of this line
+  const double ex0 = d.e0a * d.bound_first[line] + d.e0b;
+  const double ex1 = d.e1a * d.bound_last[line] + d.e1b;
+
+  // ---- phase A ----
+  double lam = 0.0, Qacc = 0.0;
+  for (int c = 0; c < nch; ++c) {
+    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    __syncwarp();
+    k5_load<XDIR>(q, q.rhs, line0, nl, i0, len, tile, lane);
+    __syncwarp();
+    const double4 *t = d.tab + i0;
+    for (int j = 0; j < len; ++j) {
+      const double4 c4 = t[j];
+      lam = fma(tile[j * PITCH + lane], c4.x, lam * c4.y);
+      if (i0 + j == 0) lam += ex0;
+      if (i0 + j == n - 1) lam += ex1;
+      if (i0 + j < e) Qacc = fma(c4.w, lam, Qacc);
+    }
+    ckpt[c * 32 + lane] = lam;
+  }
+  lamE[k * 32 + lane] = lam;
+  Qs[k * 32 + lane] = Qacc;
+  __syncthreads();
+  // ---- reduced system (warp 0; lane = line) ----
+  if (k == 0) {
+    double dp = 0.0;
+    for (int kk = 0; kk < S; ++kk) {
+      const double4 sg = d.seg[kk];
+      double rhs = lamE[kk * 32 + lane] + ((kk + 1 < S) ? sg.x * Qs[(kk + 1) * 32 + lane] : 0.0);
+      dp = (rhs - sg.y * dp) * sg.z;
+      Es[kk * 32 + lane] = dp;
+    }
+    double x = 0.0;
+    for (int kk = S - 1; kk >= 0; --kk) {
+      x = Es[kk * 32 + lane] - d.seg[kk].w * x;
+      Es[kk * 32 + lane] = x;
+    }
+  }
+  __syncthreads();
+  // ---- phase C ----
+  if (nch == 0) return;
+  const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : 0.0;
+  double x = Es[k * 32 + lane];   // x_e
+  unsigned bad = 0;
+  for (int c = nch - 1; c >= 0; --c) {
+    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    __syncwarp();
+    k5_load<XDIR>(q, q.rhs, line0, nl, i0, len, tile, lane);
+    __syncwarp();
+    const double4 *t = d.tab + i0;
+    // lambda at the start of the chunk: phase A's checkpoint plus the left-neighbour term omega * L
+    double lm = (c > 0) ? ckpt[(c - 1) * 32 + lane] + d.omega_end[(i0 - 1) / K5_CH] * L : L;
+    for (int j = 0; j < len; ++j) {
+      const double4 c4 = t[j];
+      lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
+      if (i0 + j == 0) lm += ex0;
+      if (i0 + j == n - 1) lm += ex1;
+      tile[j * PITCH + lane] = lm;
+    }
+    if (XDIR) {
+      for (int j = len - 1; j >= 0; --j) {
+        if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
+        tile[j * PITCH + lane] = x;
+      }
+      __syncwarp();
+      k5_store_x<XDIR>(q, q.out, line0, nl, i0, len, tile, lane);
+    } else if (act) {
+      double *G = q.grid_io + (size_t)i0 * q.cols + line, *P = q.predict_out + (size_t)i0 * q.cols + line;
+      // old grid values in batches of 8 (all loads of a batch in flight before its stores)
+      for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
+        double gold[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.cols] : 0.0;
+#pragma unroll
+        for (int u = 7; u >= 0; --u) {
+          const int j = jb + u;
+          if (j < len) {
+            if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
+            const double dl = x - gold[u];                     // Grid.update :474-481, aVal :508-512
+            P[(size_t)j * q.cols] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
+            G[(size_t)j * q.cols] = x;
+          }
+        }
+      }
+    }
+  }
+  if (act && !(fabs(x) <= 1.7976931348623157e308)) bad = GS_FLAG_NONFINITE;
+  if (bad) atomicOr(q.status, bad);
+}

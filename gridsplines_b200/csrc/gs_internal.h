@@ -60,6 +60,7 @@ struct gs_ctx {
   int64_t opt_pipe_cfg = 0;
   int64_t opt_seg_len = 32;
   int64_t opt_hoist_ck = 1;
+  int64_t opt_k5 = 1;
   int64_t opt_host_chunk_mb = 128;
   int64_t opt_ck_block = 16;
 };
@@ -103,6 +104,17 @@ struct gs_dim2d {
   double hf[4] = {0, 0, 0, 0};  // firstVol, fC, lastVol, lA
 };
 
+// K5 (hoisted sweeps for literal-constant coefficients): per-direction tables, valid for one time step
+struct gs_k5dir {
+  bool valid = false;
+  double time = 0.0;
+  int kind_first = -1, kind_last = -1, m = 0, S = 0;
+  size_t pool_gen = 0;
+  double4 *tab = nullptr, *seg = nullptr;
+  double *omega_end = nullptr, *ends = nullptr;
+  double ends_host[4] = {0, 0, 0, 0};
+};
+
 struct gs_bound2d {
   int kind = GS_TEMP, rep = GS_SPARSE;
   double *values = nullptr;  // device, side length (SPARSE keeps the scalar broadcast)
@@ -123,6 +135,7 @@ struct gs_grid2d {
   double *iface = nullptr;        // partitioned solver: interface coefficients / values
   size_t iface_len = 0;
   double *predict_alt = nullptr;  // partitioned fused y sweep writes predict' here, then the two swap
+  gs_k5dir k5x, k5y;
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };

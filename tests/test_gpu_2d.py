@@ -285,3 +285,22 @@ def test_partitioned_gridtest_and_medium(O, gs, seg_len):
     for _ in range(3):
         o.iteration(900.0)
     _compare_tol(cases.snapshot(g), cases.snapshot(o), "512x384 auto")
+
+
+@pytest.mark.parametrize("cols,rows", [(128, 128), (130, 257), (512, 384), (1000, 140), (129, 1025)])
+@pytest.mark.parametrize("combo", ["TTTT", "FFFF", "TFFT", "FTTF"])
+def test_k5_hoisted_constant_coefficients(O, gs, cols, rows, combo):
+    """K5: literal Spline.const coefficients -> line-independent matrix, table-driven sweeps (tolerance solver)."""
+    p = cases.bc_problem(combo, xdir=1, ydir=0, cols=cols, rows=rows, coefs="const")
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_PARTITIONED)   # K5 for both directions at these sizes
+    g.iteration(900.0, nsteps=3)
+    for _ in range(3):
+        o.iteration(900.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K5 {cols}x{rows} {combo}")
+    # xIter alone (K5 x sweep) and yIter alone (general partitioned: K5's y sweep only exists fused)
+    g.xIter(900.0); o.xIter(900.0)
+    assert max_rel_err(g.grid.result, o.result) <= TOL
+    g.yIter(900.0); o.yIter(900.0)
+    assert max_rel_err(g.grid.result, o.result) <= TOL
+    assert g.status == 0
