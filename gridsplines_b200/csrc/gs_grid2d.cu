@@ -930,6 +930,7 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->scratch);
   cudaFree(g->iface);
   cudaFree(g->predict_alt);
+  cudaFree(g->k5_ckpt);
   for (gs_k5dir *kd : {&g->k5x, &g->k5y}) {
     cudaFree(kd->tab);
     cudaFree(kd->omega_end);
@@ -1262,7 +1263,8 @@ static void k5_shape(int n, int *m, int *S) {
 }
 static size_t k5_smem(bool xdir, int m, int S) {
   size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
-  return ((size_t)3 * S * 32 + (size_t)S * (tile + (size_t)(m / K5_CH) * 32)) * sizeof(double);
+  (void)m;
+  return ((size_t)3 * S * 32 + (size_t)S * (2 * tile + 8 * K5_CH)) * sizeof(double);
 }
 
 static bool use_k5(gs_grid2d *g, bool xdir) {
@@ -1339,6 +1341,18 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   q.grid_io = g->grid;
   q.predict_out = g->predict;
   q.status = g->status;
+  {
+    size_t need = ((size_t)q.d.n / K5_CH + 2) * (((size_t)q.d.nlines + 31) / 32 * 32);
+    if (g->k5_ckpt_len < need) {
+      GS_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(g->k5_ckpt);
+      g->k5_ckpt = nullptr;
+      g->k5_ckpt_len = 0;
+      GS_CUDA(cudaMalloc(&g->k5_ckpt, need * sizeof(double)));
+      g->k5_ckpt_len = need;
+    }
+    q.ckpt = g->k5_ckpt;
+  }
   size_t smem = k5_smem(xdir, kd.m, kd.S);
   int blocks = (q.d.nlines + 31) / 32, threads = 32 * kd.S;
   if (xdir) {

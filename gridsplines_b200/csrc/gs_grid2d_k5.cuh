@@ -22,7 +22,7 @@
 // write grid', predict'  =>  48 B/node when the re-reads hit L2, against 64 algorithmic bytes.
 #pragma once
 
-#define K5_CH 32  // nodes per chunk
+#define K5_CH 16  // nodes per chunk
 
 struct K5Dir {
   int n, nlines, m, S;          // nodes per line, lines, segment length (multiple of K5_CH), segments
@@ -40,6 +40,7 @@ struct K5Params {
   double *out;           // x: result
   double *grid_io;       // y: old grid in / new grid out
   double *predict_out;   // y: new predict
+  double *ckpt;          // [n / K5_CH][nlines rounded up to 32] lambda checkpoints (0.5 B/node each way, L2)
   unsigned *status;
 };
 
@@ -162,24 +163,44 @@ struct K5Tile {
   static constexpr int DOUBLES = K5_CH * PITCH;
 };
 
-// chunk [i0, i0 + len) of the warp's 32 lines -> tile[j * PITCH + lane]
+__device__ __forceinline__ void k5_cp8(double *smem_dst, const double *gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void k5_cp16(void *smem_dst, const void *gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void k5_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void k5_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// asynchronous (cp.async) fetch of chunk [i0, i0 + len) of the warp's 32 lines -> tile[j * PITCH + lane], and of the
+// chunk's table entries -> tabs[j]; one commit group per chunk
 template <bool XDIR>
 __device__ __forceinline__ void k5_load(const K5Params &q, const double *src, int line0, int nl, int i0, int len,
-                                        double *tile, int lane) {
+                                        double *tile, double4 *tabs, int lane) {
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  if (lane < len) {
+    const char *tsrc = reinterpret_cast<const char *>(q.d.tab + i0 + lane);
+    char *tdst = reinterpret_cast<char *>(tabs + lane);
+    k5_cp16(tdst, tsrc);
+    k5_cp16(tdst + 16, tsrc + 16);
+  }
   if (XDIR) {
     if (lane < len) {
       const double *g = src + (size_t)line0 * q.cols + i0 + lane;
 #pragma unroll 8
-      for (int r = 0; r < nl; ++r) tile[lane * PITCH + r] = g[(size_t)r * q.cols];
+      for (int r = 0; r < nl; ++r) k5_cp8(&tile[lane * PITCH + r], g + (size_t)r * q.cols);
     }
   } else {
     if (lane < nl) {
       const double *g = src + (size_t)i0 * q.cols + line0 + lane;
 #pragma unroll 8
-      for (int j = 0; j < len; ++j) tile[j * PITCH + lane] = g[(size_t)j * q.cols];
+      for (int j = 0; j < len; ++j) k5_cp8(&tile[j * PITCH + lane], g + (size_t)j * q.cols);
     }
   }
+  k5_commit();
 }
 template <bool XDIR>
 __device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int line0, int nl, int i0, int len,
@@ -200,12 +221,14 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const int S = d.S, m = d.m, n = d.n;
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment k
   const int line0 = blockIdx.x * 32, nl = min(32, d.nlines - line0);
-  const int nch_max = m / K5_CH;
   // shared memory: per CTA lamE[S][32], Q[S][32], E[S][32]; per warp tile[DOUBLES] + ckpt[nch_max][32]
   double *lamE = k5sm, *Qs = lamE + S * 32, *Es = Qs + S * 32;
-  double *wbase = Es + S * 32 + (size_t)k * (K5Tile<XDIR>::DOUBLES + nch_max * 32);
-  double *tile = wbase, *ckpt = wbase + K5Tile<XDIR>::DOUBLES;
+  double *wbase = Es + S * 32 + (size_t)k * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH);
+  double4 *tabs2 = reinterpret_cast<double4 *>(wbase);         // 2 x chunk table entries (coalesced load, LDS broadcast)
+  double *tile2 = wbase + 8 * K5_CH;
+  const size_t ck_pitch = (size_t)((d.nlines + 31) / 32) * 32;
   const int s = k * m, e = min(n, s + m) - 1;
+  double *ckpt = q.ckpt + (size_t)(s / K5_CH) * ck_pitch + line0 + lane;   // [chunk * ck_pitch]
   const int nch = (e >= s) ? (e - s) / K5_CH + 1 : 0;
   const bool act = lane < nl;
   const int line = line0 + (act ? lane : 0);
@@ -213,14 +236,22 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const double ex0 = d.e0a * d.bound_first[line] + d.e0b;
   const double ex1 = d.e1a * d.bound_last[line] + d.e1b;
 
-  // ---- phase A ----
+  // ---- phase A ----  (chunk c+1 is in flight while chunk c is processed)
   double lam = 0.0, Qacc = 0.0;
+  if (nch > 0) k5_load<XDIR>(q, q.rhs, line0, nl, s, min(K5_CH, e - s + 1), tile2, tabs2, lane);
   for (int c = 0; c < nch; ++c) {
     const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    double *tile = tile2 + (c & 1) * K5Tile<XDIR>::DOUBLES;
+    const double4 *t = tabs2 + (c & 1) * K5_CH;
+    if (c + 1 < nch) {
+      const int i1 = i0 + K5_CH;
+      k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile2 + ((c + 1) & 1) * K5Tile<XDIR>::DOUBLES,
+                    tabs2 + ((c + 1) & 1) * K5_CH, lane);
+      k5_wait<1>();
+    } else {
+      k5_wait<0>();
+    }
     __syncwarp();
-    k5_load<XDIR>(q, q.rhs, line0, nl, i0, len, tile, lane);
-    __syncwarp();
-    const double4 *t = d.tab + i0;
     for (int j = 0; j < len; ++j) {
       const double4 c4 = t[j];
       lam = fma(tile[j * PITCH + lane], c4.x, lam * c4.y);
@@ -228,7 +259,8 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       if (i0 + j == n - 1) lam += ex1;
       if (i0 + j < e) Qacc = fma(c4.w, lam, Qacc);
     }
-    ckpt[c * 32 + lane] = lam;
+    ckpt[(size_t)c * ck_pitch] = lam;
+    __syncwarp();
   }
   lamE[k * 32 + lane] = lam;
   Qs[k * 32 + lane] = Qacc;
@@ -254,14 +286,28 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : 0.0;
   double x = Es[k * 32 + lane];   // x_e
   unsigned bad = 0;
+  {
+    const int il = s + (nch - 1) * K5_CH;
+    k5_load<XDIR>(q, q.rhs, line0, nl, il, min(K5_CH, e - il + 1), tile2 + ((nch - 1) & 1) * K5Tile<XDIR>::DOUBLES,
+                  tabs2 + ((nch - 1) & 1) * K5_CH, lane);
+  }
+  double ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : 0.0;   // checkpoint before the last chunk
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    double *tile = tile2 + (c & 1) * K5Tile<XDIR>::DOUBLES;
+    const double4 *t = tabs2 + (c & 1) * K5_CH;
+    if (c > 0) {
+      const int i1 = i0 - K5_CH;
+      k5_load<XDIR>(q, q.rhs, line0, nl, i1, K5_CH, tile2 + ((c - 1) & 1) * K5Tile<XDIR>::DOUBLES,
+                    tabs2 + ((c - 1) & 1) * K5_CH, lane);
+      k5_wait<1>();
+    } else {
+      k5_wait<0>();
+    }
     __syncwarp();
-    k5_load<XDIR>(q, q.rhs, line0, nl, i0, len, tile, lane);
-    __syncwarp();
-    const double4 *t = d.tab + i0;
     // lambda at the start of the chunk: phase A's checkpoint plus the left-neighbour term omega * L
-    double lm = (c > 0) ? ckpt[(c - 1) * 32 + lane] + d.omega_end[(i0 - 1) / K5_CH] * L : L;
+    double lm = (c > 0) ? ck_next + d.omega_end[(i0 - 1) / K5_CH] * L : L;
+    if (c > 1) ck_next = ckpt[(size_t)(c - 2) * ck_pitch];   // for the next iteration
     for (int j = 0; j < len; ++j) {
       const double4 c4 = t[j];
       lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
@@ -276,6 +322,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       }
       __syncwarp();
       k5_store_x<XDIR>(q, q.out, line0, nl, i0, len, tile, lane);
+      __syncwarp();
     } else if (act) {
       double *G = q.grid_io + (size_t)i0 * q.cols + line, *P = q.predict_out + (size_t)i0 * q.cols + line;
       // old grid values in batches of 8 (all loads of a batch in flight before its stores)
@@ -295,6 +342,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
         }
       }
     }
+    __syncwarp();   // every lane is done with this chunk's buffers before the one after next is fetched into them
   }
   if (act && !(fabs(x) <= 1.7976931348623157e308)) bad = GS_FLAG_NONFINITE;
   if (bad) atomicOr(q.status, bad);

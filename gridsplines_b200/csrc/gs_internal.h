@@ -136,6 +136,8 @@ struct gs_grid2d {
   size_t iface_len = 0;
   double *predict_alt = nullptr;  // partitioned fused y sweep writes predict' here, then the two swap
   gs_k5dir k5x, k5y;
+  double *k5_ckpt = nullptr;
+  size_t k5_ckpt_len = 0;
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };
