@@ -188,10 +188,12 @@ __device__ __forceinline__ void k5_load(const K5Params &q, const double *src, in
     k5_cp16(tdst + 16, tsrc + 16);
   }
   if (XDIR) {
-    if (lane < len) {
-      const double *g = src + (size_t)line0 * q.cols + i0 + lane;
-#pragma unroll 8
-      for (int r = 0; r < nl; ++r) k5_cp8(&tile[lane * PITCH + r], g + (size_t)r * q.cols);
+    // K5_CH = 16 columns per row piece: two rows per warp instruction (lanes 0-15 even rows, 16-31 odd rows)
+    const int jj = lane & (K5_CH - 1);
+    if (jj < len) {
+      const double *g = src + (size_t)line0 * q.cols + i0 + jj;
+#pragma unroll 4
+      for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) k5_cp8(&tile[jj * PITCH + r], g + (size_t)r * q.cols);
     }
   } else {
     if (lane < nl) {
@@ -206,10 +208,11 @@ template <bool XDIR>
 __device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int line0, int nl, int i0, int len,
                                            const double *tile, int lane) {
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
-  if (lane < len) {
-    double *g = dst + (size_t)line0 * q.cols + i0 + lane;
-#pragma unroll 8
-    for (int r = 0; r < nl; ++r) g[(size_t)r * q.cols] = tile[lane * PITCH + r];
+  const int jj = lane & (K5_CH - 1);
+  if (jj < len) {
+    double *g = dst + (size_t)line0 * q.cols + i0 + jj;
+#pragma unroll 4
+    for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) g[(size_t)r * q.cols] = tile[jj * PITCH + r];
   }
 }
 
