@@ -1142,6 +1142,7 @@ extern "C" int gs_grid1d_create(gs_ctx *ctx, int64_t nlines, int n, int dir, dou
   } else {
     std::vector<int> offs(2 * (size_t)n);
     for (int i = 0; i < 2 * n; ++i) offs[i] = ctx->spline_off[spline_ids[i]];
+    g->node_off_host = offs;
     G1_CUDA(cudaMalloc(&g->node_off, offs.size() * sizeof(int)));
     G1_CUDA(cudaMemcpyAsync(g->node_off, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     G1_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1180,6 +1181,11 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
   cudaFree(g->rightT);
   cudaFree(g->scratch);
   cudaFree(g->hoist_table);
+  cudaFree(g->k5_ckpt);
+  cudaFree(g->k5.tab);
+  cudaFree(g->k5.omega_end);
+  cudaFree(g->k5.seg);
+  cudaFree(g->k5.ends);
   for (int i = 0; i < 2; ++i) {
     cudaFree(g->hs_stage_in[i]);
     cudaFree(g->hs_stage_out[i]);
@@ -1440,6 +1446,9 @@ extern "C" int gs_grid1d_step(gs_grid1d *g, double time, int nsteps) {
   if (nsteps == 0) return GS_OK;
   GS_TRY(gs_ctx_use(g->ctx));
   GS_TRY(gs_ctx_sync_pool(g->ctx));
+  // long lines with constant properties: segments + reduced system (K5, tolerance 1e-12) instead of one serial
+  // chain per line, which leaves most SMs idle (config C5: 4096 lines x 65536 nodes = 128 warps)
+  if (gs_k5_1d_usable(g)) return gs_k5_1d_step(g, time, nsteps);
   return step_blocks(g, time, nsteps, 0, g->pitch / GS_LB);
 }
 

@@ -1355,14 +1355,87 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   }
   size_t smem = k5_smem(xdir, kd.m, kd.S);
   int blocks = (q.d.nlines + 31) / 32, threads = 32 * kd.S;
+  q.cta_stride = 32;        // y sweep: a CTA owns 32 adjacent columns
+  q.pitch = g->cols;
+  q.bc_stride = 1;
   if (xdir) {
-    GS_CUDA(cudaFuncSetAttribute(k5_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k5_sweep<true><<<blocks, threads, smem, ctx->stream>>>(q);
+    GS_CUDA(cudaFuncSetAttribute(k5_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_sweep<true, false><<<blocks, threads, smem, ctx->stream>>>(q);
   } else {
-    GS_CUDA(cudaFuncSetAttribute(k5_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k5_sweep<false><<<blocks, threads, smem, ctx->stream>>>(q);
+    GS_CUDA(cudaFuncSetAttribute(k5_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_sweep<false, false><<<blocks, threads, smem, ctx->stream>>>(q);
   }
   ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
+// ---- K5 for long 1-D lines (config C5): the blocked 1-D layout is a stack of 32-column strips with pitch 32 ----
+bool gs_k5_1d_usable(gs_grid1d *g) {
+  gs_ctx *ctx = g->ctx;
+  if (!g->all_const || !ctx->opt_k5 || g->solver == GS_SOLVER_THOMAS) return false;
+  if (g->n < (g->solver == GS_SOLVER_PARTITIONED ? 128 : 2048)) return false;   // AUTO keeps short lines bit-exact
+  for (int i = 0; i < (g->spline_mode == GS_SPLINE_SINGLE ? 1 : 2 * g->n); ++i) {
+    int off = g->spline_mode == GS_SPLINE_SINGLE ? g->single_off : g->node_off_host[i];
+    if (!literal_const(ctx, off, nullptr)) return false;
+  }
+  int m, S;
+  k5_shape(g->n, &m, &S);
+  return S >= 2 && k5_smem(false, m, S) <= ctx->smem_optin;
+}
+
+int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
+  gs_ctx *ctx = g->ctx;
+  gs_k5dir &kd = g->k5;
+  const int n = g->n;
+  if (!(kd.valid && kd.time == time)) {
+    k5_shape(n, &kd.m, &kd.S);
+    if (!kd.tab) {
+      GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
+      GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
+      GS_CUDA(cudaMalloc(&kd.seg, 64 * sizeof(double4)));
+      GS_CUDA(cudaMalloc(&kd.ends, 4 * sizeof(double)));
+      size_t need = ((size_t)n / K5_CH + 2) * (size_t)g->pitch;
+      GS_CUDA(cudaMalloc(&g->k5_ckpt, need * sizeof(double)));
+    }
+    K5Setup1d q;
+    q.n = n; q.m = kd.m; q.S = kd.S; q.mode = g->spline_mode;
+    q.predef = g->predef; q.pool = ctx->pool_dev; q.single_off = g->single_off; q.node_off = g->node_off;
+    q.time = time;
+    q.tab = kd.tab; q.omega_end = kd.omega_end; q.seg = kd.seg; q.ends = kd.ends; q.status = g->status;
+    k5_setup_1d<<<1, 32, 0, ctx->stream>>>(q);
+    ctx->launches++;
+    GS_CUDA(cudaGetLastError());
+    GS_CUDA(cudaMemcpyAsync(kd.ends_host, kd.ends, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GS_CUDA(cudaStreamSynchronize(ctx->stream));
+    kd.valid = true;
+    kd.time = time;
+  }
+  K5Params q;
+  q.d.n = n;
+  q.d.nlines = (int)g->nlines;
+  q.d.m = kd.m; q.d.S = kd.S;
+  q.d.tab = kd.tab; q.d.omega_end = kd.omega_end; q.d.seg = kd.seg;
+  q.d.e0a = kd.ends_host[0]; q.d.e0b = kd.ends_host[1]; q.d.e1a = kd.ends_host[2]; q.d.e1b = kd.ends_host[3];
+  q.d.bound_first = g->leftT;
+  q.d.bound_last = g->rightT;
+  q.cols = 32; q.rows = n;
+  q.rhs = g->grid;
+  q.out = nullptr;
+  q.grid_io = g->grid;
+  q.predict_out = g->predict;
+  q.ckpt = g->k5_ckpt;
+  q.cta_stride = (long long)n * 32;   // one 32-line block of the [line/32][node][line%32] layout per CTA
+  q.pitch = 32;
+  q.bc_stride = g->bc_stride;
+  q.status = g->status;
+  size_t smem = k5_smem(false, kd.m, kd.S);
+  int blocks = (int)(g->pitch / 32), threads = 32 * kd.S;
+  GS_CUDA(cudaFuncSetAttribute(k5_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int s = 0; s < nsteps; ++s) {
+    k5_sweep<false, true><<<blocks, threads, smem, ctx->stream>>>(q);
+    ctx->launches++;
+  }
   GS_CUDA(cudaGetLastError());
   return GS_OK;
 }

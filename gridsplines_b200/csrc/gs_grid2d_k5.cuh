@@ -41,6 +41,9 @@ struct K5Params {
   double *grid_io;       // y: old grid in / new grid out
   double *predict_out;   // y: new predict
   double *ckpt;          // [n / K5_CH][nlines rounded up to 32] lambda checkpoints (0.5 B/node each way, L2)
+  // lane <-> line sweeps (y sweep, 1-D batches): element (node i, lane) of CTA b is at b * cta_stride + i * pitch + lane
+  long long cta_stride, pitch;
+  int bc_stride;         // bound_first/last index = line * bc_stride (1-D batches: 0 = one value for all lines)
   unsigned *status;
 };
 
@@ -156,6 +159,64 @@ __global__ void k5_setup(K5Setup q) {
   if (flags) atomicOr(q.status, flags);
 }
 
+// 1-D batches (passion.iteration with constant conductivity): sub_i = v pd[2i], sup_i = v pd[2i+1]; Dirichlet ends
+struct K5Setup1d {
+  int n, m, S, mode;
+  const double *predef, *pool;
+  int single_off;
+  const int *node_off;
+  double time;
+  double4 *tab;
+  double *omega_end;
+  double4 *seg;
+  double *ends;
+  unsigned *status;
+};
+
+__global__ void k5_setup_1d(K5Setup1d q) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = q.n;
+  const double inv_time = 1.0 / q.time;
+  unsigned flags = 0;
+  double delta = 0.0, omega = 0.0, p = 1.0, R = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int s = (i / q.m) * q.m, e = min(n, s + q.m) - 1;
+    const int offa = q.mode == GS_SPLINE_SINGLE ? q.single_off : q.node_off[2 * i];
+    const int offc = q.mode == GS_SPLINE_SINGLE ? q.single_off : q.node_off[2 * i + 1];
+    const double a = q.pool[offa + GS_HDR + 3] * q.predef[2 * i];        // cons :21-25 with a constant spline
+    const double c = q.pool[offc + GS_HDR + 3] * q.predef[2 * i + 1];
+    const double diag = -(a + c) - inv_time;
+    const double sub = (i == 0) ? 0.0 : a, sup = (i == n - 1) ? 0.0 : c;
+    if (i > 0 && i < n - 1 && !(fabs(diag) >= fabs(c) + fabs(a))) flags |= GS_FLAG_NOT_DOMINANT;
+    if (i == 0) { q.ends[0] = -a; q.ends[1] = 0.0; }                    // rhs_0 = -t/tau - a * firstT  (:65)
+    if (i == n - 1) { q.ends[2] = -c; q.ends[3] = 0.0; }                // rhs   = -t/tau - c * lastT   (:89)
+    if (i == s) { delta = 0.0; omega = 1.0; p = 1.0; R = 0.0; }
+    const double inv = 1.0 / (diag + sub * delta);
+    const double beta = -sub * inv;
+    const double om = (s > 0) ? beta * omega : 0.0;
+    const double dl = -sup * inv;
+    q.tab[i] = make_double4(-inv_time * inv, beta, dl, p);
+    if (i == 0) { q.ends[0] *= inv; q.ends[1] *= inv; }
+    if (i == n - 1) { q.ends[2] *= inv; q.ends[3] *= inv; }
+    if (i < e) { R = R + p * om; p = p * dl; }
+    delta = dl;
+    omega = om;
+    if ((i % K5_CH) == K5_CH - 1 || i == n - 1 || i == e) q.omega_end[i / K5_CH] = om;
+    if (i == e) q.seg[i / q.m] = make_double4(dl, om, p, R);
+  }
+  double cp = 0.0;
+  for (int k = 0; k < q.S; ++k) {
+    double4 me = q.seg[k];
+    double Pn = 0.0, Rn = 0.0;
+    if (k + 1 < q.S) { Pn = q.seg[k + 1].z; Rn = q.seg[k + 1].w; }
+    double subr = -me.y, diagr = 1.0 - me.x * Rn, supr = -(me.x * Pn);
+    double den = diagr - subr * cp;
+    cp = supr / den;
+    q.seg[k] = make_double4(me.x, subr, 1.0 / den, cp);
+  }
+  if (flags) atomicOr(q.status, flags);
+}
+
 // ---- sweep ---------------------------------------------------------------------------------------------------
 template <bool XDIR>
 struct K5Tile {
@@ -197,9 +258,9 @@ __device__ __forceinline__ void k5_load(const K5Params &q, const double *src, in
     }
   } else {
     if (lane < nl) {
-      const double *g = src + (size_t)i0 * q.cols + line0 + lane;
+      const double *g = src + (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
 #pragma unroll 8
-      for (int j = 0; j < len; ++j) k5_cp8(&tile[j * PITCH + lane], g + (size_t)j * q.cols);
+      for (int j = 0; j < len; ++j) k5_cp8(&tile[j * PITCH + lane], g + (size_t)j * q.pitch);
     }
   }
   k5_commit();
@@ -216,7 +277,7 @@ __device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int l
   }
 }
 
-template <bool XDIR>
+template <bool XDIR, bool ONED>
 __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   extern __shared__ __align__(16) double k5sm[];
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
@@ -236,8 +297,8 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const bool act = lane < nl;
   const int line = line0 + (act ? lane : 0);
   // end-node terms of this line
-  const double ex0 = d.e0a * d.bound_first[line] + d.e0b;
-  const double ex1 = d.e1a * d.bound_last[line] + d.e1b;
+  const double ex0 = d.e0a * d.bound_first[(size_t)line * q.bc_stride] + d.e0b;
+  const double ex1 = d.e1a * d.bound_last[(size_t)line * q.bc_stride] + d.e1b;
 
   // ---- phase A ----  (chunk c+1 is in flight while chunk c is processed)
   double lam = 0.0, Qacc = 0.0;
@@ -327,20 +388,22 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       k5_store_x<XDIR>(q, q.out, line0, nl, i0, len, tile, lane);
       __syncwarp();
     } else if (act) {
-      double *G = q.grid_io + (size_t)i0 * q.cols + line, *P = q.predict_out + (size_t)i0 * q.cols + line;
+      const size_t off = (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
+      double *G = q.grid_io + off, *P = q.predict_out + off;
       // old grid values in batches of 8 (all loads of a batch in flight before its stores)
       for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
         double gold[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.cols] : 0.0;
+        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.pitch] : 0.0;
 #pragma unroll
         for (int u = 7; u >= 0; --u) {
           const int j = jb + u;
           if (j < len) {
             if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
-            const double dl = x - gold[u];                     // Grid.update :474-481, aVal :508-512
-            P[(size_t)j * q.cols] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
-            G[(size_t)j * q.cols] = x;
+            const double dl = x - gold[u];
+            if (ONED) P[(size_t)j * q.pitch] = x + dl / 3.0;                            // arraygrid.aVal :85-87
+            else P[(size_t)j * q.pitch] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;           // Grid.update :474-481, aVal :508-512
+            G[(size_t)j * q.pitch] = x;
           }
         }
       }

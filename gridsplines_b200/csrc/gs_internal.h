@@ -69,6 +69,17 @@ int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice
 int gs_ctx_sync_pool(gs_ctx *ctx);           // upload the spline pool if it changed
 int gs_ctx_stage(gs_ctx *ctx, size_t bytes); // make sure ctx->stage holds at least `bytes`
 
+// K5 (hoisted sweeps for literal-constant coefficients): per-direction tables, valid for one time step
+struct gs_k5dir {
+  bool valid = false;
+  double time = 0.0;
+  int kind_first = -1, kind_last = -1, m = 0, S = 0;
+  size_t pool_gen = 0;
+  double4 *tab = nullptr, *seg = nullptr;
+  double *omega_end = nullptr, *ends = nullptr;
+  double ends_host[4] = {0, 0, 0, 0};
+};
+
 struct gs_grid1d {
   gs_ctx *ctx = nullptr;
   int64_t nlines = 0, pitch = 0;
@@ -90,6 +101,9 @@ struct gs_grid1d {
   cudaEvent_t hs_in_done[2], hs_in_free[2], hs_out_ready[2], hs_out_free[2], hs_start;
   double *hs_stage_in[2] = {nullptr, nullptr}, *hs_stage_out[2] = {nullptr, nullptr};
   size_t hs_bytes = 0;
+  std::vector<int> node_off_host;  // PER_NODE pool offsets (host copy)
+  gs_k5dir k5;                     // K5 tables for long lines
+  double *k5_ckpt = nullptr;
   double *hoist_table = nullptr;  // K2h coefficients for hoist_time
   bool hoist_valid = false;
   double hoist_time = 0.0;
@@ -102,17 +116,6 @@ struct gs_dim2d {
   double *values = nullptr;  // [n+2] low ++ range ++ upp
   double *coefs = nullptr;   // [2n] Dim.coefs, sigma = 1.0
   double hf[4] = {0, 0, 0, 0};  // firstVol, fC, lastVol, lA
-};
-
-// K5 (hoisted sweeps for literal-constant coefficients): per-direction tables, valid for one time step
-struct gs_k5dir {
-  bool valid = false;
-  double time = 0.0;
-  int kind_first = -1, kind_last = -1, m = 0, S = 0;
-  size_t pool_gen = 0;
-  double4 *tab = nullptr, *seg = nullptr;
-  double *omega_end = nullptr, *ends = nullptr;
-  double ends_host[4] = {0, 0, 0, 0};
 };
 
 struct gs_bound2d {
@@ -141,3 +144,6 @@ struct gs_grid2d {
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };
+
+bool gs_k5_1d_usable(gs_grid1d *g);
+int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps);

@@ -36,7 +36,8 @@ def batch_setup(nlines, n, seed=SEED, random_grid=False):
     return d
 
 
-def run_batch(mod, nlines, n, steps, spline="const", random_grid=False, oracle=False, direction=0, per_node=False):
+def run_batch(mod, nlines, n, steps, spline="const", random_grid=False, oracle=False, direction=0, per_node=False,
+              solver=None):
     s = batch_setup(nlines, n, random_grid=random_grid)
     if spline == "const":
         mk = lambda m: m.Spline.const(1e-6)
@@ -74,6 +75,8 @@ def run_batch(mod, nlines, n, steps, spline="const", random_grid=False, oracle=F
     else:
         cond = mk(gs)
     g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], cond, s["sigma"], direction=direction, nlines=nlines)
+    if solver is not None:
+        g.set_solver(solver)
     if s["grid0"] is not None:
         g.upload(gs.GRID, s["grid0"])
     g.step(s["time"], s["leftT"], s["rightT"], nsteps=steps)

@@ -83,7 +83,8 @@ PATHS = {
 def test_batch_vs_oracle(O, gs, options, nlines, n, spline, path):
     options(**PATHS[path])
     kw = dict(nlines=nlines, n=n, steps=3, spline=spline, random_grid=True)
-    got, want = cases.run_batch(gs, **kw), cases.run_batch(O, oracle=True, **kw)
+    got = cases.run_batch(gs, solver=gs.SOLVER_THOMAS, **kw)   # one chain per line: the reference's operation order
+    want = cases.run_batch(O, oracle=True, **kw)
     for k in ("grid", "predict"):
         assert_bit_equal(got[k], want[k], f"{path} {spline} {nlines}x{n} {k}")
 
@@ -195,3 +196,21 @@ def test_step_host_pipeline(O, gs, ctx, chunk_mb, spline):
         assert g.status == 0
     finally:
         ctx.set_option("host_chunk_mb", 128)
+
+
+@pytest.mark.parametrize("nlines,n,solver", [(70, 300, 2), (33, 1000, 2), (40, 4099, 0), (64, 8192, 0), (5, 129, 2)])
+@pytest.mark.parametrize("per_node", [False, True])
+def test_long_lines_partitioned(O, gs, nlines, n, solver, per_node):
+    """K5 on 1-D batches (config C5's path: constant properties, long lines cut into segments + reduced system).
+    AUTO switches to it from 2048 nodes; tolerance 1e-12 relative per field."""
+    from helpers import max_rel_err
+
+    kw = dict(nlines=nlines, n=n, steps=3, spline="const", random_grid=True, per_node=per_node)
+    got = cases.run_batch(gs, solver=solver, **kw)
+    want = cases.run_batch(O, oracle=True, **kw)
+    for k in ("grid", "predict"):
+        err = max_rel_err(got[k], want[k])
+        assert err <= 1e-12, f"{k}: {err:.3e}"
+    exact = cases.run_batch(gs, solver=gs.SOLVER_THOMAS, **kw)
+    for k in ("grid", "predict"):
+        assert_bit_equal(exact[k], want[k], "THOMAS stays bit-exact " + k)
