@@ -613,6 +613,16 @@ class TwoDGrid:
     def iteration(self, time: float, nsteps: int = 1):
         L.check(L.lib().gs_grid2d_iteration(self._h, time, nsteps))
 
+    def yIterUpdate(self, time: float):
+        """yIter + Grid.update in one pass (the second half of iteration)."""
+        L.check(L.lib().gs_grid2d_yiter_update(self._h, time))
+
+    def copy_from_device(self, which: int, dptr: int):
+        L.check(L.lib().gs_grid2d_copy_from_device(self._h, which, dptr))
+
+    def copy_to_device(self, which: int, dptr: int):
+        L.check(L.lib().gs_grid2d_copy_to_device(self._h, which, dptr))
+
     def updatePredicted(self):
         L.check(L.lib().gs_grid2d_update_predicted(self._h))
 

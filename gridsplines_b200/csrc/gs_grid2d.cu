@@ -1461,6 +1461,36 @@ extern "C" int gs_grid2d_yiter(gs_grid2d *g, double time) {
   GS_TRY(materialise_result(g));
   return sweep_y(g, time, false);
 }
+// yIter followed by Grid.update in one pass (what iteration() runs after the x sweep); used by the row-sharded
+// multi-GPU driver, which has to exchange `result` between the two sweeps
+extern "C" int gs_grid2d_yiter_update(gs_grid2d *g, double time) {
+  GS_REQUIRE(g != nullptr, "NULL argument");
+  GS_TRY(gs_ctx_use(g->ctx));
+  GS_TRY(materialise_result(g));
+  GS_TRY(sweep_y(g, time, true));
+  g->result_is_grid = true;
+  return GS_OK;
+}
+// device-to-device copies of a whole array on the context stream (dptr: rows * cols doubles, row-major)
+extern "C" int gs_grid2d_copy_from_device(gs_grid2d *g, int which, const void *dptr) {
+  GS_REQUIRE(g && dptr, "NULL argument");
+  GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
+  GS_TRY(gs_ctx_use(g->ctx));
+  if (which == GS_RESULT) g->result_is_grid = false;
+  GS_CUDA(cudaMemcpyAsync(array2d(g, which), dptr, (size_t)g->cols * g->rows * sizeof(double), cudaMemcpyDeviceToDevice,
+                          g->ctx->stream));
+  return GS_OK;
+}
+extern "C" int gs_grid2d_copy_to_device(gs_grid2d *g, int which, void *dptr) {
+  GS_REQUIRE(g && dptr, "NULL argument");
+  GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
+  GS_TRY(gs_ctx_use(g->ctx));
+  if (which == GS_RESULT) GS_TRY(materialise_result(g));
+  GS_CUDA(cudaMemcpyAsync(dptr, array2d(g, which), (size_t)g->cols * g->rows * sizeof(double), cudaMemcpyDeviceToDevice,
+                          g->ctx->stream));
+  return GS_OK;
+}
+
 extern "C" int gs_grid2d_update(gs_grid2d *g) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   gs_ctx *ctx = g->ctx;

@@ -1,0 +1,145 @@
+"""Row-sharded TwoDGrid over the GPUs of one box (SURVEY 8e, config C4's partitioning).
+
+Rank p owns rows [p R/P, (p+1) R/P) of grid / predict / result.  One time step (TwoDGrid.iteration,
+A/TwoDGrid.scala:254-258):
+
+  1. x sweep on the local rows -- every row is an independent line, no communication;
+  2. `result` is transposed to a column-sharded layout with ONE all-to-all (NCCL over NVLink; each rank sends
+     (P-1)/P of its shard), so that every column is whole on one rank;
+  3. y sweep + Grid.update on the local columns (grid and predict are kept column-sharded as well);
+  4. grid' and predict' return to the row-sharded layout with two more all-to-alls for the next x sweep.
+
+The exchange is the only collective on the data path; both sweeps are the single-GPU kernels unchanged, so with
+GS_SOLVER_THOMAS the sharded run is bit-identical to the single-GPU run.  (The SPIKE alternative -- exchanging the
+partitioned solver's reduced-system coefficients instead of whole arrays -- is the planned optimisation; see
+DESIGN.md.)  Restrictions: rows and cols divisible by the world size; a lower HeatFlow bound is not supported when
+sharded (the reference's quirk there reads the neighbouring column, A/TwoDGrid.scala:241).
+
+The driver is backend-agnostic: `make_local(xvalues, yvalues)` returns an object with
+    set_bound(side, kind, rep, values) / get(which) -> torch tensor / set(which, tensor) / xIter(t) / yIterUpdate(t)
+so the same orchestration runs on CUDA (`GsLocalGrid`, nccl) and in the CPU tests (oracle-backed, gloo).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .sharding import block_shard
+
+UPP, LOW, RIGHT, LEFT = 0, 1, 2, 3
+GRID, PREDICT, RESULT = 0, 1, 2
+
+
+def rows_to_cols(x: torch.Tensor, world: int) -> torch.Tensor:
+    """[rows/P, cols] on every rank (row-sharded)  ->  [rows, cols/P] (column-sharded), one all-to-all."""
+    rl, cols = x.shape
+    cl = cols // world
+    send = x.view(rl, world, cl).permute(1, 0, 2).contiguous()      # block j = my rows x rank j's columns
+    recv = torch.empty_like(send)
+    if world > 1:
+        dist.all_to_all_single(recv, send)
+    else:
+        recv.copy_(send)
+    return recv.view(world * rl, cl)                                 # block i = rank i's rows x my columns
+
+
+def cols_to_rows(x: torch.Tensor, world: int) -> torch.Tensor:
+    """[rows, cols/P] (column-sharded)  ->  [rows/P, cols] (row-sharded), one all-to-all."""
+    rows, cl = x.shape
+    rl = rows // world
+    send = x.view(world, rl, cl).contiguous()                        # block i = rank i's rows x my columns
+    recv = torch.empty_like(send)
+    if world > 1:
+        dist.all_to_all_single(recv, send)
+    else:
+        recv.copy_(send)
+    return recv.permute(1, 0, 2).reshape(rl, world * cl).contiguous()  # block j = my rows x rank j's columns
+
+
+class RowShardedTwoDGrid:
+    def __init__(self, make_local: Callable, xvalues, yvalues, bounds: Dict[int, Tuple[int, int, np.ndarray]],
+                 world: int, rank: int):
+        self.world, self.rank = world, rank
+        xv, yv = np.asarray(xvalues, float), np.asarray(yvalues, float)
+        self.cols, self.rows = len(xv) - 2, len(yv) - 2
+        if self.rows % world or self.cols % world:
+            raise ValueError("rows and cols must be divisible by the world size")
+        if bounds.get(LOW, (0,))[0] == 1 and world > 1:
+            raise ValueError("a lower HeatFlow bound is not supported on a sharded grid")
+        self.r0, self.rl = block_shard(self.rows, world, rank)
+        self.c0, self.cl = block_shard(self.cols, world, rank)
+        # Dim.coefs of node i needs its two neighbours' coordinates: slicing `values` keeps them (A/Dim.scala:13-15)
+        self.gx = make_local(xv, yv[self.r0:self.r0 + self.rl + 2])     # my rows, all columns: x sweep
+        self.gy = make_local(xv[self.c0:self.c0 + self.cl + 2], yv)     # all rows, my columns: y sweep + update
+        for side, (kind, rep, values) in bounds.items():
+            v = np.atleast_1d(np.asarray(values, float))
+            full = v if v.size > 1 else None
+            if side in (LEFT, RIGHT):
+                self.gx.set_bound(side, kind, rep, full[self.r0:self.r0 + self.rl] if full is not None else v)
+                self.gy.set_bound(side, kind, rep, v if full is None else full)      # unused by the y sweep
+            else:
+                self.gy.set_bound(side, kind, rep, full[self.c0:self.c0 + self.cl] if full is not None else v)
+                self.gx.set_bound(side, kind, rep, v if full is None else full)      # unused by the x sweep
+
+    # ---- state (row-sharded view is the public one)
+    def set_local_rows(self, grid: torch.Tensor, predict: torch.Tensor):
+        """grid / predict: this rank's rows [rl, cols].  Also fills the column-sharded copies (two all-to-alls)."""
+        self.gx.set(GRID, grid)
+        self.gx.set(PREDICT, predict)
+        self.gy.set(GRID, rows_to_cols(grid, self.world))
+        self.gy.set(PREDICT, rows_to_cols(predict, self.world))
+
+    def local_rows(self, which: int = GRID) -> torch.Tensor:
+        return self.gx.get(which)
+
+    def iteration(self, time: float, nsteps: int = 1):
+        for _ in range(nsteps):
+            self.gx.xIter(time)                                                  # 1. local rows
+            self.gy.set(RESULT, rows_to_cols(self.gx.get(RESULT), self.world))   # 2. exchange
+            self.gy.yIterUpdate(time)                                            # 3. local columns (+ Grid.update)
+            self.gx.set(GRID, cols_to_rows(self.gy.get(GRID), self.world))       # 4. back to rows
+            self.gx.set(PREDICT, cols_to_rows(self.gy.get(PREDICT), self.world))
+
+
+class GsLocalGrid:
+    """libgs_b200-backed local grid for RowShardedTwoDGrid: CUDA tensors in and out (device-to-device copies on the
+    context's stream, which must be torch's current stream so that NCCL and the kernels are ordered)."""
+
+    def __init__(self, gs, ctx, xvalues, yvalues, xdir, ydir, coefs_factory, solver=None):
+        x = gs.XDim(xvalues[0], xvalues[1:-1], xvalues[-1], xdir)
+        y = gs.YDim(yvalues[0], yvalues[1:-1], yvalues[-1], ydir)
+        many = (gs.Many, gs.Temp)
+        self.gs, self.g = gs, gs.TwoDGrid(x, y, upp=many, low=many, right=many, left=many, coefs=coefs_factory(ctx),
+                                          ctx=ctx)
+        if solver is not None:
+            self.g.set_solver(solver)
+        self.shape = (self.g.rows, self.g.cols)
+
+    def set_bound(self, side, kind, rep, values):
+        v = np.atleast_1d(np.asarray(values, float))
+        n = self.g.cols if side in (UPP, LOW) else self.g.rows
+        if v.size not in (1, n):
+            v = v[:1]      # a bound the sweep on this layout never reads
+        L.check(L.lib().gs_grid2d_set_bound(self.g._h, side, kind, rep, v.ctypes.data_as(L._dp), len(v)))
+
+    def get(self, which) -> torch.Tensor:
+        out = torch.empty(self.shape, dtype=torch.float64, device="cuda")
+        self.g.copy_to_device(which, out.data_ptr())
+        return out
+
+    def set(self, which, t: torch.Tensor):
+        t = t.contiguous()
+        assert tuple(t.shape) == self.shape and t.dtype == torch.float64 and t.is_cuda
+        self.g.copy_from_device(which, t.data_ptr())
+        # the copy is asynchronous on the context stream = torch's current stream; keep `t` alive until it ran
+        self._keep = t
+
+    def xIter(self, time):
+        self.g.xIter(time)
+
+    def yIterUpdate(self, time):
+        self.g.yIterUpdate(time)
