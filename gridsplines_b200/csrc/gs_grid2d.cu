@@ -808,6 +808,8 @@ __global__ void __launch_bounds__(128, 5) k_part_C(PartParams q) {
   gs_raise(p.status, flags);
 }
 
+#include "gs_grid2d_k6.cuh"
+
 // ---------------------------------------------------------------------------------
 // small kernels: Grid.update, edges, reductions
 // ---------------------------------------------------------------------------------
@@ -931,6 +933,9 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->iface);
   cudaFree(g->predict_alt);
   cudaFree(g->k5_ckpt);
+  cudaFree(g->k6_F);
+  cudaFree(g->k6_ends);
+  cudaFree(g->k6_ckpt);
   for (gs_k5dir *kd : {&g->k5x, &g->k5y}) {
     cudaFree(kd->tab);
     cudaFree(kd->omega_end);
@@ -1440,12 +1445,99 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   return GS_OK;
 }
 
+// ---- K6: faces kernel + elimination sweeps for temperature-dependent tables --------------------------------
+static void k6_shape(int n, int *m, int *S) {
+  int s = std::max(2, std::min(8, n / 64));
+  int mm = ((n + s - 1) / s + K5_CH - 1) / K5_CH * K5_CH;
+  *m = mm;
+  *S = (n + mm - 1) / mm;
+}
+static size_t k6_smem(bool xdir, int S) {
+  size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
+  return ((size_t)6 * S * 32 + (size_t)S * (4 * tile + 4 * K5_CH)) * sizeof(double);
+}
+static bool use_k6(gs_grid2d *g, bool xdir) {
+  gs_ctx *ctx = g->ctx;
+  if (g->solver == GS_SOLVER_THOMAS || !ctx->opt_k6) return false;
+  const int n = xdir ? g->cols : g->rows;
+  if (n < (g->solver == GS_SOLVER_PARTITIONED ? 128 : 256)) return false;
+  int m, S;
+  k6_shape(n, &m, &S);
+  return S >= 2 && k6_smem(xdir, S) <= ctx->smem_optin;
+}
+
+static int launch_k6(gs_grid2d *g, double time, bool xdir) {
+  gs_ctx *ctx = g->ctx;
+  GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
+  GS_TRY(gs_ctx_sync_pool(ctx));
+  const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
+  const size_t cells = (size_t)g->cols * g->rows;
+  if (!g->k6_F) GS_CUDA(cudaMalloc(&g->k6_F, cells * sizeof(double)));
+  const size_t ends_need = 6 * (size_t)std::max(g->cols, g->rows);
+  if (!g->k6_ends) GS_CUDA(cudaMalloc(&g->k6_ends, ends_need * sizeof(double)));
+  const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / K5_CH + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
+  if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
+  // 1. faces + end rows of this direction (reads predict, rhs; every spline evaluation of the sweep happens here)
+  K6FacesParams fq;
+  bool single;
+  fill_common(g, fq.sw, time, single);
+  Sweep2dParams &p = fq.sw;
+  const gs_dim2d &d = xdir ? g->x : g->y;
+  p.rhs = xdir ? g->grid : g->result;
+  p.coefs = d.coefs;
+  p.firstVol = d.hf[0]; p.fC = d.hf[1]; p.lastVol = d.hf[2]; p.lA = d.hf[3];
+  const int sf = xdir ? GS_LEFT : GS_UPP, sl = xdir ? GS_RIGHT : GS_LOW;
+  p.bound_first = g->b[sf].values; p.bound_last = g->b[sl].values;
+  p.kind_first = g->b[sf].kind; p.kind_last = g->b[sl].kind;
+  fq.F = g->k6_F;
+  fq.first3 = g->k6_ends;
+  fq.last3 = g->k6_ends + 3 * (size_t)nlines;
+  size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
+  int fblocks = (int)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 16);
+  bool lit = single;
+  for (int s4 = 0; s4 < 4 && lit; ++s4) lit = literal_const(ctx, p.maps.single_off[s4], nullptr);
+#define GS_FACES(XD, SG) k6_faces<XD, SG><<<fblocks, 256, pool_smem, ctx->stream>>>(fq)
+  if (xdir) {
+    if (lit) GS_FACES(true, CoefSelLit); else if (single) GS_FACES(true, CoefSel<true>); else GS_FACES(true, CoefSel<false>);
+  } else {
+    if (lit) GS_FACES(false, CoefSelLit); else if (single) GS_FACES(false, CoefSel<true>); else GS_FACES(false, CoefSel<false>);
+  }
+#undef GS_FACES
+  // 2. elimination sweep
+  K6Params q;
+  q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
+  k6_shape(n, &q.m, &q.S);
+  q.coefs = d.coefs;
+  q.F = g->k6_F; q.first3 = fq.first3; q.last3 = fq.last3;
+  q.rhs = p.rhs;
+  q.out = g->result;
+  q.grid_io = g->grid;
+  q.predict_out = g->predict;
+  q.ckpt = g->k6_ckpt;
+  q.time = time;
+  q.status = g->status;
+  size_t smem = k6_smem(xdir, q.S);
+  int blocks = (nlines + 31) / 32, threads = 32 * q.S;
+  if (xdir) {
+    GS_CUDA(cudaFuncSetAttribute(k6_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k6_sweep<true><<<blocks, threads, smem, ctx->stream>>>(q);
+  } else {
+    GS_CUDA(cudaFuncSetAttribute(k6_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k6_sweep<false><<<blocks, threads, smem, ctx->stream>>>(q);
+  }
+  ctx->launches += 2;
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
 static int sweep_x(gs_grid2d *g, double time) {
   if (use_k5(g, true)) return launch_k5(g, time, true);
+  if (use_k6(g, true)) return launch_k6(g, time, true);
   return use_partitioned(g, g->cols) ? launch_part(g, time, true, false) : launch_xsweep(g, time);
 }
 static int sweep_y(gs_grid2d *g, double time, bool fuse) {
-  if (fuse && use_k5(g, false)) return launch_k5(g, time, false);   // K5's y sweep is always fused with Grid.update
+  if (fuse && use_k5(g, false)) return launch_k5(g, time, false);   // K5's / K6's y sweeps are always fused with Grid.update
+  if (fuse && use_k6(g, false)) return launch_k6(g, time, false);
   return use_partitioned(g, g->rows) ? launch_part(g, time, false, fuse) : launch_ysweep(g, time, fuse);
 }
 

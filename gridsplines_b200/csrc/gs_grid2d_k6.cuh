@@ -1,0 +1,287 @@
+// gs_grid2d_k6.cuh -- K6: 2-D sweeps for temperature-dependent properties (spline tables, any coefficient map):
+// assembly is split from elimination.  Tolerance solver family (GS_SOLVER_PARTITIONED / AUTO): <= 1e-12 per field.
+//
+// The expensive part of the reference's row assembly is the material property at every cell face: an interval
+// average of a spline table (A/Dim.scala:67-83 -> A/AlwaysDefinedSpline.scala:43-46), ~100+ instructions with a
+// division.  It depends on `predict` only, which is frozen during a step, so it is NOT part of the Thomas
+// recurrence: k6_faces evaluates every face of a direction in one fully parallel, coalesced pass
+//     F[i] = co(predict_i, predict_{i+1}, z_i)        (Dim.general's `co`; the carry out of the first node at i = 0)
+// with the reference's own formulas (same doubles), and assembles the two end rows of every line (Dirichlet or
+// heat-flow, A/Dim.scala:28-64, 86-128) into small per-line arrays.  k6_sweep then is K5's one-CTA-per-strip
+// pipeline (phase A -> reduced system -> phase C, cp.async double-buffered chunks, checkpoints per chunk) whose
+// per-node work is only the elimination:  sub = cf0 F[i-1], sup = cf1 F[i], diag = -(sub+sup) - 1/tau,
+// Delta = diag + sub delta, one reciprocal, delta, lambda, omega and the composed map (P, Q, R) of the segment.
+#pragma once
+
+// ---- faces -------------------------------------------------------------------------------------------------------
+struct K6FacesParams {
+  Sweep2dParams sw;      // predict, rhs, coefs, bounds, maps, pool, time, geometry of the swept direction
+  double *F;             // [rows * cols] face values (stored at node i's position)
+  double *first3;        // [nlines][3] diag, sup, rhs of node 0
+  double *last3;         // [nlines][3] sub, diag, rhs of node n-1
+};
+
+template <bool XDIR, class SEL>
+__global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
+  extern __shared__ double k6sm[];
+  const Sweep2dParams &p = q.sw;
+  const double *pool = stage_pool(p, k6sm);
+  const size_t total = (size_t)p.cols * p.rows;
+  SEL sel(p.maps, pool, p.cols);
+  SweepConsts k;
+  k.fast_allowed = false;
+  bool dummy = true;
+  k.rt = gs_rcp_invariant(p.time, dummy);
+  k.inv_time = 1.0 / p.time;
+  k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
+  unsigned flags = 0;
+  bool ok = true;
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(f / p.cols), col = (int)(f % p.cols);
+    const int line = XDIR ? row : col, i = XDIR ? col : row;
+    LineAcc<XDIR> A(p, line);
+    const int n = A.n();
+    const double p0 = A.pred(i);
+    if (i == 0) {
+      double face = 0.0;
+      Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, p0, A.pred(1), A.rhs(0), face, flags, ok);
+      q.F[f] = face;                       // carry into node 1: co, or cond / cap after a heat-flow end
+      double *o = q.first3 + 3 * (size_t)line;
+      o[0] = r.diag; o[1] = r.sup; o[2] = r.rhs;
+    } else if (i == n - 1) {
+      double face = face_before<XDIR, SEL, false>(A, sel, k, i, A.pred(i - 1), p0, flags, ok);
+      Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, i, p0, 0.0, A.rhs(i), face, flags, ok);
+      q.F[f] = 0.0;
+      double *o = q.last3 + 3 * (size_t)line;
+      o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
+    } else {
+      q.F[f] = gs_take_average<false>(sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), p0, A.pred(i + 1), flags, ok);
+    }
+  }
+  if (flags) atomicOr(p.status, flags);
+}
+
+// ---- sweep -------------------------------------------------------------------------------------------------------
+struct K6Params {
+  int n, nlines, m, S, cols, rows;
+  const double *coefs;     // Dim.coefs [2n]
+  const double *F, *first3, *last3;
+  const double *rhs;       // x: grid, y: result
+  double *out;             // x: result
+  double *grid_io;         // y: old grid in / new grid out
+  double *predict_out;     // y: new predict
+  double4 *ckpt;           // [n / K5_CH][nlines padded]: delta, lambda, omega, fprev at the end of every chunk
+  double time;
+  unsigned *status;
+};
+
+template <bool XDIR>
+__device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, int i0, int len, double *tileT,
+                                        double *tileF, double2 *tabs, int lane) {
+  constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  if (lane < len) k5_cp16(tabs + lane, q.coefs + 2 * (size_t)(i0 + lane));   // (cf0, cf1) of the chunk's nodes
+  if (XDIR) {
+    const int jj = lane & (K5_CH - 1);
+    if (jj < len) {
+      const size_t off = (size_t)line0 * q.cols + i0 + jj;
+#pragma unroll 4
+      for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) {
+        k5_cp8(&tileT[jj * PITCH + r], q.rhs + off + (size_t)r * q.cols);
+        k5_cp8(&tileF[jj * PITCH + r], q.F + off + (size_t)r * q.cols);
+      }
+    }
+  } else {
+    if (lane < nl) {
+      const size_t off = (size_t)i0 * q.cols + line0 + lane;
+#pragma unroll 8
+      for (int j = 0; j < len; ++j) {
+        k5_cp8(&tileT[j * PITCH + lane], q.rhs + off + (size_t)j * q.cols);
+        k5_cp8(&tileF[j * PITCH + lane], q.F + off + (size_t)j * q.cols);
+      }
+    }
+  }
+  k5_commit();
+}
+
+// elimination of one node; returns delta, updates lambda (and omega)
+struct K6State {
+  double delta, lambda, omega, fprev;
+};
+
+template <bool XDIR>
+__global__ void __launch_bounds__(256) k6_sweep(K6Params q) {
+  extern __shared__ __align__(16) double k6s[];
+  constexpr int PITCH = K5Tile<XDIR>::PITCH;
+  constexpr int TD = K5Tile<XDIR>::DOUBLES;
+  const int S = q.S, m = q.m, n = q.n;
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+  const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
+  // shared: per CTA seg[6][S][32] (delta_e, omega_e, P, R, lambda_e, Q) ; per warp 2 x (tileT, tileF) + 2 x tabs
+  double *segs = k6s;
+  double *wbase = k6s + 6 * S * 32 + (size_t)k * (4 * TD + 4 * K5_CH);
+  double2 *tabs2 = reinterpret_cast<double2 *>(wbase);
+  double *tiles = wbase + 4 * K5_CH;
+  const int s = k * m, e = min(n, s + m) - 1;
+  const int nch = (e >= s) ? (e - s) / K5_CH + 1 : 0;
+  const bool act = lane < nl;
+  const int line = line0 + (act ? lane : 0);
+  const size_t ck_pitch = (size_t)((q.nlines + 31) / 32) * 32;
+  double4 *ckpt = q.ckpt + (size_t)(s / K5_CH) * ck_pitch + line0 + lane;
+  const double inv_time = 1.0 / q.time;
+  const double f_diag = q.first3[3 * (size_t)line], f_sup = q.first3[3 * (size_t)line + 1], f_rhs = q.first3[3 * (size_t)line + 2];
+  const double l_sub = q.last3[3 * (size_t)line], l_diag = q.last3[3 * (size_t)line + 1], l_rhs = q.last3[3 * (size_t)line + 2];
+  const size_t lstride = XDIR ? 1 : (size_t)q.cols, lbase = XDIR ? (size_t)line * q.cols : (size_t)line;
+
+  // one node of the forward elimination; st carries (delta, lambda, omega, fprev)
+  auto node = [&](int i, double t, double F, double2 cf, K6State &st) {
+    double sub, diag, sup, rhs;
+    if (i == 0) { sub = 0.0; diag = f_diag; sup = f_sup; rhs = f_rhs; }
+    else if (i == n - 1) { sub = l_sub; diag = l_diag; sup = 0.0; rhs = l_rhs; }
+    else {
+      sub = cf.x * st.fprev;
+      sup = cf.y * F;
+      diag = -(sub + sup) - inv_time;
+      rhs = -t * inv_time;
+    }
+    const double inv = __drcp_rn(diag + sub * st.delta);
+    const double beta = -sub * inv;
+    st.delta = -sup * inv;
+    st.lambda = fma(rhs, inv, st.lambda * beta);
+    st.omega = beta * st.omega;
+    st.fprev = F;
+  };
+
+  // ---- phase A ----
+  K6State st;
+  st.delta = 0.0; st.lambda = 0.0; st.omega = (s > 0) ? 1.0 : 0.0;
+  st.fprev = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
+  double P = 1.0, Qa = 0.0, R = 0.0;
+  if (nch > 0) k6_load<XDIR>(q, line0, nl, s, min(K5_CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
+  for (int c = 0; c < nch; ++c) {
+    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
+    const double2 *cf = tabs2 + (c & 1) * K5_CH;
+    if (c + 1 < nch) {
+      const int i1 = i0 + K5_CH;
+      double *nT = tiles + ((c + 1) & 1) * 2 * TD;
+      k6_load<XDIR>(q, line0, nl, i1, min(K5_CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * K5_CH, lane);
+      k5_wait<1>();
+    } else {
+      k5_wait<0>();
+    }
+    __syncwarp();
+    for (int j = 0; j < len; ++j) {
+      node(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
+      if (i0 + j < e) {   // x_s = P x_e + Q + R L gathers nodes s .. e-1
+        Qa = fma(P, st.lambda, Qa);
+        R = fma(P, st.omega, R);
+        P = P * st.delta;
+      }
+    }
+    ckpt[(size_t)c * ck_pitch] = make_double4(st.delta, st.lambda, st.omega, st.fprev);
+    __syncwarp();
+  }
+  {
+    double *sg = segs + (size_t)k * 32 + lane;
+    sg[0 * S * 32] = st.delta;    // delta_e (0 on the line's last node)
+    sg[1 * S * 32] = st.omega;
+    sg[2 * S * 32] = P;
+    sg[3 * S * 32] = R;
+    sg[4 * S * 32] = st.lambda;
+    sg[5 * S * 32] = Qa;
+  }
+  __syncthreads();
+  // ---- reduced system: warp 0, lane = line; E_k overwrites slot 4, scratch in slots 2/3 ----
+  if (k == 0) {
+    double cp = 0.0, dp = 0.0;
+    for (int kk = 0; kk < S; ++kk) {
+      double *sg = segs + (size_t)kk * 32 + lane;
+      const double de = sg[0], om = sg[1 * S * 32], la = sg[4 * S * 32];
+      double Pn = 0.0, Rn = 0.0, Qn = 0.0;
+      if (kk + 1 < S) { Pn = sg[2 * S * 32 + 32]; Rn = sg[3 * S * 32 + 32]; Qn = sg[5 * S * 32 + 32]; }
+      const double sub = -om, diag = 1.0 - de * Rn, sup = -(de * Pn), rhs = la + de * Qn;
+      const double inv = 1.0 / (diag - sub * cp);
+      cp = sup * inv;
+      dp = (rhs - sub * dp) * inv;
+      sg[2 * S * 32] = cp;        // P, R of segment kk were consumed at kk-1
+      sg[3 * S * 32] = dp;
+    }
+    double x = 0.0;
+    for (int kk = S - 1; kk >= 0; --kk) {
+      double *sg = segs + (size_t)kk * 32 + lane;
+      x = sg[3 * S * 32] - sg[2 * S * 32] * x;
+      sg[4 * S * 32] = x;
+    }
+  }
+  __syncthreads();
+  // ---- phase C ----
+  if (nch == 0) return;
+  const double L = (k > 0) ? segs[4 * S * 32 + (size_t)(k - 1) * 32 + lane] : 0.0;
+  double x = segs[4 * S * 32 + (size_t)k * 32 + lane];
+  {
+    const int il = s + (nch - 1) * K5_CH;
+    double *nT = tiles + ((nch - 1) & 1) * 2 * TD;
+    k6_load<XDIR>(q, line0, nl, il, min(K5_CH, e - il + 1), nT, nT + TD, tabs2 + ((nch - 1) & 1) * K5_CH, lane);
+  }
+  double4 ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : make_double4(0.0, 0.0, 0.0, 0.0);
+  const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
+  for (int c = nch - 1; c >= 0; --c) {
+    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
+    const double2 *cf = tabs2 + (c & 1) * K5_CH;
+    if (c > 0) {
+      double *nT = tiles + ((c - 1) & 1) * 2 * TD;
+      k6_load<XDIR>(q, line0, nl, i0 - K5_CH, K5_CH, nT, nT + TD, tabs2 + ((c - 1) & 1) * K5_CH, lane);
+      k5_wait<1>();
+    } else {
+      k5_wait<0>();
+    }
+    __syncwarp();
+    // state at the start of the chunk: phase A's checkpoint, with the left-neighbour value folded into lambda
+    K6State sc;
+    if (c > 0) {
+      sc.delta = ck_next.x; sc.lambda = ck_next.y + ck_next.z * L; sc.omega = 0.0; sc.fprev = ck_next.w;
+    } else {
+      sc.delta = 0.0; sc.lambda = L; sc.omega = 0.0; sc.fprev = f_seg;   // lambda_s = rhs/Delta + beta_s L
+    }
+    if (c > 1) ck_next = ckpt[(size_t)(c - 2) * ck_pitch];
+    for (int j = 0; j < len; ++j) {
+      node(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], sc);
+      tF[j * PITCH + lane] = sc.delta;
+      tT[j * PITCH + lane] = sc.lambda;
+    }
+    if (XDIR) {
+      for (int j = len - 1; j >= 0; --j) {
+        if (i0 + j != e) x = fma(tF[j * PITCH + lane], x, tT[j * PITCH + lane]);
+        tT[j * PITCH + lane] = x;
+      }
+      __syncwarp();
+      const int jj = lane & (K5_CH - 1);
+      if (jj < len) {
+        double *g = q.out + (size_t)line0 * q.cols + i0 + jj;
+#pragma unroll 4
+        for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) g[(size_t)r * q.cols] = tT[jj * PITCH + r];
+      }
+    } else if (act) {
+      const size_t off = (size_t)i0 * q.cols + line0 + lane;
+      double *G = q.grid_io + off, *Pp = q.predict_out + off;
+      for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
+        double gold[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.cols] : 0.0;
+#pragma unroll
+        for (int u = 7; u >= 0; --u) {
+          const int j = jb + u;
+          if (j < len) {
+            if (i0 + j != e) x = fma(tF[j * PITCH + lane], x, tT[j * PITCH + lane]);
+            const double dl = x - gold[u];                                   // Grid.update :474-481, aVal :508-512
+            Pp[(size_t)j * q.cols] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
+            G[(size_t)j * q.cols] = x;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (act && !(fabs(x) <= 1.7976931348623157e308)) atomicOr(q.status, GS_FLAG_NONFINITE);
+}

@@ -61,6 +61,7 @@ struct gs_ctx {
   int64_t opt_seg_len = 32;
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
+  int64_t opt_k6 = 1;
   int64_t opt_host_chunk_mb = 128;
   int64_t opt_ck_block = 16;
 };
@@ -141,6 +142,8 @@ struct gs_grid2d {
   gs_k5dir k5x, k5y;
   double *k5_ckpt = nullptr;
   size_t k5_ckpt_len = 0;
+  double *k6_F = nullptr, *k6_ends = nullptr;   // K6: face values, end rows
+  double4 *k6_ckpt = nullptr;
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };

@@ -304,3 +304,27 @@ def test_k5_hoisted_constant_coefficients(O, gs, cols, rows, combo):
     g.yIter(900.0); o.yIter(900.0)
     assert max_rel_err(g.grid.result, o.result) <= TOL
     assert g.status == 0
+
+
+@pytest.mark.parametrize("coefs", ["hermite", "per_row", "per_col", "dense", "const"])
+@pytest.mark.parametrize("combo,cols,rows", [("TTTT", 130, 257), ("FFTF", 300, 140), ("TFFT", 128, 128), ("FTFT", 513, 129)])
+def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
+    """K6: every spline evaluation in an elementwise faces kernel, then K5-style fused partitioned sweeps over the
+    precomputed face values (temperature-dependent tables, every coefficient-map mode, all bound kinds)."""
+    ctx.set_option("k5", 0)   # constant coefficients would otherwise take K5
+    try:
+        p = cases.bc_problem(combo, xdir=1, ydir=0, cols=cols, rows=rows, coefs=coefs)
+        r = np.random.default_rng(6)
+        p.grid0 = r.uniform(-15.0, 70.0, p.grid0.shape)
+        p.predict0 = p.grid0 + r.uniform(-12.0, 12.0, p.grid0.shape)
+        g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+        g.set_solver(gs.SOLVER_PARTITIONED)
+        g.iteration(900.0, nsteps=3)
+        for _ in range(3):
+            o.iteration(900.0)
+        O.set_ascending_fold(True)
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs} {combo} {cols}x{rows}")
+        g.xIter(900.0); o.xIter(900.0)
+        assert max_rel_err(g.grid.result, o.result) <= TOL
+    finally:
+        ctx.set_option("k5", 1)
