@@ -61,15 +61,28 @@ extern "C" int gs_ctx_create(int device, void *stream, gs_ctx **out) {
   return GS_OK;
 }
 
-extern "C" int gs_ctx_destroy(gs_ctx *ctx) {
-  if (!ctx) return GS_OK;
+static void ctx_free(gs_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->pool_dev) cudaFree(ctx->pool_dev);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+// Grids keep their context alive: hosts with garbage collectors (the JVM, CPython) may finalise the context
+// object before the grids made from it.
+extern "C" int gs_ctx_destroy(gs_ctx *ctx) {
+  if (!ctx) return GS_OK;
+  if (ctx->refs > 0) {
+    ctx->dead = true;
+    return GS_OK;
+  }
+  ctx_free(ctx);
   return GS_OK;
+}
+void gs_ctx_retain(gs_ctx *ctx) { ctx->refs++; }
+void gs_ctx_release(gs_ctx *ctx) {
+  if (--ctx->refs <= 0 && ctx->dead) ctx_free(ctx);
 }
 
 int gs_ctx_use(gs_ctx *ctx) {
@@ -104,6 +117,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "hoist_ck")) ctx->opt_hoist_ck = value;
   else if (!strcmp(name, "k5")) ctx->opt_k5 = value;
   else if (!strcmp(name, "k6")) ctx->opt_k6 = value;
+  else if (!strcmp(name, "k6_chunk")) ctx->opt_k6_chunk = value;
   else if (!strcmp(name, "host_chunk_mb")) ctx->opt_host_chunk_mb = value;
   else if (!strcmp(name, "ck_block")) ctx->opt_ck_block = value;
   else {

@@ -1112,6 +1112,7 @@ extern "C" int gs_grid1d_create(gs_ctx *ctx, int64_t nlines, int n, int dir, dou
 
   gs_grid1d *g = new gs_grid1d();
   g->ctx = ctx;
+  gs_ctx_retain(ctx);
   g->nlines = nlines;
   g->n = n;
   g->dir = dir;
@@ -1195,7 +1196,9 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
     cudaStreamDestroy(g->hs_out);
   }
   cudaFree(g->status);
+  gs_ctx *owner = g->ctx;
   delete g;
+  gs_ctx_release(owner);
   return GS_OK;
 }
 

@@ -885,6 +885,7 @@ extern "C" int gs_grid2d_create(gs_ctx *ctx, int cols, int rows, int xdir, int y
   GS_REQUIRE((xdir == GS_ORTHO || xdir == GS_RADIAL) && (ydir == GS_ORTHO || ydir == GS_RADIAL), "unknown direction kind");
   gs_grid2d *g = new gs_grid2d();
   g->ctx = ctx;
+  gs_ctx_retain(ctx);
   g->cols = cols;
   g->rows = rows;
   int s = GS_OK;
@@ -943,7 +944,9 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
     cudaFree(kd->ends);
   }
   cudaFree(g->status);
+  gs_ctx *owner = g->ctx;
   delete g;
+  gs_ctx_release(owner);
   return GS_OK;
 }
 
@@ -1446,15 +1449,18 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
 }
 
 // ---- K6: faces kernel + elimination sweeps for temperature-dependent tables --------------------------------
-static void k6_shape(int n, int *m, int *S) {
-  int s = std::max(2, std::min(8, n / 64));
-  int mm = ((n + s - 1) / s + K5_CH - 1) / K5_CH * K5_CH;
+static int k6_chunk(gs_ctx *ctx) { return ctx->opt_k6_chunk == 16 ? 16 : 8; }
+static void k6_shape(gs_ctx *ctx, int n, int *m, int *S) {
+  const int ch = k6_chunk(ctx);
+  int s = std::max(2, std::min(ch == 16 ? 8 : 16, n / 64));
+  int mm = ((n + s - 1) / s + ch - 1) / ch * ch;
   *m = mm;
   *S = (n + mm - 1) / mm;
 }
-static size_t k6_smem(bool xdir, int S) {
-  size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
-  return ((size_t)6 * S * 32 + (size_t)S * (4 * tile + 4 * K5_CH)) * sizeof(double);
+static size_t k6_smem(gs_ctx *ctx, bool xdir, int S) {
+  const int ch = k6_chunk(ctx);
+  size_t tile = (size_t)ch * (xdir ? 33 : 32);
+  return ((size_t)6 * S * 32 + (size_t)S * (4 * tile + 4 * ch)) * sizeof(double);
 }
 static bool use_k6(gs_grid2d *g, bool xdir) {
   gs_ctx *ctx = g->ctx;
@@ -1462,8 +1468,8 @@ static bool use_k6(gs_grid2d *g, bool xdir) {
   const int n = xdir ? g->cols : g->rows;
   if (n < (g->solver == GS_SOLVER_PARTITIONED ? 128 : 256)) return false;
   int m, S;
-  k6_shape(n, &m, &S);
-  return S >= 2 && k6_smem(xdir, S) <= ctx->smem_optin;
+  k6_shape(ctx, n, &m, &S);
+  return S >= 2 && k6_smem(ctx, xdir, S) <= ctx->smem_optin;
 }
 
 static int launch_k6(gs_grid2d *g, double time, bool xdir) {
@@ -1475,7 +1481,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   if (!g->k6_F) GS_CUDA(cudaMalloc(&g->k6_F, cells * sizeof(double)));
   const size_t ends_need = 6 * (size_t)std::max(g->cols, g->rows);
   if (!g->k6_ends) GS_CUDA(cudaMalloc(&g->k6_ends, ends_need * sizeof(double)));
-  const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / K5_CH + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
+  const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / 8 + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
   if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
   // 1. faces + end rows of this direction (reads predict, rhs; every spline evaluation of the sweep happens here)
   K6FacesParams fq;
@@ -1506,7 +1512,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   // 2. elimination sweep
   K6Params q;
   q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
-  k6_shape(n, &q.m, &q.S);
+  k6_shape(ctx, n, &q.m, &q.S);
   q.coefs = d.coefs;
   q.F = g->k6_F; q.first3 = fq.first3; q.last3 = fq.last3;
   q.rhs = p.rhs;
@@ -1516,15 +1522,12 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   q.ckpt = g->k6_ckpt;
   q.time = time;
   q.status = g->status;
-  size_t smem = k6_smem(xdir, q.S);
+  size_t smem = k6_smem(ctx, xdir, q.S);
   int blocks = (nlines + 31) / 32, threads = 32 * q.S;
-  if (xdir) {
-    GS_CUDA(cudaFuncSetAttribute(k6_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k6_sweep<true><<<blocks, threads, smem, ctx->stream>>>(q);
-  } else {
-    GS_CUDA(cudaFuncSetAttribute(k6_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k6_sweep<false><<<blocks, threads, smem, ctx->stream>>>(q);
-  }
+  void (*kern)(K6Params) = k6_chunk(ctx) == 16 ? (xdir ? k6_sweep<true, 16> : k6_sweep<false, 16>)
+                                                : (xdir ? k6_sweep<true, 8> : k6_sweep<false, 8>);
+  GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, threads, smem, ctx->stream>>>(q);
   ctx->launches += 2;
   GS_CUDA(cudaGetLastError());
   return GS_OK;

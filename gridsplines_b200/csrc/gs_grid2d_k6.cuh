@@ -70,22 +70,22 @@ struct K6Params {
   double *out;             // x: result
   double *grid_io;         // y: old grid in / new grid out
   double *predict_out;     // y: new predict
-  double4 *ckpt;           // [n / K5_CH][nlines padded]: delta, lambda, omega, fprev at the end of every chunk
+  double4 *ckpt;           // [n / CH][nlines padded]: delta, lambda, omega, fprev at the end of every chunk
   double time;
   unsigned *status;
 };
 
-template <bool XDIR>
+template <bool XDIR, int CH>
 __device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, int i0, int len, double *tileT,
                                         double *tileF, double2 *tabs, int lane) {
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
   if (lane < len) k5_cp16(tabs + lane, q.coefs + 2 * (size_t)(i0 + lane));   // (cf0, cf1) of the chunk's nodes
   if (XDIR) {
-    const int jj = lane & (K5_CH - 1);
+    const int jj = lane & (CH - 1);
     if (jj < len) {
       const size_t off = (size_t)line0 * q.cols + i0 + jj;
 #pragma unroll 4
-      for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) {
+      for (int r = lane / CH; r < nl; r += 32 / CH) {
         k5_cp8(&tileT[jj * PITCH + r], q.rhs + off + (size_t)r * q.cols);
         k5_cp8(&tileF[jj * PITCH + r], q.F + off + (size_t)r * q.cols);
       }
@@ -108,25 +108,25 @@ struct K6State {
   double delta, lambda, omega, fprev;
 };
 
-template <bool XDIR>
-__global__ void __launch_bounds__(256) k6_sweep(K6Params q) {
+template <bool XDIR, int CH>
+__global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   extern __shared__ __align__(16) double k6s[];
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
-  constexpr int TD = K5Tile<XDIR>::DOUBLES;
+  constexpr int TD = CH * PITCH;
   const int S = q.S, m = q.m, n = q.n;
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
   const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
   // shared: per CTA seg[6][S][32] (delta_e, omega_e, P, R, lambda_e, Q) ; per warp 2 x (tileT, tileF) + 2 x tabs
   double *segs = k6s;
-  double *wbase = k6s + 6 * S * 32 + (size_t)k * (4 * TD + 4 * K5_CH);
+  double *wbase = k6s + 6 * S * 32 + (size_t)k * (4 * TD + 4 * CH);
   double2 *tabs2 = reinterpret_cast<double2 *>(wbase);
-  double *tiles = wbase + 4 * K5_CH;
+  double *tiles = wbase + 4 * CH;
   const int s = k * m, e = min(n, s + m) - 1;
-  const int nch = (e >= s) ? (e - s) / K5_CH + 1 : 0;
+  const int nch = (e >= s) ? (e - s) / CH + 1 : 0;
   const bool act = lane < nl;
   const int line = line0 + (act ? lane : 0);
   const size_t ck_pitch = (size_t)((q.nlines + 31) / 32) * 32;
-  double4 *ckpt = q.ckpt + (size_t)(s / K5_CH) * ck_pitch + line0 + lane;
+  double4 *ckpt = q.ckpt + (size_t)(s / CH) * ck_pitch + line0 + lane;
   const double inv_time = 1.0 / q.time;
   const double f_diag = q.first3[3 * (size_t)line], f_sup = q.first3[3 * (size_t)line + 1], f_rhs = q.first3[3 * (size_t)line + 2];
   const double l_sub = q.last3[3 * (size_t)line], l_diag = q.last3[3 * (size_t)line + 1], l_rhs = q.last3[3 * (size_t)line + 2];
@@ -156,15 +156,15 @@ __global__ void __launch_bounds__(256) k6_sweep(K6Params q) {
   st.delta = 0.0; st.lambda = 0.0; st.omega = (s > 0) ? 1.0 : 0.0;
   st.fprev = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
   double P = 1.0, Qa = 0.0, R = 0.0;
-  if (nch > 0) k6_load<XDIR>(q, line0, nl, s, min(K5_CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
+  if (nch > 0) k6_load<XDIR, CH>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
   for (int c = 0; c < nch; ++c) {
-    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
     double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
-    const double2 *cf = tabs2 + (c & 1) * K5_CH;
+    const double2 *cf = tabs2 + (c & 1) * CH;
     if (c + 1 < nch) {
-      const int i1 = i0 + K5_CH;
+      const int i1 = i0 + CH;
       double *nT = tiles + ((c + 1) & 1) * 2 * TD;
-      k6_load<XDIR>(q, line0, nl, i1, min(K5_CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * K5_CH, lane);
+      k6_load<XDIR, CH>(q, line0, nl, i1, min(CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * CH, lane);
       k5_wait<1>();
     } else {
       k5_wait<0>();
@@ -219,19 +219,19 @@ __global__ void __launch_bounds__(256) k6_sweep(K6Params q) {
   const double L = (k > 0) ? segs[4 * S * 32 + (size_t)(k - 1) * 32 + lane] : 0.0;
   double x = segs[4 * S * 32 + (size_t)k * 32 + lane];
   {
-    const int il = s + (nch - 1) * K5_CH;
+    const int il = s + (nch - 1) * CH;
     double *nT = tiles + ((nch - 1) & 1) * 2 * TD;
-    k6_load<XDIR>(q, line0, nl, il, min(K5_CH, e - il + 1), nT, nT + TD, tabs2 + ((nch - 1) & 1) * K5_CH, lane);
+    k6_load<XDIR, CH>(q, line0, nl, il, min(CH, e - il + 1), nT, nT + TD, tabs2 + ((nch - 1) & 1) * CH, lane);
   }
   double4 ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : make_double4(0.0, 0.0, 0.0, 0.0);
   const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
   for (int c = nch - 1; c >= 0; --c) {
-    const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
+    const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
     double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
-    const double2 *cf = tabs2 + (c & 1) * K5_CH;
+    const double2 *cf = tabs2 + (c & 1) * CH;
     if (c > 0) {
       double *nT = tiles + ((c - 1) & 1) * 2 * TD;
-      k6_load<XDIR>(q, line0, nl, i0 - K5_CH, K5_CH, nT, nT + TD, tabs2 + ((c - 1) & 1) * K5_CH, lane);
+      k6_load<XDIR, CH>(q, line0, nl, i0 - CH, CH, nT, nT + TD, tabs2 + ((c - 1) & 1) * CH, lane);
       k5_wait<1>();
     } else {
       k5_wait<0>();
@@ -256,11 +256,11 @@ __global__ void __launch_bounds__(256) k6_sweep(K6Params q) {
         tT[j * PITCH + lane] = x;
       }
       __syncwarp();
-      const int jj = lane & (K5_CH - 1);
+      const int jj = lane & (CH - 1);
       if (jj < len) {
         double *g = q.out + (size_t)line0 * q.cols + i0 + jj;
 #pragma unroll 4
-        for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) g[(size_t)r * q.cols] = tT[jj * PITCH + r];
+        for (int r = lane / CH; r < nl; r += 32 / CH) g[(size_t)r * q.cols] = tT[jj * PITCH + r];
       }
     } else if (act) {
       const size_t off = (size_t)i0 * q.cols + line0 + lane;

@@ -40,6 +40,8 @@ struct gs_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   uint64_t launches = 0;
+  int refs = 0;        // live grids made from this context
+  bool dead = false;   // gs_ctx_destroy was called while grids were still alive: freed with the last grid
   // spline pool (host copy + device mirror, re-uploaded when it grows)
   std::vector<double> pool;
   std::vector<int> spline_off;
@@ -62,11 +64,14 @@ struct gs_ctx {
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
   int64_t opt_k6 = 1;
+  int64_t opt_k6_chunk = 8;
   int64_t opt_host_chunk_mb = 128;
   int64_t opt_ck_block = 16;
 };
 
 int gs_ctx_use(gs_ctx *ctx);                 // cudaSetDevice
+void gs_ctx_retain(gs_ctx *ctx);             // a grid now refers to the context
+void gs_ctx_release(gs_ctx *ctx);            // ... and no longer does
 int gs_ctx_sync_pool(gs_ctx *ctx);           // upload the spline pool if it changed
 int gs_ctx_stage(gs_ctx *ctx, size_t bytes); // make sure ctx->stage holds at least `bytes`
 

@@ -212,10 +212,25 @@ def seg_len(ctx):
     ctx.set_option("seg_len", 32)
 
 
-def _compare_tol(got, want, what):
+def _compare_tol(got, want, what, tol=TOL):
     for k, v in want.items():
         err = max_rel_err(got[k], v)
-        assert err <= TOL, f"{what} {k}: max relative error per field {err:.3e}"
+        assert err <= tol, f"{what} {k}: max relative error per field {err:.3e} (tolerance {tol:.1e})"
+
+
+def _oracle_sensitivity(O, p, steps):
+    """How much the REFERENCE algorithm itself moves when `predict` changes by one ulp.  With spline tables the
+    face property is (antider(hi) - antider(lo)) / (hi - lo): for neighbouring temperatures a fraction of a degree
+    apart the cancellation amplifies a 1e-16 input difference to ~1e-11 in the coefficient, so no implementation
+    with a different operation order can agree with the reference better than this, whatever its own accuracy."""
+    a, b = p.build_oracle(O, ascending=False), p.build_oracle(O, ascending=False)
+    b.predict[:] = np.nextafter(b.predict, np.inf)
+    worst = 0.0
+    for _ in range(steps):
+        a.iteration(900.0); b.iteration(900.0)
+        worst = max(worst, max_rel_err(a.grid, b.grid), max_rel_err(a.predict, b.predict))
+    O.set_ascending_fold(True)
+    return worst
 
 
 @pytest.mark.parametrize("combo", ["".join(c) for c in itertools.product("TF", repeat=4)])
@@ -263,7 +278,7 @@ def test_partitioned_coefficient_maps_and_tables(O, gs, seg_len, coefs):
     for _ in range(3):
         o.iteration(900.0)
     O.set_ascending_fold(True)
-    _compare_tol(cases.snapshot(g), cases.snapshot(o), coefs)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), coefs, tol=max(TOL, 4.0 * _oracle_sensitivity(O, p, 3)))
 
 
 def test_partitioned_gridtest_and_medium(O, gs, seg_len):
@@ -323,8 +338,9 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         for _ in range(3):
             o.iteration(900.0)
         O.set_ascending_fold(True)
-        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs} {combo} {cols}x{rows}")
+        tol = TOL if coefs == "const" else max(TOL, 4.0 * _oracle_sensitivity(O, p, 3))
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs} {combo} {cols}x{rows}", tol=tol)
         g.xIter(900.0); o.xIter(900.0)
-        assert max_rel_err(g.grid.result, o.result) <= TOL
+        assert max_rel_err(g.grid.result, o.result) <= tol
     finally:
         ctx.set_option("k5", 1)
