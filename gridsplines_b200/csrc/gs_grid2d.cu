@@ -1499,7 +1499,10 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   fq.first3 = g->k6_ends;
   fq.last3 = g->k6_ends + 3 * (size_t)nlines;
   size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
-  int fblocks = (int)std::min<size_t>((cells + 255) / 256, (size_t)ctx->sm_count * 16);
+  // blocks of 256 columns x a stride of rows: enough CTAs to fill the chip a few times over, each staging the
+  // spline pool once
+  const int fbx = (g->cols + 255) / 256;
+  dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * 12 / fbx)));
   bool lit = single;
   for (int s4 = 0; s4 < 4 && lit; ++s4) lit = literal_const(ctx, p.maps.single_off[s4], nullptr);
 #define GS_FACES(XD, SG) k6_faces<XD, SG><<<fblocks, 256, pool_smem, ctx->stream>>>(fq)

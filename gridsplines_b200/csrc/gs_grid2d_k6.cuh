@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
   extern __shared__ double k6sm[];
   const Sweep2dParams &p = q.sw;
   const double *pool = stage_pool(p, k6sm);
-  const size_t total = (size_t)p.cols * p.rows;
   SEL sel(p.maps, pool, p.cols);
   SweepConsts k;
   k.fast_allowed = false;
@@ -36,12 +35,15 @@ __global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
   bool ok = true;
-  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)(f / p.cols), col = (int)(f % p.cols);
+  // 2-D launch: blockIdx.y = row, threads along the row (coalesced in both directions, no index division)
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < p.cols)
+  for (int row = blockIdx.y; row < p.rows; row += gridDim.y) {
+    const size_t f = (size_t)row * p.cols + col;
     const int line = XDIR ? row : col, i = XDIR ? col : row;
     LineAcc<XDIR> A(p, line);
     const int n = A.n();
-    const double p0 = A.pred(i);
+    const double p0 = p.predict[f];
     if (i == 0) {
       double face = 0.0;
       Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, p0, A.pred(1), A.rhs(0), face, flags, ok);
@@ -55,7 +57,8 @@ __global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
       double *o = q.last3 + 3 * (size_t)line;
       o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
     } else {
-      q.F[f] = gs_take_average<false>(sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), p0, A.pred(i + 1), flags, ok);
+      const double p1 = p.predict[f + (XDIR ? 1 : (size_t)p.cols)];
+      q.F[f] = gs_take_average<false>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, ok);
     }
   }
   if (flags) atomicOr(p.status, flags);
