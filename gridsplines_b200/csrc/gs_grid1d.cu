@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "gs_device.cuh"
 #include "gs_internal.h"
@@ -1018,6 +1019,247 @@ __global__ void __launch_bounds__(128, 3) k_step1d_hoist_ck(Step1dParams p, cons
 }
 
 // ---------------------------------------------------------------------------------
+// K2f: temperature-dependent conductivity (one spline table for the batch) -- assembly split from elimination,
+// checkpoint/recompute instead of a (delta, lambda) scratch.  Bit-exact: every operation of the reference is kept,
+// only WHEN it is evaluated changes.
+//
+//   k_faces1d   conductivity at every cell face, cons()'s  z((t1 + t2) / 2.0)  (A/passion/package.scala:21-25),
+//               in one elementwise pass over the blocked arrays: CR[i] = face between nodes i and i+1 (the last
+//               one against lastT), C0[line] = face between firstT and node 0.  `predict` is frozen during a step,
+//               so the spline work does not belong inside the serial Thomas chain.
+//   k_step1d_faces_ck   K2c's two-pass structure on (grid, CR): pass 1 runs the reference's elimination and keeps
+//               (delta, lambda, condL) at the end of every K-node block (through L2: 1.5 B/node); pass 2 walks the
+//               blocks backwards, recomputes each block's (delta, lambda) with the same operations into shared
+//               memory, back-substitutes, applies the predictor and stores grid' / predict' in place of its
+//               buffers.  The shared-reciprocal division and its validity fallback are those of K2.
+// DRAM: faces R 8 + W 8; pass 1 R 16; pass 2 R 16 (L2 when it fits) + W 16  =>  48-64 B/node, against K2's 67.5.
+// MEASURED (B200, C2 shape, M1Hermite3 table): 5.7 ms/step against K2's 4.3 ms -- unlike K2c, whose hoisted
+// recurrence costs 8 FP64 instructions per node, the exact elimination (~23 FP64 + range checks) is too expensive to
+// run twice, so the traffic saved does not pay for the recomputation.  Kept behind the option `faces1d` (default
+// off) as a tested, bit-exact variant.
+// ---------------------------------------------------------------------------------
+struct Faces1dParams {
+  int n;
+  long long nlines, nblocks;
+  const double *predict;
+  double *CR, *C0;
+  const double *pool;
+  int pool_len, single_off, smem_pool;
+  const double *leftT, *rightT;
+  int bc_stride;
+  unsigned *status;
+};
+
+__global__ void __launch_bounds__(256) k_faces1d(Faces1dParams p) {
+  extern __shared__ double fsm[];
+  const double *pool = p.pool;
+  if (p.smem_pool) {
+    for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) fsm[i] = p.pool[i];
+    pool = fsm;
+    __syncthreads();
+  }
+  const GsSpline z = gs_spline_view(pool, p.single_off);
+  const int lane = threadIdx.x & 31;
+  const int n = p.n;
+  unsigned flags = 0;
+  // one warp handles a run of nodes of one line block: (block, node) pairs in a grid-stride loop over warps
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = p.nblocks * n;
+  for (long long w = warp; w < total; w += nwarps) {
+    const long long blk = w / n;
+    const int i = (int)(w - blk * n);
+    const long long line = blk * GS_LB + lane;
+    const long long bcl = (line < p.nlines ? line : p.nlines - 1) * p.bc_stride;
+    const size_t e = (size_t)blk * n * GS_LB + (size_t)i * GS_LB + lane;
+    const double t2 = p.predict[e];
+    const double t3 = (i == n - 1) ? p.rightT[bcl] : p.predict[e + GS_LB];
+    p.CR[e] = gs_ads_apply(z, (t2 + t3) / 2.0, flags);
+    if (i == 0) p.C0[blk * GS_LB + lane] = gs_ads_apply(z, (p.leftT[bcl] + t2) / 2.0, flags);
+  }
+  gs_raise(p.status, flags);
+}
+
+template <int K>
+struct PipeF {
+  static constexpr int kBufBytes = K * 256;
+  static constexpr int kWarpBytes = 5 * kBufBytes + 128;   // 2 x (grid, cond) stages + lambda/predict' buffer + mbarriers
+};
+
+// elimination of node i of a line (reference order); condL is carried
+template <bool FAST>
+GS_DEV void faces_node(const Line1d &L, int i, double g, double condL, double condR, double firstT, double lastT,
+                       double &delta, double &lambda, unsigned &flags, bool &ok) {
+  const int n = L.n;
+  const double a = condL * L.pd[2 * i];
+  const double c = condR * L.pd[2 * i + 1];
+  double vect = gs_div<FAST>(-g, L.rt, ok);
+  const double diag = -(a + c) - L.inv_time;
+  if (i == 0) {
+    vect = vect - a * firstT;                                              // :65
+    gs_forward_first<FAST>(diag, c, vect, delta, lambda, ok);
+  } else if (i == n - 1) {
+    vect = vect - c * lastT;                                               // :89
+    gs_forward_last<FAST>(a, diag, vect, delta, lambda, ok);
+  } else {
+    gs_forward_unit<FAST>(a, diag, c, vect, delta, lambda, flags, ok);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_step1d_faces_ck(Step1dParams p, const double *CR, const double *C0,
+                                                         double *ckpt_g) {
+  typedef PipeF<K> PP;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = p.n;
+  const int nw = blockDim.x >> 5;
+  Line1d L;
+  L.n = n;
+  L.pd = p.predef;
+  L.pool = p.pool;
+  L.node_off = p.node_off;
+  if (p.smem_predef) {
+    double *smd = reinterpret_cast<double *>(smraw + (size_t)nw * PP::kWarpBytes);
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) smd[i] = p.predef[i];
+    L.pd = smd;
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  char *wsm = reinterpret_cast<char *>(smraw) + (size_t)wib * PP::kWarpBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(wsm + 5 * PP::kBufBytes);
+  if (lane == 0) {
+    for (int s = 0; s < 2; ++s) gs_mbar_init(&full[s], 1);
+    gs_mbar_init_fence();
+  }
+  gs_fence_proxy_async();
+  __syncthreads();
+  const long long warp = (long long)blockIdx.x * nw + wib;
+  if (warp >= p.nwarps) return;
+  bool fast_allowed = p.allow_fast != 0;
+  L.rt = gs_rcp_invariant(p.time, fast_allowed);
+  GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
+  L.inv_time = 1.0 / p.time;
+  const uint64_t pol_keep = gs_policy_evict_last(), pol_stream = gs_policy_evict_first();
+  unsigned flags = 0;
+  const size_t block_elems = (size_t)n * GS_LB;
+  const int NB = (n + K - 1) / K;
+  double *ck = ckpt_g + (size_t)warp * NB * 96 + lane;   // [block][delta | lambda | condL][32]
+  uint32_t phase = 0;
+
+  for (long long blk = p.blk0 + warp; blk < p.nblocks; blk += p.nwarps) {
+    const long long line = blk * GS_LB + lane;
+    const bool valid = line < p.nlines;
+    const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
+    double *Gblk = p.grid + (size_t)blk * block_elems;
+    double *Pblk = p.predict + (size_t)blk * block_elems;
+    const double *Cblk = CR + (size_t)blk * block_elems;
+    const double firstT = p.leftT[bcl], lastT = p.rightT[bcl];
+    const double cond0 = C0[blk * GS_LB + lane];
+    // stage s holds (grid chunk | cond chunk) in buffers 2s, 2s+1
+    auto load = [&](int c, int s, uint64_t pol) {
+      int len = min(K, n - c * K);
+      gs_mbar_expect_tx(&full[s], (uint32_t)len * 512u);
+      gs_bulk_g2s_hint(wsm + (2 * s) * PP::kBufBytes, Gblk + (size_t)c * K * GS_LB, (uint32_t)len * 256u, &full[s], pol);
+      gs_bulk_g2s_hint(wsm + (2 * s + 1) * PP::kBufBytes, Cblk + (size_t)c * K * GS_LB, (uint32_t)len * 256u, &full[s], pol);
+    };
+    unsigned lf = 0;
+    // ---- pass 1: the reference's forward elimination, checkpoints only ----
+    auto pass1 = [&](auto fastTag) -> bool {
+      constexpr bool FAST = decltype(fastTag)::value;
+      bool ok = true;
+      double delta = 0.0, lambda = 0.0, condL = cond0;
+      if (lane == 0) load(0, 0, pol_keep);
+      for (int c = 0; c < NB; ++c) {
+        const int s = c & 1;
+        if (lane == 0 && c + 1 < NB) load(c + 1, s ^ 1, pol_keep);
+        gs_mbar_wait(&full[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        const double *sG = reinterpret_cast<const double *>(wsm + (2 * s) * PP::kBufBytes) + lane;
+        const double *sC = reinterpret_cast<const double *>(wsm + (2 * s + 1) * PP::kBufBytes) + lane;
+        const int len = min(K, n - c * K);
+        for (int m = 0; m < len; ++m) {
+          const double condR = sC[m * GS_LB];
+          faces_node<FAST>(L, c * K + m, sG[m * GS_LB], condL, condR, firstT, lastT, delta, lambda, lf, ok);
+          condL = condR;
+        }
+        double *cb = ck + (size_t)c * 96;
+        cb[0] = delta; cb[32] = lambda; cb[64] = condL;
+        __syncwarp();   // everybody is done with stage s before it is refilled two chunks later
+      }
+      return ok;
+    };
+    for (int step = 0; step < p.nsteps; ++step) {
+      lf = 0;
+      bool use_fast = fast_allowed;
+      if (use_fast) {
+        bool ok = pass1(std::true_type());
+        if (!__all_sync(0xffffffffu, ok)) use_fast = false;
+      }
+      if (!use_fast) {
+        lf = 0;
+        pass1(std::false_type());
+      }
+      __syncwarp();
+      // ---- pass 2: per block, recompute (delta, lambda), back-substitute, predictor, store ----
+      if (lane == 0) load(NB - 1, (NB - 1) & 1, pol_stream);
+      double u = 0.0;
+      double cdl = 0.0, cla = 0.0, cco = cond0;   // state at the start of the current block
+      if (NB > 1) { const double *cb = ck + (size_t)(NB - 2) * 96; cdl = cb[0]; cla = cb[32]; cco = cb[64]; }
+      for (int b = NB - 1; b >= 0; --b) {
+        const int s = b & 1;
+        if (lane == 0) {
+          gs_bulk_wait_read<0>();   // block b+1's stores have read their buffers (stage s^1 and the lambda buffer)
+          if (b >= 1) load(b - 1, s ^ 1, pol_stream);
+        }
+        __syncwarp();
+        // next block's start state, fetched a block ahead
+        double ndl = 0.0, nla = 0.0, nco = cond0;
+        if (b >= 2) { const double *cb = ck + (size_t)(b - 2) * 96; ndl = cb[0]; nla = cb[32]; nco = cb[64]; }
+        gs_mbar_wait(&full[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        double *bG = reinterpret_cast<double *>(wsm + (2 * s) * PP::kBufBytes) + lane;       // grid -> grid'
+        double *bC = reinterpret_cast<double *>(wsm + (2 * s + 1) * PP::kBufBytes) + lane;   // cond -> delta
+        double *bL = reinterpret_cast<double *>(wsm + 4 * PP::kBufBytes) + lane;             // lambda -> predict'
+        const int len = min(K, n - b * K);
+        double delta = (b > 0) ? cdl : 0.0, lambda = (b > 0) ? cla : 0.0, condL = (b > 0) ? cco : cond0;
+        bool ok2 = true;
+        unsigned lf2 = 0;
+        for (int m = 0; m < len; ++m) {
+          const double condR = bC[m * GS_LB];
+          if (use_fast) faces_node<true>(L, b * K + m, bG[m * GS_LB], condL, condR, firstT, lastT, delta, lambda, lf2, ok2);
+          else faces_node<false>(L, b * K + m, bG[m * GS_LB], condL, condR, firstT, lastT, delta, lambda, lf2, ok2);
+          condL = condR;
+          bC[m * GS_LB] = delta;
+          bL[m * GS_LB] = lambda;
+        }
+        // back-substitution (backwardPassion :345-365) + predictor (arraygrid.aVal :85-87) + grid <- result
+        bool okb = fast_allowed;
+        for (int m = len - 1; m >= 0; --m) {
+          u = bC[m * GS_LB] * u + bL[m * GS_LB];
+          const double d = u - bG[m * GS_LB];
+          double q = gs_div<true>(d, r3, okb);
+          if (!okb) { q = d / 3.0; okb = fast_allowed; }
+          bL[m * GS_LB] = u + q;
+          bG[m * GS_LB] = u;
+        }
+        gs_fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          gs_bulk_s2g_hint(Gblk + (size_t)b * K * GS_LB, wsm + (2 * s) * PP::kBufBytes, (uint32_t)len * 256u, pol_stream);
+          gs_bulk_s2g_hint(Pblk + (size_t)b * K * GS_LB, wsm + 4 * PP::kBufBytes, (uint32_t)len * 256u, pol_stream);
+          gs_bulk_commit();
+        }
+        cdl = ndl; cla = nla; cco = nco;
+      }
+      if (lane == 0) gs_bulk_wait<0>();
+      __syncwarp();
+      if (!(fabs(u) <= 1.7976931348623157e308)) lf |= GS_FLAG_NONFINITE;
+      if (valid) flags |= lf;
+    }
+  }
+  gs_raise(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------
 // device index of (line, node) in the blocked layout [line / 32][node][line % 32]
@@ -1182,6 +1424,9 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
   cudaFree(g->rightT);
   cudaFree(g->scratch);
   cudaFree(g->hoist_table);
+  cudaFree(g->faces_CR);
+  cudaFree(g->faces_C0);
+  cudaFree(g->faces_ck);
   cudaFree(g->k5_ckpt);
   cudaFree(g->k5.tab);
   cudaFree(g->k5.omega_end);
@@ -1307,6 +1552,12 @@ extern "C" int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double 
 // steps the line blocks [blk0, blk1) (all of them for the public entry point)
 static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, long long blk1) {
   gs_ctx *ctx = g->ctx;
+  // K2f works one step per launch pair (faces, elimination)
+  if (nsteps > 1 && ctx->opt_pipeline && ctx->opt_faces1d && g->spline_mode == GS_SPLINE_SINGLE &&
+      !(g->all_const && ctx->opt_const_hoist) && blk0 == 0 && blk1 == g->pitch / GS_LB) {
+    for (int s = 0; s < nsteps; ++s) GS_TRY(step_blocks(g, time, 1, blk0, blk1));
+    return GS_OK;
+  }
   int block = (int)std::max<int64_t>(32, std::min<int64_t>(256, ctx->opt_block_1d / 32 * 32));
   long long nblocks = blk1 - blk0;
   // resident line threads per SM: measured optimum per path on B200 (profiles/): the hoisted kernel is
@@ -1409,6 +1660,44 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
       default: GS_LAUNCH_HOIST(8, 4); break;
     }
 #undef GS_LAUNCH_HOIST
+  } else if (ctx->opt_pipeline && ctx->opt_faces1d && g->spline_mode == GS_SPLINE_SINGLE && nsteps == 1 &&
+             blk0 == 0 && blk1 == g->pitch / GS_LB) {
+    // K2f: faces kernel + elimination with checkpoint/recompute (one step per launch pair: the faces of step k+1
+    // need predict' of step k for the whole batch)
+    constexpr int K = 16;
+    const size_t elems = (size_t)g->pitch * g->n;
+    if (!g->faces_CR) {
+      GS_CUDA(cudaMalloc(&g->faces_CR, elems * sizeof(double)));
+      GS_CUDA(cudaMalloc(&g->faces_C0, (size_t)g->pitch * sizeof(double)));
+    }
+    Faces1dParams fp;
+    fp.n = g->n; fp.nlines = g->nlines; fp.nblocks = g->pitch / GS_LB;
+    fp.predict = g->predict; fp.CR = g->faces_CR; fp.C0 = g->faces_C0;
+    fp.pool = ctx->pool_dev; fp.pool_len = p.pool_len; fp.single_off = g->single_off;
+    fp.smem_pool = (size_t)p.pool_len * sizeof(double) <= 40 * 1024 ? 1 : 0;
+    fp.leftT = g->leftT; fp.rightT = g->rightT; fp.bc_stride = g->bc_stride; fp.status = g->status;
+    const long long fwarps = std::min<long long>(fp.nblocks * g->n, (long long)ctx->sm_count * 64);
+    k_faces1d<<<(unsigned)((fwarps * 32 + 255) / 256), 256, fp.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0, ctx->stream>>>(fp);
+    ctx->launches++;
+    int pblock = 64;
+    size_t psmem = (p.smem_predef ? 2 * (size_t)g->n * sizeof(double) : 0) + (size_t)(pblock / 32) * PipeF<K>::kWarpBytes;
+    auto kern = k_step1d_faces_ck<K>;
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    int per_sm = 0;
+    GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pblock, psmem));
+    GS_REQUIRE(per_sm >= 1, "line kernel does not fit on an SM");
+    p.nwarps = std::min<long long>(nblocks, (long long)per_sm * ctx->sm_count * (pblock / 32));
+    const int NB = (g->n + K - 1) / K;
+    size_t ck_need = (size_t)p.nwarps * NB * 96;
+    if (g->faces_ck_len < ck_need) {
+      GS_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(g->faces_ck);
+      g->faces_ck = nullptr;
+      GS_CUDA(cudaMalloc(&g->faces_ck, ck_need * sizeof(double)));
+      g->faces_ck_len = ck_need;
+    }
+    int blocks = (int)((p.nwarps + pblock / 32 - 1) / (pblock / 32));
+    kern<<<blocks, pblock, psmem, ctx->stream>>>(p, g->faces_CR, g->faces_C0, g->faces_ck);
   } else if (ctx->opt_pipeline) {
     // persistent warps, each with its own bulk-copy ring
     int pblock = (int)std::max<int64_t>(32, std::min<int64_t>(128, ctx->opt_block_1d / 32 * 32));

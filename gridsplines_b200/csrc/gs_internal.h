@@ -64,6 +64,7 @@ struct gs_ctx {
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
   int64_t opt_k6 = 1;
+  int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k6_chunk = 8;
   int64_t opt_host_chunk_mb = 128;
   int64_t opt_ck_block = 16;
@@ -110,6 +111,8 @@ struct gs_grid1d {
   std::vector<int> node_off_host;  // PER_NODE pool offsets (host copy)
   gs_k5dir k5;                     // K5 tables for long lines
   double *k5_ckpt = nullptr;
+  double *faces_CR = nullptr, *faces_C0 = nullptr, *faces_ck = nullptr;   // K2f: face conductivities, checkpoints
+  size_t faces_ck_len = 0;
   double *hoist_table = nullptr;  // K2h coefficients for hoist_time
   bool hoist_valid = false;
   double hoist_time = 0.0;

@@ -49,7 +49,7 @@ def test_batch_vs_golden(gs, name, args):
 def options(ctx):
     """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
     defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0,
-                "hoist_ck": 1, "ck_block": 16}
+                "hoist_ck": 1, "ck_block": 16, "faces1d": 0}
 
     def set_(**kw):
         for k, v in kw.items():
@@ -67,7 +67,9 @@ PATHS = {
     "hoist_scratch": {"hoist_ck": 0},
     "hoist_ck32": {"ck_block": 32},
     "hoist_ck_native": {"native_div": 1},
-    "general": {"const_hoist": 0},
+    "general": {"const_hoist": 0},                          # K2: TMA ring + (delta, lambda) scratch
+    "k2f": {"const_hoist": 0, "faces1d": 1},                # K2f: faces kernel + elimination with checkpoint/recompute
+    "k2f_native_div": {"const_hoist": 0, "faces1d": 1, "native_div": 1},
     "direct": {"const_hoist": 0, "pipeline": 0},
     "native_div": {"native_div": 1, "hoist_ck": 0},
     "general_native_div": {"const_hoist": 0, "native_div": 1},
