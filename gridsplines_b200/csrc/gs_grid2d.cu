@@ -1366,6 +1366,16 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   q.cta_stride = 32;        // y sweep: a CTA owns 32 adjacent columns
   q.pitch = g->cols;
   q.bc_stride = 1;
+  q.strip = 32;
+  if (xdir && ctx->opt_k5_xstrip > 0 && ctx->opt_k5_xstrip <= 32) {
+    // x sweep: rows per CTA may be fewer than 32 so that the number of CTAs matches the SM count
+    q.strip = (int)ctx->opt_k5_xstrip;
+    blocks = (q.d.nlines + q.strip - 1) / q.strip;
+  } else if (xdir && ctx->opt_k5_xstrip == 0 && blocks < ctx->sm_count) {
+    // fewer CTAs than SMs: narrow the strips (down to 24 rows) so that every SM gets one (+1-2 % at 4096 rows)
+    q.strip = std::max(24, (q.d.nlines + ctx->sm_count - 1) / ctx->sm_count);
+    blocks = (q.d.nlines + q.strip - 1) / q.strip;
+  }
   if (xdir) {
     GS_CUDA(cudaFuncSetAttribute(k5_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k5_sweep<true, false><<<blocks, threads, smem, ctx->stream>>>(q);
@@ -1435,6 +1445,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   q.ckpt = g->k5_ckpt;
   q.cta_stride = (long long)n * 32;   // one 32-line block of the [line/32][node][line%32] layout per CTA
   q.pitch = 32;
+  q.strip = 32;
   q.bc_stride = g->bc_stride;
   q.status = g->status;
   size_t smem = k5_smem(false, kd.m, kd.S);

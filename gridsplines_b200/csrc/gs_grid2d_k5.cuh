@@ -43,6 +43,7 @@ struct K5Params {
   double *ckpt;          // [n / K5_CH][nlines rounded up to 32] lambda checkpoints (0.5 B/node each way, L2)
   // lane <-> line sweeps (y sweep, 1-D batches): element (node i, lane) of CTA b is at b * cta_stride + i * pitch + lane
   long long cta_stride, pitch;
+  int strip;             // lines per CTA (<= 32): 28 puts 147 CTAs on the 148 SMs for 4096 lines (x sweep only)
   int bc_stride;         // bound_first/last index = line * bc_stride (1-D batches: 0 = one value for all lines)
   unsigned *status;
 };
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const K5Dir &d = q.d;
   const int S = d.S, m = d.m, n = d.n;
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment k
-  const int line0 = blockIdx.x * 32, nl = min(32, d.nlines - line0);
+  const int line0 = blockIdx.x * q.strip, nl = min(q.strip, d.nlines - line0);
   // shared memory: per CTA lamE[S][32], Q[S][32], E[S][32]; per warp tile[DOUBLES] + ckpt[nch_max][32]
   double *lamE = k5sm, *Qs = lamE + S * 32, *Es = Qs + S * 32;
   double *wbase = Es + S * 32 + (size_t)k * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       if (i0 + j == n - 1) lam += ex1;
       if (i0 + j < e) Qacc = fma(c4.w, lam, Qacc);
     }
-    ckpt[(size_t)c * ck_pitch] = lam;
+    if (act) ckpt[(size_t)c * ck_pitch] = lam;   // (a narrower strip's idle lanes would hit the next CTA's slots)
     __syncwarp();
   }
   lamE[k * 32 + lane] = lam;

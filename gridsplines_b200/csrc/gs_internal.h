@@ -63,6 +63,7 @@ struct gs_ctx {
   int64_t opt_seg_len = 32;
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
+  int64_t opt_k5_xstrip = 0;   // 0 = automatic
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k6_chunk = 8;
