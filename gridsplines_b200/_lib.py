@@ -69,6 +69,7 @@ SIGNATURES = {
     "gs_grid2d_yiter_update": (_vp, C.c_double),
     "gs_grid2d_copy_from_device": (_vp, C.c_int, _vp),
     "gs_grid2d_copy_to_device": (_vp, C.c_int, _vp),
+    "gs_grid2d_bind_device": (_vp, C.c_int, _vp),
     "gs_grid2d_iteration": (_vp, C.c_double, C.c_int),
     "gs_grid2d_update_predicted": (_vp,),
     "gs_grid2d_no_heat_flow": (_vp, C.c_int),

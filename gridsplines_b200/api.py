@@ -623,6 +623,9 @@ class TwoDGrid:
     def copy_to_device(self, which: int, dptr: int):
         L.check(L.lib().gs_grid2d_copy_to_device(self._h, which, dptr))
 
+    def bind_device(self, which: int, dptr: int):
+        L.check(L.lib().gs_grid2d_bind_device(self._h, which, dptr))
+
     def updatePredicted(self):
         L.check(L.lib().gs_grid2d_update_predicted(self._h))
 

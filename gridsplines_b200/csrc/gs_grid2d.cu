@@ -928,7 +928,9 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaStreamSynchronize(g->ctx->stream);
   cudaFree(g->x.values); cudaFree(g->x.coefs);
   cudaFree(g->y.values); cudaFree(g->y.coefs);
-  cudaFree(g->grid); cudaFree(g->predict); cudaFree(g->result);
+  if (!g->bound[GS_GRID]) cudaFree(g->grid);
+  if (!g->bound[GS_PREDICT]) cudaFree(g->predict);
+  if (!g->bound[GS_RESULT]) cudaFree(g->result);
   for (int s = 0; s < 4; ++s) { cudaFree(g->b[s].values); cudaFree(g->map[s]); }
   cudaFree(g->scratch);
   cudaFree(g->iface);
@@ -1250,7 +1252,13 @@ static int launch_part(gs_grid2d *g, double time, bool xdir, bool fuse) {
 #undef GS_PART
   ctx->launches += 3;
   GS_CUDA(cudaGetLastError());
-  if (fuse) std::swap(g->predict, g->predict_alt);  // predict' was written to the second buffer
+  if (fuse) {
+    if (g->bound[GS_PREDICT]) {   // caller-owned predict: copy back instead of swapping pointers
+      GS_CUDA(cudaMemcpyAsync(g->predict, g->predict_alt, (size_t)g->cols * g->rows * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      std::swap(g->predict, g->predict_alt);  // predict' was written to the second buffer
+    }
+  }
   return GS_OK;
 }
 
@@ -1577,7 +1585,8 @@ extern "C" int gs_grid2d_yiter_update(gs_grid2d *g, double time) {
   GS_TRY(gs_ctx_use(g->ctx));
   GS_TRY(materialise_result(g));
   GS_TRY(sweep_y(g, time, true));
-  g->result_is_grid = true;
+  // (a caller-owned `result` buffer is the caller's business: it is not lazily refreshed from `grid`)
+  g->result_is_grid = !g->bound[GS_RESULT];
   return GS_OK;
 }
 // device-to-device copies of a whole array on the context stream (dptr: rows * cols doubles, row-major)
@@ -1600,6 +1609,22 @@ extern "C" int gs_grid2d_copy_to_device(gs_grid2d *g, int which, void *dptr) {
   return GS_OK;
 }
 
+// Makes the grid use caller-owned device memory (rows * cols doubles, row-major) for one of its arrays, e.g. a torch
+// tensor that is also the send / receive buffer of a collective: no staging copies.  The previous contents are not
+// copied; the caller keeps the memory alive and on the context's device.
+extern "C" int gs_grid2d_bind_device(gs_grid2d *g, int which, void *dptr) {
+  GS_REQUIRE(g && dptr, "NULL argument");
+  GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
+  GS_TRY(gs_ctx_use(g->ctx));
+  GS_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  double **slot = which == GS_GRID ? &g->grid : which == GS_PREDICT ? &g->predict : &g->result;
+  if (!g->bound[which]) cudaFree(*slot);
+  *slot = static_cast<double *>(dptr);
+  g->bound[which] = true;
+  if (which == GS_RESULT) g->result_is_grid = false;
+  return GS_OK;
+}
+
 extern "C" int gs_grid2d_update(gs_grid2d *g) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   gs_ctx *ctx = g->ctx;
@@ -1619,7 +1644,7 @@ extern "C" int gs_grid2d_iteration(gs_grid2d *g, double time, int nsteps) {
   for (int s = 0; s < nsteps; ++s) {
     GS_TRY(sweep_x(g, time));
     GS_TRY(sweep_y(g, time, true));
-    g->result_is_grid = true;
+    g->result_is_grid = !g->bound[GS_RESULT];
   }
   return GS_OK;
 }

@@ -139,6 +139,7 @@ struct gs_grid2d {
   gs_dim2d x, y;
   gs_bound2d b[4];
   double *grid = nullptr, *predict = nullptr, *result = nullptr;
+  bool bound[3] = {false, false, false};   // array lives in caller-owned device memory (gs_grid2d_bind_device)
   bool result_is_grid = false;  // after a fused iteration `result` equals `grid`
   int map_mode[4] = {0, 0, 0, 0};
   int *map[4] = {nullptr, nullptr, nullptr, nullptr};  // device, pool OFFSETS (not ids)

@@ -34,12 +34,13 @@ UPP, LOW, RIGHT, LEFT = 0, 1, 2, 3
 GRID, PREDICT, RESULT = 0, 1, 2
 
 
-def rows_to_cols(x: torch.Tensor, world: int) -> torch.Tensor:
-    """[rows/P, cols] on every rank (row-sharded)  ->  [rows, cols/P] (column-sharded), one all-to-all."""
+def rows_to_cols(x: torch.Tensor, world: int, out: torch.Tensor = None) -> torch.Tensor:
+    """[rows/P, cols] on every rank (row-sharded)  ->  [rows, cols/P] (column-sharded), one all-to-all.
+    `out` (contiguous [rows, cols/P]) receives the blocks directly when given."""
     rl, cols = x.shape
     cl = cols // world
     send = x.view(rl, world, cl).permute(1, 0, 2).contiguous()      # block j = my rows x rank j's columns
-    recv = torch.empty_like(send)
+    recv = send.new_empty(send.shape) if out is None else out.view(world, rl, cl)
     if world > 1:
         dist.all_to_all_single(recv, send)
     else:
@@ -47,17 +48,21 @@ def rows_to_cols(x: torch.Tensor, world: int) -> torch.Tensor:
     return recv.view(world * rl, cl)                                 # block i = rank i's rows x my columns
 
 
-def cols_to_rows(x: torch.Tensor, world: int) -> torch.Tensor:
-    """[rows, cols/P] (column-sharded)  ->  [rows/P, cols] (row-sharded), one all-to-all."""
+def cols_to_rows(x: torch.Tensor, world: int, out: torch.Tensor = None) -> torch.Tensor:
+    """[rows, cols/P] (column-sharded, contiguous)  ->  [rows/P, cols] (row-sharded), one all-to-all."""
     rows, cl = x.shape
     rl = rows // world
-    send = x.view(world, rl, cl).contiguous()                        # block i = rank i's rows x my columns
+    send = x.view(world, rl, cl)                                     # block i = rank i's rows x my columns (a view)
     recv = torch.empty_like(send)
     if world > 1:
         dist.all_to_all_single(recv, send)
     else:
         recv.copy_(send)
-    return recv.permute(1, 0, 2).reshape(rl, world * cl).contiguous()  # block j = my rows x rank j's columns
+    res = recv.permute(1, 0, 2)                                      # block j = my rows x rank j's columns
+    if out is None:
+        return res.reshape(rl, world * cl).contiguous()
+    out.view(rl, world, cl).copy_(res)
+    return out
 
 
 class RowShardedTwoDGrid:
@@ -97,12 +102,20 @@ class RowShardedTwoDGrid:
         return self.gx.get(which)
 
     def iteration(self, time: float, nsteps: int = 1):
+        zero_copy = hasattr(self.gx, "view")
         for _ in range(nsteps):
             self.gx.xIter(time)                                                  # 1. local rows
-            self.gy.set(RESULT, rows_to_cols(self.gx.get(RESULT), self.world))   # 2. exchange
-            self.gy.yIterUpdate(time)                                            # 3. local columns (+ Grid.update)
-            self.gx.set(GRID, cols_to_rows(self.gy.get(GRID), self.world))       # 4. back to rows
-            self.gx.set(PREDICT, cols_to_rows(self.gy.get(PREDICT), self.world))
+            if zero_copy:
+                # the local grids work in torch-owned buffers: the collective receives straight into them
+                rows_to_cols(self.gx.view(RESULT), self.world, out=self.gy.view(RESULT))           # 2. exchange
+                self.gy.yIterUpdate(time)                                                          # 3. local columns
+                cols_to_rows(self.gy.view(GRID), self.world, out=self.gx.view(GRID))               # 4. back to rows
+                cols_to_rows(self.gy.view(PREDICT), self.world, out=self.gx.view(PREDICT))
+            else:
+                self.gy.set(RESULT, rows_to_cols(self.gx.get(RESULT), self.world))
+                self.gy.yIterUpdate(time)
+                self.gx.set(GRID, cols_to_rows(self.gy.get(GRID), self.world))
+                self.gx.set(PREDICT, cols_to_rows(self.gy.get(PREDICT), self.world))
 
 
 class GsLocalGrid:
@@ -118,6 +131,15 @@ class GsLocalGrid:
         if solver is not None:
             self.g.set_solver(solver)
         self.shape = (self.g.rows, self.g.cols)
+        # the three arrays live in torch tensors bound into the library (gs_grid2d_bind_device): the collectives
+        # of the sharded driver send from / receive into them without staging copies
+        self._t = [torch.zeros(self.shape, dtype=torch.float64, device="cuda") for _ in range(3)]
+        torch.cuda.current_stream().synchronize()
+        for which, t in enumerate(self._t):
+            self.g.bind_device(which, t.data_ptr())
+
+    def view(self, which) -> torch.Tensor:
+        return self._t[which]
 
     def set_bound(self, side, kind, rep, values):
         v = np.atleast_1d(np.asarray(values, float))
@@ -127,16 +149,11 @@ class GsLocalGrid:
         L.check(L.lib().gs_grid2d_set_bound(self.g._h, side, kind, rep, v.ctypes.data_as(L._dp), len(v)))
 
     def get(self, which) -> torch.Tensor:
-        out = torch.empty(self.shape, dtype=torch.float64, device="cuda")
-        self.g.copy_to_device(which, out.data_ptr())
-        return out
+        return self._t[which].clone()
 
     def set(self, which, t: torch.Tensor):
-        t = t.contiguous()
         assert tuple(t.shape) == self.shape and t.dtype == torch.float64 and t.is_cuda
-        self.g.copy_from_device(which, t.data_ptr())
-        # the copy is asynchronous on the context stream = torch's current stream; keep `t` alive until it ran
-        self._keep = t
+        self._t[which].copy_(t)
 
     def xIter(self, time):
         self.g.xIter(time)

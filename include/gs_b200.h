@@ -174,6 +174,8 @@ int gs_grid2d_yiter_update(gs_grid2d *g, double time);    /* yIter + Grid.update
 /* device-to-device copies of a whole row-major array on the context's stream (multi-GPU glue) */
 int gs_grid2d_copy_from_device(gs_grid2d *g, int which, const void *dptr);
 int gs_grid2d_copy_to_device(gs_grid2d *g, int which, void *dptr);
+/* use caller-owned device memory (rows * cols doubles) for an array, e.g. the buffer of a collective */
+int gs_grid2d_bind_device(gs_grid2d *g, int which, void *dptr);
 int gs_grid2d_iteration(gs_grid2d *g, double time, int nsteps); /* TwoDGrid.iteration :254-258 */
 int gs_grid2d_update_predicted(gs_grid2d *g);             /* :442-444 */
 int gs_grid2d_no_heat_flow(gs_grid2d *g, int side);       /* :413-440 */
