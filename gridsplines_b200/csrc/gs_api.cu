@@ -107,10 +107,8 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   GS_REQUIRE(ctx && name, "NULL argument");
   if (!strcmp(name, "threads_per_sm_1d")) ctx->opt_threads_per_sm_1d = value;
   else if (!strcmp(name, "block_1d")) ctx->opt_block_1d = value;
-  else if (!strcmp(name, "block_y")) ctx->opt_block_y = value;
   else if (!strcmp(name, "native_div")) ctx->opt_native_div = value;
   else if (!strcmp(name, "const_hoist")) ctx->opt_const_hoist = value;
-  else if (!strcmp(name, "smem_nodes")) ctx->opt_smem_nodes = value;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = value;
   else if (!strcmp(name, "pipe_cfg")) ctx->opt_pipe_cfg = value;
   else if (!strcmp(name, "seg_len")) ctx->opt_seg_len = value;

@@ -69,8 +69,6 @@ __global__ void k5_setup(K5Setup q) {
   const double inv_time = 1.0 / q.time;
   unsigned flags = 0;
   double face = q.v_apply;   // value carried from node i-1's right face
-  // per-segment results needed by the reduced system
-  double prevP = 0.0, prevR = 0.0;  // of segment k+1 while walking k downwards: do two passes instead
   // pass 1: rows, local elimination, tables; keep (delta_e, omega_e, P, R) per segment in q.seg temporarily
   double delta = 0.0, omega = 0.0, p = 1.0, R = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -154,9 +152,7 @@ __global__ void k5_setup(K5Setup q) {
     cp = supr / den;
     // overwrite in place: segment k+1's (P, R) are still intact (different element)
     q.seg[k] = make_double4(me.x, subr, 1.0 / den, cp);
-    // keep P, R of k+1 readable: they live in q.seg[k+1].z/.w until iteration k+1 rewrites that element
   }
-  (void)prevP; (void)prevR;
   if (flags) atomicOr(q.status, flags);
 }
 

@@ -54,10 +54,8 @@ struct gs_ctx {
   // options
   int64_t opt_threads_per_sm_1d = 0;  // 0 = per-path default
   int64_t opt_block_1d = 128;
-  int64_t opt_block_y = 128;
   int64_t opt_native_div = 0;
   int64_t opt_const_hoist = 1;
-  int64_t opt_smem_nodes = -1;
   int64_t opt_pipeline = 1;
   int64_t opt_pipe_cfg = 0;
   int64_t opt_seg_len = 32;
