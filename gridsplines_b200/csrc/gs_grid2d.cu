@@ -982,6 +982,7 @@ extern "C" int gs_grid2d_set_map(gs_grid2d *g, int selector, int mode, const int
   GS_CUDA(cudaStreamSynchronize(ctx->stream));
   g->map_mode[selector] = mode;
   g->map_host[selector].assign(ids, ids + n);
+  g->k5x.valid = g->k5y.valid = false;   // K5's line-independent tables were built from the previous coefficients
   return GS_OK;
 }
 

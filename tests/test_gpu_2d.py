@@ -344,3 +344,26 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         assert max_rel_err(g.grid.result, o.result) <= tol
     finally:
         ctx.set_option("k5", 1)
+
+
+def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
+    """K5 caches its line-independent tables per (grid, direction, time step): changing the coefficients, the time
+    step or a bound's kind must rebuild them."""
+    p = cases.bc_problem("TTTT", xdir=0, ydir=0, cols=256, rows=256, coefs="const")
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.iteration(900.0); o.iteration(900.0)
+    # other constants
+    g.set_coefs(gs.ConstantCoef(gs.Spline.const(2.5), gs.Spline.const(1.1e6), gs.Spline.const(2.5 / 1.1e6)))
+    ads = [O.AlwaysDefinedSpline(O.Spline.const(v)) for v in (2.5, 1.1e6, 2.5 / 1.1e6)]
+    o.set_constant_coef(*ads)
+    g.iteration(900.0); o.iteration(900.0)
+    # other time step
+    g.iteration(450.0); o.iteration(450.0)
+    # a bound changes kind (Temperature -> HeatFlow)
+    q = np.full(256, 12.0)
+    g.bounds.left.kind = gs.FLOW
+    g.bounds.left.update(q)
+    o.set_bound(O.LEFT, O.FLOW, O.DENSE, q)
+    g.iteration(450.0); o.iteration(450.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), "K5 cache invalidation")
