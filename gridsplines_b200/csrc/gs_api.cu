@@ -183,6 +183,16 @@ extern "C" int gs_spline_create(gs_ctx *ctx, int kind, int npieces, const double
   h[4] = lowerY;
   h[5] = upperY;
   h[6] = h[7] = 0.0;
+  if (npieces >= 2) {
+    // equally spaced knots (exactly representable steps): gs_knot_floor may guess the piece arithmetically
+    volatile double step = knots[1] - knots[0];
+    bool uniform = step > 0.0;
+    for (int i = 0; i <= npieces && uniform; ++i) {
+      volatile double expect = knots[0] + (double)i * step;
+      uniform = expect == knots[i];
+    }
+    if (uniform) h[6] = 1.0 / step;
+  }
   double *k = h + GS_HDR;
   memcpy(k, knots, (size_t)(npieces + 1) * sizeof(double));
   double *pc = k + (npieces + 1);

@@ -58,7 +58,10 @@ __global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
       o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
     } else {
       const double p1 = p.predict[f + (XDIR ? 1 : (size_t)p.cols)];
-      q.F[f] = gs_take_average<false>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, ok);
+      bool okf = true;
+      double v = gs_take_average<true>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, okf);
+      if (!okf) v = gs_take_average<false>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, ok);   // operands out of the fast range
+      q.F[f] = v;
     }
   }
   if (flags) atomicOr(p.status, flags);
