@@ -66,6 +66,7 @@ GS_DEV int map_off(const Maps2d &m, int sel, int col, int row, int cols) {
 template <bool SINGLE>
 struct CoefSel {
   typedef GsSpline Z;
+  static constexpr bool single = SINGLE;
   const Maps2d &m;
   const double *pool;
   int cols;
@@ -84,6 +85,7 @@ struct CoefSel {
 // every selector is SINGLE and a literal Spline.const (ConstantCoef over Spline.const values)
 struct CoefSelLit {
   typedef GsLitConst Z;
+  static constexpr bool single = true;
   GsLitConst z[4];
   GS_DEV CoefSelLit(const Maps2d &maps, const double *pool, int) {
 #pragma unroll
@@ -1519,17 +1521,32 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   fq.first3 = g->k6_ends;
   fq.last3 = g->k6_ends + 3 * (size_t)nlines;
   size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
-  // blocks of 256 columns x a stride of rows: enough CTAs to fill the chip a few times over, each staging the
-  // spline pool once
+  // blocks of 256 columns x a stride of rows, ONE wave: as many CTAs as are resident at once, equal rows each
+  // (several short waves leave the chip part-empty while the last one drains)
   const int fbx = (g->cols + 255) / 256;
-  dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * 12 / fbx)));
   bool lit = single;
   for (int s4 = 0; s4 < 4 && lit; ++s4) lit = literal_const(ctx, p.maps.single_off[s4], nullptr);
-#define GS_FACES(XD, SG) k6_faces<XD, SG><<<fblocks, 256, pool_smem, ctx->stream>>>(fq)
+  const bool tab = !lit && p.smem_pool;
+  const int eblocks = (nlines + 127) / 128;
+#define GS_FACES(XD, SG, TB)                                        \
+  do {                                                              \
+    k6_ends<XD, SG><<<eblocks, 128, pool_smem, ctx->stream>>>(fq);  \
+    int resident = 0;                                               \
+    GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k6_faces<XD, SG, TB>, 256, pool_smem)); \
+    dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * std::max(resident, 1) / fbx)));          \
+    if (TB) fblocks = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(resident, 1), (cells / 32 + 7) / 8)), 1); \
+    k6_faces<XD, SG, TB><<<fblocks, 256, pool_smem, ctx->stream>>>(fq); \
+  } while (0)
   if (xdir) {
-    if (lit) GS_FACES(true, CoefSelLit); else if (single) GS_FACES(true, CoefSel<true>); else GS_FACES(true, CoefSel<false>);
+    if (lit) GS_FACES(true, CoefSelLit, false);
+    else if (tab) { if (single) GS_FACES(true, CoefSel<true>, true); else GS_FACES(true, CoefSel<false>, true); }
+    else if (single) GS_FACES(true, CoefSel<true>, false);
+    else GS_FACES(true, CoefSel<false>, false);
   } else {
-    if (lit) GS_FACES(false, CoefSelLit); else if (single) GS_FACES(false, CoefSel<true>); else GS_FACES(false, CoefSel<false>);
+    if (lit) GS_FACES(false, CoefSelLit, false);
+    else if (tab) { if (single) GS_FACES(false, CoefSel<true>, true); else GS_FACES(false, CoefSel<false>, true); }
+    else if (single) GS_FACES(false, CoefSel<true>, false);
+    else GS_FACES(false, CoefSel<false>, false);
   }
 #undef GS_FACES
   // 2. elimination sweep
@@ -1551,7 +1568,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
                                                 : (xdir ? k6_sweep<true, 8> : k6_sweep<false, 8>);
   GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, threads, smem, ctx->stream>>>(q);
-  ctx->launches += 2;
+  ctx->launches += 3;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
 }

@@ -21,11 +21,15 @@ struct K6FacesParams {
   double *last3;         // [nlines][3] sub, diag, rhs of node n-1
 };
 
+// The two end rows of every line (Dirichlet or heat-flow, A/Dim.scala:28-64, 86-128) with the reference's general
+// assembly: one thread per line.  Also writes the carry out of node 0 (F at i = 0) and F = 0 at i = n - 1.
 template <bool XDIR, class SEL>
-__global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
+__global__ void __launch_bounds__(128) k6_ends(K6FacesParams q) {
   extern __shared__ double k6sm[];
   const Sweep2dParams &p = q.sw;
   const double *pool = stage_pool(p, k6sm);
+  const int line = blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= (XDIR ? p.rows : p.cols)) return;
   SEL sel(p.maps, pool, p.cols);
   SweepConsts k;
   k.fast_allowed = false;
@@ -35,36 +39,190 @@ __global__ void __launch_bounds__(256) k6_faces(K6FacesParams q) {
   k.firstVol = p.firstVol; k.fC = p.fC; k.lastVol = p.lastVol; k.lA = p.lA;
   unsigned flags = 0;
   bool ok = true;
-  // 2-D launch: blockIdx.y = row, threads along the row (coalesced in both directions, no index division)
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col < p.cols)
-  for (int row = blockIdx.y; row < p.rows; row += gridDim.y) {
-    const size_t f = (size_t)row * p.cols + col;
-    const int line = XDIR ? row : col, i = XDIR ? col : row;
-    LineAcc<XDIR> A(p, line);
-    const int n = A.n();
-    const double p0 = p.predict[f];
-    if (i == 0) {
-      double face = 0.0;
-      Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, p0, A.pred(1), A.rhs(0), face, flags, ok);
-      q.F[f] = face;                       // carry into node 1: co, or cond / cap after a heat-flow end
-      double *o = q.first3 + 3 * (size_t)line;
-      o[0] = r.diag; o[1] = r.sup; o[2] = r.rhs;
-    } else if (i == n - 1) {
-      double face = face_before<XDIR, SEL, false>(A, sel, k, i, A.pred(i - 1), p0, flags, ok);
-      Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, i, p0, 0.0, A.rhs(i), face, flags, ok);
-      q.F[f] = 0.0;
-      double *o = q.last3 + 3 * (size_t)line;
-      o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
-    } else {
-      const double p1 = p.predict[f + (XDIR ? 1 : (size_t)p.cols)];
+  LineAcc<XDIR> A(p, line);
+  const int n = A.n();
+  {
+    double face = 0.0;
+    Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, A.pred(0), A.pred(1), A.rhs(0), face, flags, ok);
+    q.F[A.idx(0)] = face;                  // carry into node 1: co, or cond / cap after a heat-flow end
+    double *o = q.first3 + 3 * (size_t)line;
+    o[0] = r.diag; o[1] = r.sup; o[2] = r.rhs;
+  }
+  {
+    const int i = n - 1;
+    const double p0 = A.pred(i);
+    double face = face_before<XDIR, SEL, false>(A, sel, k, i, A.pred(i - 1), p0, flags, ok);
+    Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, i, p0, 0.0, A.rhs(i), face, flags, ok);
+    q.F[A.idx(i)] = 0.0;
+    double *o = q.last3 + 3 * (size_t)line;
+    o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
+  }
+  if (flags) atomicOr(p.status, flags);
+}
+
+// What the straight-line face path needs of one table (shared-memory copy of the pool)
+struct K6Tab {
+  double lowerX, upperX, k0, inv_h;
+  int np, fast;                 // fast: cubic pieces on equally spaced knots
+  const double *knots, *pieces;
+};
+GS_DEV K6Tab k6_tab(const double *h) {
+  K6Tab z;
+  z.np = (int)h[1];
+  z.lowerX = h[2];
+  z.upperX = h[3];
+  z.inv_h = h[6];
+  z.fast = ((int)h[0] == GS_CUBIC) && (z.inv_h != 0.0);
+  z.knots = h + GS_HDR;
+  z.k0 = z.knots[0];
+  z.pieces = z.knots + (z.np + 1);
+  return z;
+}
+// takeAverage for the common interior face: two different, ordered-able temperatures strictly inside the clamps and
+// inside ONE cubic piece.  AlwaysDefinedSpline.average then is  (0.0 + (antider(hi) - antider(lo)) + 0.0) / (hi - lo)
+// (gs_ads_average's one-piece case); the same doubles are produced here without a data-dependent branch.  Returns
+// false -- and the caller takes the general walk -- for anything else (clamped, several pieces, equal, NaN, a
+// quotient outside the fast divider's range).
+GS_DEV bool k6_face_fast(const K6Tab &z, double p0, double p1, double &v) {
+  const bool lt = p0 < p1;
+  const double lo = lt ? p0 : p1, hi = lt ? p1 : p0;
+  bool good = z.fast && (lo > z.lowerX) && (hi < z.upperX) && (lo < hi) && (lo >= z.k0);
+  int i = (int)((lo - z.k0) * z.inv_h);          // saturating conversion; NaN -> 0
+  i = max(0, min(z.np - 1, i));
+  double ka = z.knots[i], kb = z.knots[i + 1];
+  if (lo < ka) { i = max(i - 1, 0); kb = ka; ka = z.knots[i]; }
+  else if (lo >= kb) { i = min(i + 1, z.np - 1); ka = kb; kb = z.knots[i + 1]; }
+  good = good && (lo >= ka) && (hi < kb);
+  const double *pc = z.pieces + i * GS_PIECE;
+  const double x0 = pc[0], a1 = pc[1], a2 = pc[5], a3 = pc[6], a4 = pc[7];
+  const double su = hi - x0, sl = lo - x0;
+  const double Au = fma(fma(fma(fma(a4, su, a3), su, a2), su, a1), su, 0.0);   // gs_cubic_antider
+  const double Al = fma(fma(fma(fma(a4, sl, a3), sl, a2), sl, a1), sl, 0.0);
+  const double area = 0.0 + (Au - Al) + 0.0;
+  bool okd = true;
+  v = gs_div<true>(area, gs_rcp<true>(hi - lo, okd), okd);
+  return good && okd;
+}
+// second tier (a few lanes): equal temperatures (average = apply) and intervals that straddle ONE knot, both
+// strictly inside the clamps and the knots.  Follows gs_ads_average / gs_spline_area term by term (same doubles),
+// native division.  Returns false for anything else.
+__device__ __noinline__ bool k6_face_mid(const double *h, double p0, double p1, double *out) {
+  const GsSpline s = gs_spline_view(h, 0);
+  if (s.kind != GS_CUBIC) return false;
+  const bool eq = p0 == p1;
+  const double lo = eq ? gs_jmin(p0, p1) : (p0 < p1 ? p0 : p1), hi = eq ? gs_jmax(p0, p1) : (p0 < p1 ? p1 : p0);
+  if (!(lo > s.lowerX && hi < s.upperX && lo >= s.knots[0] && hi <= s.knots[s.np])) return false;
+  const int i = gs_knot_floor(s, lo);
+  const double *pc = s.pieces + i * GS_PIECE;
+  if (eq) {
+    *out = gs_piece_apply(GS_CUBIC, pc, lo);
+    return true;
+  }
+  if (i + 2 > s.np) return false;
+  const double kb = s.knots[i + 1];
+  if (!(hi > kb && hi < s.knots[i + 2])) return false;
+  double acc = 0.0 + (gs_cubic_antider(pc, kb) - gs_cubic_antider(pc, lo));
+  acc = acc + (gs_cubic_antider(pc + GS_PIECE, hi) - gs_cubic_antider(pc + GS_PIECE, kb));
+  acc = 0.0 + acc + 0.0;
+  bool ok = true;
+  *out = gs_div<false>(acc, gs_rcp<false>(hi - lo, ok), ok);
+  return true;
+}
+// the general walk (cold): every case of the reference, native division
+__device__ __noinline__ double k6_face_general(const double *pool, int off, double p0, double p1, unsigned *status) {
+  unsigned flags = 0;
+  bool ok = true;
+  double v = gs_take_average<false>(gs_spline_view(pool, off), p0, p1, flags, ok);
+  if (flags) atomicOr(status, flags);
+  return v;
+}
+
+// Interior faces F[i], 1 <= i <= n - 2, of every line.  TAB (table-driven maps, pool staged in shared memory): every
+// warp walks (row, 32-column group) tiles  t = warp + k * nwarps  in row-major order, the column group rotated by the
+// row so that no warp keeps the same columns (a boundary layer along one edge makes those columns' faces take the
+// slower tiers); loads run D tiles ahead of the arithmetic.  Otherwise (literal constants, oversized pools): blocks
+// of 256 columns x a stride of rows with the generic evaluation.
+template <bool XDIR, class SEL, bool TAB>
+__global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
+  extern __shared__ double k6sm[];
+  const Sweep2dParams &p = q.sw;
+  const int c_lo = XDIR ? 1 : 0, c_hi = XDIR ? p.cols - 1 : p.cols;
+  const int r_lo = XDIR ? 0 : 1, r_hi = XDIR ? p.rows : p.rows - 1;
+  const size_t nb = XDIR ? 1 : (size_t)p.cols;
+  if (TAB) {
+    for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) k6sm[i] = p.pool[i];
+    __syncthreads();
+    constexpr bool single = SEL::single;
+    constexpr int D = 2;
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ncg = (p.cols + 31) >> 5, nrows = r_hi - r_lo;
+    const int dj = W % ncg, drow = W / ncg, drm = drow % ncg;
+    // tile walker: j = t % ncg, row = t / ncg (relative to r_lo), rmod = row % ncg
+    int j = w % ncg, row = w / ncg, rmod = row % ncg;
+    int off = p.maps.single_off[GS_SEL_APPLY];
+    K6Tab z = k6_tab(k6sm + off);
+    double q0[D], q1[D];
+    int qrow[D], qcol[D];
+    auto fetch = [&](int d) {   // loads of the walker's tile into slot d, then advances the walker
+      int cg = j + rmod;
+      if (cg >= ncg) cg -= ncg;
+      const int col = cg * 32 + lane;
+      qrow[d] = row;
+      qcol[d] = (col >= c_lo && col < c_hi) ? col : -1;
+      q0[d] = q1[d] = 0.0;
+      if (row < nrows && qcol[d] >= 0) {
+        const double *pp = p.predict + (size_t)(row + r_lo) * p.cols + col;
+        q0[d] = pp[0];
+        q1[d] = pp[nb];
+      }
+      j += dj;
+      const int c = j >= ncg;
+      j -= c ? ncg : 0;
+      row += drow + c;
+      rmod += drm + c;
+      if (rmod >= ncg) rmod -= ncg;
+    };
+#pragma unroll
+    for (int d = 0; d < D; ++d) fetch(d);
+#pragma unroll 1
+    while (qrow[0] < nrows) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int rw = qrow[d] + r_lo, col = qcol[d];
+        const bool live = qrow[d] < nrows;
+        const double c0 = q0[d], c1 = q1[d];
+        fetch(d);
+        if (live && col >= 0) {
+          if (!single) {
+            off = map_off(p.maps, GS_SEL_APPLY, col, rw, p.cols);
+            z = k6_tab(k6sm + off);
+          }
+          double v;
+          if (!k6_face_fast(z, c0, c1, v)) {
+            if (!k6_face_mid(k6sm + off, c0, c1, &v)) v = k6_face_general(p.pool, off, c0, c1, p.status);
+          }
+          q.F[(size_t)rw * p.cols + col] = v;
+        }
+      }
+    }
+  } else {
+    const double *pool = stage_pool(p, k6sm);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!(col >= c_lo && col < c_hi)) return;
+    SEL sel(p.maps, pool, p.cols);
+    unsigned flags = 0;
+    bool ok = true;
+    for (int row = r_lo + blockIdx.y; row < r_hi; row += gridDim.y) {
+      const size_t f = (size_t)row * p.cols + col;
+      const double p0 = p.predict[f], p1 = p.predict[f + nb];
       bool okf = true;
       double v = gs_take_average<true>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, okf);
       if (!okf) v = gs_take_average<false>(sel.get(GS_SEL_APPLY, col, row), p0, p1, flags, ok);   // operands out of the fast range
       q.F[f] = v;
     }
+    if (flags) atomicOr(p.status, flags);
   }
-  if (flags) atomicOr(p.status, flags);
 }
 
 // ---- sweep -------------------------------------------------------------------------------------------------------

@@ -346,6 +346,38 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         ctx.set_option("k5", 1)
 
 
+@pytest.mark.parametrize("field", ["uniform", "clamped", "blocks", "knots"])
+def test_k6_face_tiers(O, gs, ctx, field):
+    """The faces kernel answers the common face (two different temperatures inside one table piece) in straight-line
+    code and hands everything else to slower tiers: equal temperatures (average = apply), one straddled knot, and the
+    reference's general walk (clamps, several pieces, values on a knot).  Each field below lives in one of those."""
+    ctx.set_option("k5", 0)
+    try:
+        p = cases.bc_problem("TTTT", xdir=0, ydir=1, cols=256, rows=288, coefs="hermite")
+        r = np.random.default_rng(11)
+        shape = p.grid0.shape
+        if field == "uniform":
+            g0 = np.full(shape, 4.0)
+        elif field == "clamped":
+            g0 = r.uniform(-60.0, 140.0, shape)          # the tables cover a narrower range: clamp areas on many faces
+        elif field == "blocks":
+            g0 = np.kron(r.integers(-2, 8, (shape[0] // 16, shape[1] // 16)) * 9.5, np.ones((16, 16)))
+        else:
+            g0 = r.integers(-2, 8, shape) * 10.0         # every temperature exactly on a knot
+        p.grid0 = g0.astype(float)
+        p.predict0 = p.grid0.copy()
+        g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+        g.set_solver(gs.SOLVER_PARTITIONED)
+        g.iteration(900.0, nsteps=2)
+        for _ in range(2):
+            o.iteration(900.0)
+        O.set_ascending_fold(True)
+        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 tiers {field}", tol=tol)
+    finally:
+        ctx.set_option("k5", 1)
+
+
 def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
     """K5 caches its line-independent tables per (grid, direction, time step): changing the coefficients, the time
     step or a bound's kind must rebuild them."""
