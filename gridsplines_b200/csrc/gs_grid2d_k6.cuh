@@ -248,29 +248,51 @@ __device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, in
     const int jj = lane & (CH - 1);
     if (jj < len) {
       const size_t off = (size_t)line0 * q.cols + i0 + jj;
-#pragma unroll 4
-      for (int r = lane / CH; r < nl; r += 32 / CH) {
-        k5_cp8(&tileT[jj * PITCH + r], q.rhs + off + (size_t)r * q.cols);
-        k5_cp8(&tileF[jj * PITCH + r], q.F + off + (size_t)r * q.cols);
+      const double *gT = q.rhs + off, *gF = q.F + off;
+      const size_t rs = (size_t)(32 / CH) * q.cols;
+      int r = lane / CH;
+      gT += (size_t)r * q.cols; gF += (size_t)r * q.cols;
+      double *sT = &tileT[jj * PITCH + r], *sF = &tileF[jj * PITCH + r];
+#pragma unroll
+      for (int u = 0; u < CH; ++u, r += 32 / CH) {
+        if (r < nl) {
+          k5_cp8(sT + u * (32 / CH), gT);
+          k5_cp8(sF + u * (32 / CH), gF);
+        }
+        gT += rs; gF += rs;
       }
     }
   } else {
     if (lane < nl) {
       const size_t off = (size_t)i0 * q.cols + line0 + lane;
-#pragma unroll 8
-      for (int j = 0; j < len; ++j) {
-        k5_cp8(&tileT[j * PITCH + lane], q.rhs + off + (size_t)j * q.cols);
-        k5_cp8(&tileF[j * PITCH + lane], q.F + off + (size_t)j * q.cols);
+      const double *gT = q.rhs + off, *gF = q.F + off;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (j < len) {
+          k5_cp8(&tileT[j * PITCH + lane], gT);
+          k5_cp8(&tileF[j * PITCH + lane], gF);
+        }
+        gT += q.cols; gF += q.cols;
       }
     }
   }
   k5_commit();
 }
 
-// elimination of one node; returns delta, updates lambda (and omega)
+// elimination state carried along a line: (delta, lambda, omega) of the last node and its upper face value
 struct K6State {
   double delta, lambda, omega, fprev;
 };
+
+// 1 / b to within an ulp: hardware seed (relative error < 2^-20) and one cubically convergent step
+// y0 (1 + e + e^2), e = 1 - b y0.  K6 is the tolerance solver (<= 1e-12 per field); a division's last-bit rounding
+// is not part of its contract, its speed is: the pivot's reciprocal sits on every node's critical path.
+__device__ __forceinline__ double k6_rcp(double b) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(b));
+  const double e = fma(-b, y0, 1.0);
+  return fma(y0, fma(e, e, e), y0);
+}
 
 template <bool XDIR, int CH>
 __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
@@ -296,24 +318,33 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   const double l_sub = q.last3[3 * (size_t)line], l_diag = q.last3[3 * (size_t)line + 1], l_rhs = q.last3[3 * (size_t)line + 2];
   const size_t lstride = XDIR ? 1 : (size_t)q.cols, lbase = XDIR ? (size_t)line * q.cols : (size_t)line;
 
-  // one node of the forward elimination; st carries (delta, lambda, omega, fprev)
-  auto node = [&](int i, double t, double F, double2 cf, K6State &st) {
-    double sub, diag, sup, rhs;
-    if (i == 0) { sub = 0.0; diag = f_diag; sup = f_sup; rhs = f_rhs; }
-    else if (i == n - 1) { sub = l_sub; diag = l_diag; sup = 0.0; rhs = l_rhs; }
-    else {
-      sub = cf.x * st.fprev;
-      sup = cf.y * F;
-      diag = -(sub + sup) - inv_time;
-      rhs = -t * inv_time;
-    }
-    const double inv = __drcp_rn(diag + sub * st.delta);
+  // forward elimination of an interior node (0 < i < n - 1); st carries (delta, lambda, omega, fprev)
+  auto node_mid = [&](double t, double F, double2 cf, K6State &st) {
+    const double sub = cf.x * st.fprev, sup = cf.y * F;
+    const double diag = -(sub + sup) - inv_time, rhs = -t * inv_time;
+    const double inv = k6_rcp(diag + sub * st.delta);
     const double beta = -sub * inv;
     st.delta = -sup * inv;
     st.lambda = fma(rhs, inv, st.lambda * beta);
     st.omega = beta * st.omega;
     st.fprev = F;
   };
+  // any node: the two end rows come assembled from k6_ends
+  auto node_any = [&](int i, double t, double F, double2 cf, K6State &st) {
+    if (i > 0 && i < n - 1) { node_mid(t, F, cf, st); return; }
+    double sub, diag, sup, rhs;
+    if (i == 0) { sub = 0.0; diag = f_diag; sup = f_sup; rhs = f_rhs; }
+    else { sub = l_sub; diag = l_diag; sup = 0.0; rhs = l_rhs; }
+    const double inv = k6_rcp(diag + sub * st.delta);
+    const double beta = -sub * inv;
+    st.delta = -sup * inv;
+    st.lambda = fma(rhs, inv, st.lambda * beta);
+    st.omega = beta * st.omega;
+    st.fprev = F;
+  };
+  // a chunk is `plain` when it is full and holds neither node 0 nor the segment's last node e (hence not n - 1):
+  // its loops are unrolled without per-node tests
+  auto plain = [&](int i0) { return i0 > 0 && i0 + CH - 1 < e; };
 
   // ---- phase A ----
   K6State st;
@@ -321,6 +352,7 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   st.fprev = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
   double P = 1.0, Qa = 0.0, R = 0.0;
   if (nch > 0) k6_load<XDIR, CH>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
+#pragma unroll 1
   for (int c = 0; c < nch; ++c) {
     const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
     double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
@@ -334,12 +366,22 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       k5_wait<0>();
     }
     __syncwarp();
-    for (int j = 0; j < len; ++j) {
-      node(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
-      if (i0 + j < e) {   // x_s = P x_e + Q + R L gathers nodes s .. e-1
-        Qa = fma(P, st.lambda, Qa);
+    if (plain(i0)) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        node_mid(tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
+        Qa = fma(P, st.lambda, Qa);      // x_s = P x_e + Q + R L gathers nodes s .. e-1
         R = fma(P, st.omega, R);
         P = P * st.delta;
+      }
+    } else {
+      for (int j = 0; j < len; ++j) {
+        node_any(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
+        if (i0 + j < e) {
+          Qa = fma(P, st.lambda, Qa);
+          R = fma(P, st.omega, R);
+          P = P * st.delta;
+        }
       }
     }
     ckpt[(size_t)c * ck_pitch] = make_double4(st.delta, st.lambda, st.omega, st.fprev);
@@ -389,10 +431,18 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   }
   double4 ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : make_double4(0.0, 0.0, 0.0, 0.0);
   const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
+#pragma unroll 1
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
     double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
     const double2 *cf = tabs2 + (c & 1) * CH;
+    // old grid values of the chunk (fused Grid.update): issued ahead of the arithmetic
+    double gold[CH];
+    const size_t yoff = (size_t)i0 * q.cols + line0 + lane;
+    if (!XDIR) {
+#pragma unroll
+      for (int u = 0; u < CH; ++u) gold[u] = (act && u < len) ? q.grid_io[yoff + (size_t)u * q.cols] : 0.0;
+    }
     if (c > 0) {
       double *nT = tiles + ((c - 1) & 1) * 2 * TD;
       k6_load<XDIR, CH>(q, line0, nl, i0 - CH, CH, nT, nT + TD, tabs2 + ((c - 1) & 1) * CH, lane);
@@ -409,39 +459,55 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       sc.delta = 0.0; sc.lambda = L; sc.omega = 0.0; sc.fprev = f_seg;   // lambda_s = rhs/Delta + beta_s L
     }
     if (c > 1) ck_next = ckpt[(size_t)(c - 2) * ck_pitch];
-    for (int j = 0; j < len; ++j) {
-      node(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], sc);
-      tF[j * PITCH + lane] = sc.delta;
-      tT[j * PITCH + lane] = sc.lambda;
+    double xs[CH];
+    if (plain(i0)) {
+      double dl[CH], la[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        node_mid(tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], sc);
+        dl[j] = sc.delta; la[j] = sc.lambda;
+      }
+#pragma unroll
+      for (int j = CH - 1; j >= 0; --j) {
+        x = fma(dl[j], x, la[j]);
+        xs[j] = x;
+      }
+    } else {
+      for (int j = 0; j < len; ++j) {
+        node_any(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], sc);
+        tF[j * PITCH + lane] = sc.delta;
+        tT[j * PITCH + lane] = sc.lambda;
+      }
+#pragma unroll
+      for (int j = CH - 1; j >= 0; --j) {
+        xs[j] = 0.0;
+        if (j < len) {
+          if (i0 + j != e) x = fma(tF[j * PITCH + lane], x, tT[j * PITCH + lane]);
+          xs[j] = x;
+        }
+      }
     }
     if (XDIR) {
-      for (int j = len - 1; j >= 0; --j) {
-        if (i0 + j != e) x = fma(tF[j * PITCH + lane], x, tT[j * PITCH + lane]);
-        tT[j * PITCH + lane] = x;
-      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) tT[j * PITCH + lane] = xs[j];
       __syncwarp();
       const int jj = lane & (CH - 1);
       if (jj < len) {
-        double *g = q.out + (size_t)line0 * q.cols + i0 + jj;
-#pragma unroll 4
-        for (int r = lane / CH; r < nl; r += 32 / CH) g[(size_t)r * q.cols] = tT[jj * PITCH + r];
+        int r = lane / CH;
+        double *g = q.out + (size_t)(line0 + r) * q.cols + i0 + jj;
+        const size_t rs = (size_t)(32 / CH) * q.cols;
+#pragma unroll
+        for (int u = 0; u < CH; ++u, r += 32 / CH, g += rs)
+          if (r < nl) *g = tT[jj * PITCH + r];
       }
     } else if (act) {
-      const size_t off = (size_t)i0 * q.cols + line0 + lane;
-      double *G = q.grid_io + off, *Pp = q.predict_out + off;
-      for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
-        double gold[8];
+      double *G = q.grid_io + yoff, *Pp = q.predict_out + yoff;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.cols] : 0.0;
-#pragma unroll
-        for (int u = 7; u >= 0; --u) {
-          const int j = jb + u;
-          if (j < len) {
-            if (i0 + j != e) x = fma(tF[j * PITCH + lane], x, tT[j * PITCH + lane]);
-            const double dl = x - gold[u];                                   // Grid.update :474-481, aVal :508-512
-            Pp[(size_t)j * q.cols] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
-            G[(size_t)j * q.cols] = x;
-          }
+      for (int u = 0; u < CH; ++u) {
+        if (u < len) {
+          const double xv = xs[u], d = xv - gold[u];                      // Grid.update :474-481, aVal :508-512
+          Pp[(size_t)u * q.cols] = (fabs(d) > 1.5) ? xv : xv + d / 2.0;
+          G[(size_t)u * q.cols] = xv;
         }
       }
     }
