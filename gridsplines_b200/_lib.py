@@ -67,6 +67,8 @@ SIGNATURES = {
     "gs_grid2d_yiter": (_vp, C.c_double),
     "gs_grid2d_update": (_vp,),
     "gs_grid2d_yiter_update": (_vp, C.c_double),
+    "gs_grid2d_yiter_update_begin": (_vp, C.c_double, _vp, _vp, _vp),
+    "gs_grid2d_yiter_update_end": (_vp, C.c_double, _vp, C.c_int, C.c_int),
     "gs_grid2d_copy_from_device": (_vp, C.c_int, _vp),
     "gs_grid2d_copy_to_device": (_vp, C.c_int, _vp),
     "gs_grid2d_bind_device": (_vp, C.c_int, _vp),

@@ -617,6 +617,15 @@ class TwoDGrid:
         """yIter + Grid.update in one pass (the second half of iteration)."""
         L.check(L.lib().gs_grid2d_yiter_update(self._h, time))
 
+    def yIterUpdateBegin(self, time: float, halo_prev: int | None, halo_next: int | None, exported: int):
+        """First half of the y sweep of a row-sharded grid (device pointers; None = physical boundary on that end):
+        writes this rank's 6 x cols interface values to `exported` for the all-gather."""
+        L.check(L.lib().gs_grid2d_yiter_update_begin(self._h, time, halo_prev, halo_next, exported))
+
+    def yIterUpdateEnd(self, time: float, gathered: int, nranks: int, rank: int):
+        """Second half: `gathered` = [nranks][6][cols] device doubles, every rank's `exported` in rank order."""
+        L.check(L.lib().gs_grid2d_yiter_update_end(self._h, time, gathered, nranks, rank))
+
     def copy_from_device(self, which: int, dptr: int):
         L.check(L.lib().gs_grid2d_copy_from_device(self._h, which, dptr))
 

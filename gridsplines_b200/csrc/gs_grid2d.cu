@@ -941,6 +941,7 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->k6_F);
   cudaFree(g->k6_ends);
   cudaFree(g->k6_ckpt);
+  cudaFree(g->k6_split);
   for (gs_k5dir *kd : {&g->k5x, &g->k5y}) {
     cudaFree(kd->tab);
     cudaFree(kd->omega_end);
@@ -1494,7 +1495,16 @@ static bool use_k6(gs_grid2d *g, bool xdir) {
   return S >= 2 && k6_smem(ctx, xdir, S) <= ctx->smem_optin;
 }
 
-static int launch_k6(gs_grid2d *g, double time, bool xdir) {
+// arguments of the split y sweep (row-sharded grids): gs_grid2d_yiter_update_begin / _end
+struct K6Split {
+  int mode;                              // K6_BEGIN / K6_END
+  const double *halo_prev, *halo_next;   // device, [cols]; NULL = that end is the physical boundary
+  double *exported;                      // device, [6][cols]
+  const double *gathered;                // device, [nranks][6][cols]
+  int nranks, rank;
+};
+
+static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split = nullptr) {
   gs_ctx *ctx = g->ctx;
   GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
   GS_TRY(gs_ctx_sync_pool(ctx));
@@ -1505,6 +1515,9 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   if (!g->k6_ends) GS_CUDA(cudaMalloc(&g->k6_ends, ends_need * sizeof(double)));
   const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / 8 + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
   if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
+  const int mode = split ? split->mode : K6_FUSED;
+  const size_t nl_pad = ((size_t)nlines + 31) / 32 * 32;
+  if (split && !g->k6_split) GS_CUDA(cudaMalloc(&g->k6_split, (nl_pad + 16 * 3 * nl_pad) * sizeof(double)));
   // 1. faces + end rows of this direction (reads predict, rhs; every spline evaluation of the sweep happens here)
   K6FacesParams fq;
   bool single;
@@ -1520,6 +1533,11 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   fq.F = g->k6_F;
   fq.first3 = g->k6_ends;
   fq.last3 = g->k6_ends + 3 * (size_t)nlines;
+  fq.open_first = split && split->halo_prev;
+  fq.open_last = split && split->halo_next;
+  fq.halo_prev = split ? split->halo_prev : nullptr;
+  fq.halo_next = split ? split->halo_next : nullptr;
+  fq.fm1 = g->k6_split;
   size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
   // blocks of 256 columns x a stride of rows, ONE wave: as many CTAs as are resident at once, equal rows each
   // (several short waves leave the chip part-empty while the last one drains)
@@ -1537,7 +1555,9 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
     if (TB) fblocks = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(resident, 1), (cells / 32 + 7) / 8)), 1); \
     k6_faces<XD, SG, TB><<<fblocks, 256, pool_smem, ctx->stream>>>(fq); \
   } while (0)
-  if (xdir) {
+  if (mode == K6_END) {
+    // the faces and end rows of the begin call are still in place
+  } else if (xdir) {
     if (lit) GS_FACES(true, CoefSelLit, false);
     else if (tab) { if (single) GS_FACES(true, CoefSel<true>, true); else GS_FACES(true, CoefSel<false>, true); }
     else if (single) GS_FACES(true, CoefSel<true>, false);
@@ -1562,13 +1582,24 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir) {
   q.ckpt = g->k6_ckpt;
   q.time = time;
   q.status = g->status;
+  q.open_first = fq.open_first; q.open_last = fq.open_last;
+  q.fm1 = g->k6_split;
+  q.cdw = g->k6_split ? g->k6_split + nl_pad : nullptr;
+  q.exported = split ? split->exported : nullptr;
+  q.gathered = split ? split->gathered : nullptr;
+  q.nranks = split ? split->nranks : 1;
+  q.rank = split ? split->rank : 0;
   size_t smem = k6_smem(ctx, xdir, q.S);
   int blocks = (nlines + 31) / 32, threads = 32 * q.S;
-  void (*kern)(K6Params) = k6_chunk(ctx) == 16 ? (xdir ? k6_sweep<true, 16> : k6_sweep<false, 16>)
-                                                : (xdir ? k6_sweep<true, 8> : k6_sweep<false, 8>);
+  void (*kern)(K6Params);
+  const bool ch16 = k6_chunk(ctx) == 16;
+  if (mode == K6_BEGIN) kern = ch16 ? k6_sweep<false, 16, K6_BEGIN> : k6_sweep<false, 8, K6_BEGIN>;
+  else if (mode == K6_END) kern = ch16 ? k6_sweep<false, 16, K6_END> : k6_sweep<false, 8, K6_END>;
+  else kern = ch16 ? (xdir ? k6_sweep<true, 16, K6_FUSED> : k6_sweep<false, 16, K6_FUSED>)
+                   : (xdir ? k6_sweep<true, 8, K6_FUSED> : k6_sweep<false, 8, K6_FUSED>);
   GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<blocks, threads, smem, ctx->stream>>>(q);
-  ctx->launches += 3;
+  ctx->launches += mode == K6_END ? 1 : 3;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
 }
@@ -1604,6 +1635,44 @@ extern "C" int gs_grid2d_yiter_update(gs_grid2d *g, double time) {
   GS_TRY(materialise_result(g));
   GS_TRY(sweep_y(g, time, true));
   // (a caller-owned `result` buffer is the caller's business: it is not lazily refreshed from `grid`)
+  g->result_is_grid = !g->bound[GS_RESULT];
+  return GS_OK;
+}
+// The y sweep + Grid.update of a ROW-SHARDED grid, split around the ranks' exchange (partitioned solver only).  This
+// grid holds rows [r0, r1) of every column; `halo_prev` / `halo_next` are the predict rows just above / below them
+// (device, cols doubles; NULL where this rank holds the physical boundary, whose bound then applies).
+//   begin: faces, forward elimination of the local rows and their condensation into ONE segment per column ->
+//          exported[6][cols] (device).  The caller all-gathers `exported` of all ranks, in rank order.
+//   end:   every rank solves the ranks' reduced system from gathered[nranks][6][cols], then back-substitutes, updates
+//          grid and predict.
+extern "C" int gs_grid2d_yiter_update_begin(gs_grid2d *g, double time, const void *halo_prev, const void *halo_next,
+                                            void *exported) {
+  GS_REQUIRE(g && exported, "NULL argument");
+  GS_TRY(gs_ctx_use(g->ctx));
+  GS_REQUIRE(g->solver != GS_SOLVER_THOMAS, "the split y sweep needs the partitioned solver (GS_SOLVER_AUTO / PARTITIONED)");
+  GS_REQUIRE(g->ctx->opt_k6 && g->rows >= 16, "the split y sweep needs K6 and at least 16 local rows");
+  {
+    int m, S;
+    k6_shape(g->ctx, g->rows, &m, &S);
+    GS_REQUIRE(S >= 2 && S <= 16 && k6_smem(g->ctx, false, S) <= g->ctx->smem_optin, "local rows do not fit the K6 shape");
+  }
+  GS_REQUIRE(!(halo_next == nullptr && g->b[GS_LOW].kind == GS_FLOW && halo_prev != nullptr),
+             "a lower HeatFlow bound is not supported on a sharded grid (it reads the neighbouring column's last row)");
+  GS_TRY(materialise_result(g));
+  K6Split sp{K6_BEGIN, (const double *)halo_prev, (const double *)halo_next, (double *)exported, nullptr, 1, 0};
+  GS_TRY(launch_k6(g, time, false, &sp));
+  g->k6_split_open = true;
+  return GS_OK;
+}
+extern "C" int gs_grid2d_yiter_update_end(gs_grid2d *g, double time, const void *gathered, int nranks, int rank) {
+  GS_REQUIRE(g && gathered, "NULL argument");
+  GS_REQUIRE(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "bad rank / nranks (at most 16 ranks)");
+  GS_REQUIRE(g->k6_split_open, "gs_grid2d_yiter_update_end without a matching _begin");
+  GS_TRY(gs_ctx_use(g->ctx));
+  K6Split sp{K6_END, rank > 0 ? (const double *)gathered : nullptr, rank + 1 < nranks ? (const double *)gathered : nullptr,
+             nullptr, (const double *)gathered, nranks, rank};
+  GS_TRY(launch_k6(g, time, false, &sp));
+  g->k6_split_open = false;
   g->result_is_grid = !g->bound[GS_RESULT];
   return GS_OK;
 }

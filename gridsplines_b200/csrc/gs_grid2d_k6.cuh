@@ -19,6 +19,11 @@ struct K6FacesParams {
   double *F;             // [rows * cols] face values (stored at node i's position)
   double *first3;        // [nlines][3] diag, sup, rhs of node 0
   double *last3;         // [nlines][3] sub, diag, rhs of node n-1
+  // row-sharded y sweep (a rank owns rows [r0, r1) of every column): an open end has no boundary row, its outer
+  // neighbour is a halo row of predict held by the adjacent rank
+  int open_first, open_last;
+  const double *halo_prev, *halo_next;   // [nlines] predict of the row above node 0 / below node n-1
+  double *fm1;                            // [nlines] face between the upper halo row and node 0
 };
 
 // The two end rows of every line (Dirichlet or heat-flow, A/Dim.scala:28-64, 86-128) with the reference's general
@@ -41,14 +46,22 @@ __global__ void __launch_bounds__(128) k6_ends(K6FacesParams q) {
   bool ok = true;
   LineAcc<XDIR> A(p, line);
   const int n = A.n();
-  {
+  if (q.open_first) {
+    // face above node 0 (coefficients of row -1, like the reference's coefs(col, -1) for the face of the first row)
+    q.fm1[line] = gs_take_average<false>(XDIR ? sel.get(GS_SEL_APPLY, -1, line) : sel.get(GS_SEL_APPLY, line, -1),
+                                         q.halo_prev[line], A.pred(0), flags, ok);
+  } else {
     double face = 0.0;
     Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, A.pred(0), A.pred(1), A.rhs(0), face, flags, ok);
     q.F[A.idx(0)] = face;                  // carry into node 1: co, or cond / cap after a heat-flow end
     double *o = q.first3 + 3 * (size_t)line;
     o[0] = r.diag; o[1] = r.sup; o[2] = r.rhs;
   }
-  {
+  if (q.open_last) {
+    const int i = n - 1;
+    q.F[A.idx(i)] = gs_take_average<false>(sel.get(GS_SEL_APPLY, A.col(i), A.row(i)), A.pred(i), q.halo_next[line],
+                                           flags, ok);
+  } else {
     const int i = n - 1;
     const double p0 = A.pred(i);
     double face = face_before<XDIR, SEL, false>(A, sel, k, i, A.pred(i - 1), p0, flags, ok);
@@ -146,8 +159,9 @@ template <bool XDIR, class SEL, bool TAB>
 __global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
   extern __shared__ double k6sm[];
   const Sweep2dParams &p = q.sw;
-  const int c_lo = XDIR ? 1 : 0, c_hi = XDIR ? p.cols - 1 : p.cols;
-  const int r_lo = XDIR ? 0 : 1, r_hi = XDIR ? p.rows : p.rows - 1;
+  // an open first end has no boundary row: face 0 is an ordinary interior face
+  const int c_lo = XDIR ? (q.open_first ? 0 : 1) : 0, c_hi = XDIR ? p.cols - 1 : p.cols;
+  const int r_lo = XDIR ? 0 : (q.open_first ? 0 : 1), r_hi = XDIR ? p.rows : p.rows - 1;
   const size_t nb = XDIR ? 1 : (size_t)p.cols;
   if (TAB) {
     for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) k6sm[i] = p.pool[i];
@@ -237,7 +251,17 @@ struct K6Params {
   double4 *ckpt;           // [n / CH][nlines padded]: delta, lambda, omega, fprev at the end of every chunk
   double time;
   unsigned *status;
+  // split sweep of a row-sharded grid (K6_BEGIN / K6_END around the ranks' exchange)
+  int open_first, open_last;
+  const double *fm1;       // [nlines] face above node 0 (open first end)
+  double *cdw;             // [S][3][nlines padded]: the local reduced system after elimination, E_k = c E_{k+1} + d + w L0
+  double *exported;        // [6][nlines]: this rank as ONE segment: C, D, W of its last node and P, Q, R of its first
+  const double *gathered;  // [nranks][6][nlines]
+  int nranks, rank;
 };
+#define K6_FUSED 0
+#define K6_BEGIN 1
+#define K6_END 2
 
 template <bool XDIR, int CH>
 __device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, int i0, int len, double *tileT,
@@ -294,7 +318,10 @@ __device__ __forceinline__ double k6_rcp(double b) {
   return fma(y0, fma(e, e, e), y0);
 }
 
-template <bool XDIR, int CH>
+// MODE K6_FUSED: the whole solve.  K6_BEGIN: phase A and the condensation of this rank's rows into one segment
+// (exported for the all-gather).  K6_END: the ranks' reduced system (every rank solves all of it, a few unknowns per
+// line), the local back-substitution and phase C.
+template <bool XDIR, int CH, int MODE>
 __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   extern __shared__ __align__(16) double k6s[];
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
@@ -330,8 +357,9 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
     st.fprev = F;
   };
   // any node: the two end rows come assembled from k6_ends
+  const bool open_first = MODE != K6_FUSED && q.open_first, open_last = MODE != K6_FUSED && q.open_last;
   auto node_any = [&](int i, double t, double F, double2 cf, K6State &st) {
-    if (i > 0 && i < n - 1) { node_mid(t, F, cf, st); return; }
+    if ((i > 0 || open_first) && (i < n - 1 || open_last)) { node_mid(t, F, cf, st); return; }
     double sub, diag, sup, rhs;
     if (i == 0) { sub = 0.0; diag = f_diag; sup = f_sup; rhs = f_rhs; }
     else { sub = l_sub; diag = l_diag; sup = 0.0; rhs = l_rhs; }
@@ -346,83 +374,150 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   // its loops are unrolled without per-node tests
   auto plain = [&](int i0) { return i0 > 0 && i0 + CH - 1 < e; };
 
-  // ---- phase A ----
-  K6State st;
-  st.delta = 0.0; st.lambda = 0.0; st.omega = (s > 0) ? 1.0 : 0.0;
-  st.fprev = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
-  double P = 1.0, Qa = 0.0, R = 0.0;
-  if (nch > 0) k6_load<XDIR, CH>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
+  const size_t cd_pitch = ck_pitch;
+  // face below the segment's left neighbour (the rank above holds that neighbour when the first end is open)
+  const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : ((s == 0 && open_first) ? q.fm1[line] : 0.0);
+  if (MODE != K6_END) {
+    // ---- phase A ----
+    K6State st;
+    st.delta = 0.0; st.lambda = 0.0; st.omega = (s > 0 || open_first) ? 1.0 : 0.0;
+    st.fprev = f_seg;
+    double P = 1.0, Qa = 0.0, R = 0.0;
+    if (nch > 0) k6_load<XDIR, CH>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
 #pragma unroll 1
-  for (int c = 0; c < nch; ++c) {
-    const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
-    double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
-    const double2 *cf = tabs2 + (c & 1) * CH;
-    if (c + 1 < nch) {
-      const int i1 = i0 + CH;
-      double *nT = tiles + ((c + 1) & 1) * 2 * TD;
-      k6_load<XDIR, CH>(q, line0, nl, i1, min(CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * CH, lane);
-      k5_wait<1>();
-    } else {
-      k5_wait<0>();
-    }
-    __syncwarp();
-    if (plain(i0)) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        node_mid(tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
-        Qa = fma(P, st.lambda, Qa);      // x_s = P x_e + Q + R L gathers nodes s .. e-1
-        R = fma(P, st.omega, R);
-        P = P * st.delta;
+    for (int c = 0; c < nch; ++c) {
+      const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
+      double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
+      const double2 *cf = tabs2 + (c & 1) * CH;
+      if (c + 1 < nch) {
+        const int i1 = i0 + CH;
+        double *nT = tiles + ((c + 1) & 1) * 2 * TD;
+        k6_load<XDIR, CH>(q, line0, nl, i1, min(CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * CH, lane);
+        k5_wait<1>();
+      } else {
+        k5_wait<0>();
       }
-    } else {
-      for (int j = 0; j < len; ++j) {
-        node_any(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
-        if (i0 + j < e) {
-          Qa = fma(P, st.lambda, Qa);
+      __syncwarp();
+      if (plain(i0)) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          node_mid(tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
+          Qa = fma(P, st.lambda, Qa);      // x_s = P x_e + Q + R L gathers nodes s .. e-1
           R = fma(P, st.omega, R);
           P = P * st.delta;
         }
+      } else {
+        for (int j = 0; j < len; ++j) {
+          node_any(i0 + j, tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
+          if (i0 + j < e) {
+            Qa = fma(P, st.lambda, Qa);
+            R = fma(P, st.omega, R);
+            P = P * st.delta;
+          }
+        }
       }
+      ckpt[(size_t)c * ck_pitch] = make_double4(st.delta, st.lambda, st.omega, st.fprev);
+      __syncwarp();
     }
-    ckpt[(size_t)c * ck_pitch] = make_double4(st.delta, st.lambda, st.omega, st.fprev);
-    __syncwarp();
-  }
-  {
-    double *sg = segs + (size_t)k * 32 + lane;
-    sg[0 * S * 32] = st.delta;    // delta_e (0 on the line's last node)
-    sg[1 * S * 32] = st.omega;
-    sg[2 * S * 32] = P;
-    sg[3 * S * 32] = R;
-    sg[4 * S * 32] = st.lambda;
-    sg[5 * S * 32] = Qa;
+    {
+      double *sg = segs + (size_t)k * 32 + lane;
+      sg[0 * S * 32] = st.delta;    // delta_e (0 on a closed line's last node)
+      sg[1 * S * 32] = st.omega;
+      sg[2 * S * 32] = P;
+      sg[3 * S * 32] = R;
+      sg[4 * S * 32] = st.lambda;
+      sg[5 * S * 32] = Qa;
+    }
   }
   __syncthreads();
-  // ---- reduced system: warp 0, lane = line; E_k overwrites slot 4, scratch in slots 2/3 ----
+  // ---- reduced system: warp 0, lane = line.  Unknowns E_k = x at the end of segment k:
+  //   (1 - de_k R_{k+1}) E_k - om_k E_{k-1} - de_k P_{k+1} E_{k+1} = la_k + de_k Q_{k+1}
+  // eliminated forward into  E_k = c_k E_{k+1} + d_k + w_k L0  (L0 = x above node 0, X = x below node n-1; both absent
+  // on a closed line, where om_0 = 0 and de_{S-1} = 0 make w and the last c vanish by themselves).
+  // Slots afterwards: 4 = E_k, 2 = c_k, 3 = d_k, 1 = w_k; 5*S*32 + lane = L0.
   if (k == 0) {
-    double cp = 0.0, dp = 0.0;
-    for (int kk = 0; kk < S; ++kk) {
-      double *sg = segs + (size_t)kk * 32 + lane;
-      const double de = sg[0], om = sg[1 * S * 32], la = sg[4 * S * 32];
-      double Pn = 0.0, Rn = 0.0, Qn = 0.0;
-      if (kk + 1 < S) { Pn = sg[2 * S * 32 + 32]; Rn = sg[3 * S * 32 + 32]; Qn = sg[5 * S * 32 + 32]; }
-      const double sub = -om, diag = 1.0 - de * Rn, sup = -(de * Pn), rhs = la + de * Qn;
-      const double inv = 1.0 / (diag - sub * cp);
-      cp = sup * inv;
-      dp = (rhs - sub * dp) * inv;
-      sg[2 * S * 32] = cp;        // P, R of segment kk were consumed at kk-1
-      sg[3 * S * 32] = dp;
+    double L0 = 0.0, Elast = 0.0;
+    if (MODE != K6_END) {
+      double c = 0.0, d = 0.0, w = 1.0;
+      double Pc = 1.0, Qc = 0.0, Rc = 0.0;                  // E_0 = Pc E_k + Qc + Rc L0
+      const double P0 = segs[2 * S * 32 + lane], Q0 = segs[5 * S * 32 + lane], R0 = segs[3 * S * 32 + lane];
+      for (int kk = 0; kk < S; ++kk) {
+        double *sg = segs + (size_t)kk * 32 + lane;
+        const double de = sg[0], om = sg[1 * S * 32], la = sg[4 * S * 32];
+        double Pn = 0.0, Rn = 0.0, Qn = 0.0;
+        if (kk + 1 < S) { Pn = sg[2 * S * 32 + 32]; Rn = sg[3 * S * 32 + 32]; Qn = sg[5 * S * 32 + 32]; }
+        const double a = -om, b = (kk + 1 < S) ? 1.0 - de * Rn : 1.0, gg = (kk + 1 < S) ? -(de * Pn) : -de;
+        const double r = la + de * Qn;
+        const double inv = 1.0 / (b + a * c);
+        if (kk > 0) { Qc = fma(Pc, d, Qc); Rc = fma(Pc, w, Rc); Pc = Pc * c; }   // folds E_{kk-1} = c E_kk + d + w L0
+        c = -gg * inv;
+        d = (r - a * d) * inv;
+        w = -(a * w) * inv;
+        sg[2 * S * 32] = c;        // P, R of segment kk were consumed at kk-1
+        sg[3 * S * 32] = d;
+        sg[1 * S * 32] = w;
+      }
+      if (MODE == K6_BEGIN) {
+        if (act) {
+          double *ex = q.exported + line;
+          const size_t nlp = (size_t)q.nlines;
+          ex[0 * nlp] = c; ex[1 * nlp] = d; ex[2 * nlp] = w;             // E_last = c X + d + w L0
+          ex[3 * nlp] = P0 * Pc;                                        // x_first = P E_last + Q + R L0
+          ex[4 * nlp] = fma(P0, Qc, Q0);
+          ex[5 * nlp] = fma(P0, Rc, R0);
+        }
+        for (int kk = 0; kk < S; ++kk) {
+          const double *sg = segs + (size_t)kk * 32 + lane;
+          double *o = q.cdw + (size_t)kk * 3 * cd_pitch + line0 + lane;
+          o[0] = sg[2 * S * 32]; o[cd_pitch] = sg[3 * S * 32]; o[2 * cd_pitch] = sg[1 * S * 32];
+        }
+      } else {
+        Elast = d;   // closed line: X = L0 = 0
+      }
+    } else {
+      // the ranks' reduced system (same recurrence, one segment per rank), then this rank's two interface values
+      const size_t nlp = (size_t)q.nlines;
+      double cs[16], ds[16];
+      double c = 0.0, d = 0.0;
+      for (int r = 0; r < q.nranks; ++r) {
+        const double *gr = q.gathered + (size_t)r * 6 * nlp + line;
+        const double de = gr[0], la = gr[nlp], om = gr[2 * nlp];
+        double Pn = 0.0, Qn = 0.0, Rn = 0.0;
+        if (r + 1 < q.nranks) { Pn = gr[9 * nlp]; Qn = gr[10 * nlp]; Rn = gr[11 * nlp]; }
+        const double a = -om, b = 1.0 - de * Rn, gg = -(de * Pn), rr = la + de * Qn;
+        const double inv = 1.0 / (b + a * c);
+        c = -gg * inv;
+        d = (rr - a * d) * inv;
+        cs[r] = c; ds[r] = d;
+      }
+      double x = 0.0;
+      for (int r = q.nranks - 1; r >= 0; --r) {
+        x = fma(cs[r], x, ds[r]);
+        if (r == q.rank) Elast = x;
+        if (r == q.rank - 1) L0 = x;
+      }
+      for (int kk = 0; kk < S; ++kk) {
+        const double *o = q.cdw + (size_t)kk * 3 * cd_pitch + line0 + lane;
+        double *sg = segs + (size_t)kk * 32 + lane;
+        sg[2 * S * 32] = o[0]; sg[3 * S * 32] = o[cd_pitch]; sg[1 * S * 32] = o[2 * cd_pitch];
+      }
     }
-    double x = 0.0;
-    for (int kk = S - 1; kk >= 0; --kk) {
-      double *sg = segs + (size_t)kk * 32 + lane;
-      x = sg[3 * S * 32] - sg[2 * S * 32] * x;
-      sg[4 * S * 32] = x;
+    if (MODE != K6_BEGIN) {
+      double x = Elast;
+      segs[4 * S * 32 + (size_t)(S - 1) * 32 + lane] = x;
+      for (int kk = S - 2; kk >= 0; --kk) {
+        double *sg = segs + (size_t)kk * 32 + lane;
+        x = fma(sg[2 * S * 32], x, fma(sg[1 * S * 32], L0, sg[3 * S * 32]));
+        sg[4 * S * 32] = x;
+      }
+      segs[5 * S * 32 + lane] = L0;
     }
   }
+  if (MODE == K6_BEGIN) return;
   __syncthreads();
   // ---- phase C ----
   if (nch == 0) return;
-  const double L = (k > 0) ? segs[4 * S * 32 + (size_t)(k - 1) * 32 + lane] : 0.0;
+  const double L = (k > 0) ? segs[4 * S * 32 + (size_t)(k - 1) * 32 + lane] : segs[5 * S * 32 + lane];
   double x = segs[4 * S * 32 + (size_t)k * 32 + lane];
   {
     const int il = s + (nch - 1) * CH;
@@ -430,7 +525,6 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
     k6_load<XDIR, CH>(q, line0, nl, il, min(CH, e - il + 1), nT, nT + TD, tabs2 + ((nch - 1) & 1) * CH, lane);
   }
   double4 ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : make_double4(0.0, 0.0, 0.0, 0.0);
-  const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : 0.0;
 #pragma unroll 1
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * CH, len = min(CH, e - i0 + 1);

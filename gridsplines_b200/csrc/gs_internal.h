@@ -152,6 +152,8 @@ struct gs_grid2d {
   size_t k5_ckpt_len = 0;
   double *k6_F = nullptr, *k6_ends = nullptr;   // K6: face values, end rows
   double4 *k6_ckpt = nullptr;
+  double *k6_split = nullptr;                    // split y sweep: fm1 [nlines] + cdw [S][3][nlines padded]
+  bool k6_split_open = false;                    // a begin call is waiting for its end call
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
 };

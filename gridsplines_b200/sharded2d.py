@@ -118,6 +118,76 @@ class RowShardedTwoDGrid:
                 self.gx.set(PREDICT, cols_to_rows(self.gy.get(PREDICT), self.world))
 
 
+class SpikeShardedTwoDGrid:
+    """Row-sharded TwoDGrid whose y sweep stays row-sharded: no transposes.
+
+    Rank p owns rows [p R/P, (p+1) R/P) of grid / predict / result -- a contiguous SEGMENT of every column.  One step:
+
+      1. x sweep on the local rows (whole lines, no communication);
+      2. all-gather of every rank's first and last predict row (2 x cols doubles per rank): the faces across a cut
+         need the neighbour's temperature;
+      3. begin: faces, forward elimination of the local segment of every column, condensed to six numbers per column
+         (the segment's map  x_first = P E + Q + R L0,  E = C X + D + W L0  in terms of the unknown values L0 above,
+         X below and E at its own last row);
+      4. all-gather of those 6 x cols doubles per rank -- the only data-path exchange, ~0.8 MB per rank at 16384
+         columns against the 3 x 268 MB per rank the transposing driver moves;
+      5. end: every rank solves the P-unknown reduced system of every column, back-substitutes its rows and applies
+         Grid.update.
+
+    This is the partitioned solver of the single-GPU K5/K6 kernels continued across GPUs (tolerance family, <= 1e-12
+    per field against the reference); `RowShardedTwoDGrid` remains the bit-exact variant.  `make_local(xvalues,
+    yvalues)` returns the local solver: set_bound / get / set / xIter / predict_edges() -> [2, cols] tensor /
+    yIterUpdateBegin(time, halo_prev, halo_next) -> [6, cols] tensor / yIterUpdateEnd(time, gathered, world, rank).
+    """
+
+    def __init__(self, make_local: Callable, xvalues, yvalues, bounds: Dict[int, Tuple[int, int, np.ndarray]],
+                 world: int, rank: int):
+        self.world, self.rank = world, rank
+        xv, yv = np.asarray(xvalues, float), np.asarray(yvalues, float)
+        self.cols, self.rows = len(xv) - 2, len(yv) - 2
+        if self.rows % world:
+            raise ValueError("rows must be divisible by the world size")
+        if bounds.get(LOW, (0,))[0] == 1 and world > 1:
+            raise ValueError("a lower HeatFlow bound is not supported on a sharded grid")
+        self.r0, self.rl = block_shard(self.rows, world, rank)
+        self.g = make_local(xv, yv[self.r0:self.r0 + self.rl + 2])
+        for side, (kind, rep, values) in bounds.items():
+            v = np.atleast_1d(np.asarray(values, float))
+            if side in (LEFT, RIGHT) and v.size > 1:
+                v = v[self.r0:self.r0 + self.rl]
+            self.g.set_bound(side, kind, rep, v)
+        self._edges = self._gathered = None
+
+    def set_local_rows(self, grid: torch.Tensor, predict: torch.Tensor):
+        self.g.set(GRID, grid)
+        self.g.set(PREDICT, predict)
+
+    def local_rows(self, which: int = GRID) -> torch.Tensor:
+        return self.g.get(which)
+
+    def iteration(self, time: float, nsteps: int = 1):
+        P, r = self.world, self.rank
+        for _ in range(nsteps):
+            self.g.xIter(time)
+            mine = self.g.predict_edges()
+            if self._edges is None:
+                self._edges = mine.new_empty((P,) + tuple(mine.shape))
+            if P > 1:
+                dist.all_gather_into_tensor(self._edges, mine)
+            else:
+                self._edges[0].copy_(mine)
+            prev = self._edges[r - 1, 1] if r > 0 else None
+            nxt = self._edges[r + 1, 0] if r + 1 < P else None
+            exported = self.g.yIterUpdateBegin(time, prev, nxt)
+            if self._gathered is None:
+                self._gathered = exported.new_empty((P,) + tuple(exported.shape))
+            if P > 1:
+                dist.all_gather_into_tensor(self._gathered, exported)
+            else:
+                self._gathered[0].copy_(exported)
+            self.g.yIterUpdateEnd(time, self._gathered, P, r)
+
+
 class GsLocalGrid:
     """libgs_b200-backed local grid for RowShardedTwoDGrid: CUDA tensors in and out (device-to-device copies on the
     context's stream, which must be torch's current stream so that NCCL and the kernels are ordered)."""
@@ -160,3 +230,21 @@ class GsLocalGrid:
 
     def yIterUpdate(self, time):
         self.g.yIterUpdate(time)
+
+    # ---- split y sweep (SpikeShardedTwoDGrid)
+    def predict_edges(self) -> torch.Tensor:
+        p = self._t[PREDICT]
+        return torch.stack((p[0], p[-1]))
+
+    def yIterUpdateBegin(self, time, halo_prev, halo_next) -> torch.Tensor:
+        if getattr(self, "_exported", None) is None:
+            self._exported = torch.empty((6, self.g.cols), dtype=torch.float64, device="cuda")
+        for h in (halo_prev, halo_next):
+            assert h is None or (h.is_contiguous() and h.dtype == torch.float64 and h.numel() == self.g.cols)
+        self.g.yIterUpdateBegin(time, None if halo_prev is None else halo_prev.data_ptr(),
+                                None if halo_next is None else halo_next.data_ptr(), self._exported.data_ptr())
+        return self._exported
+
+    def yIterUpdateEnd(self, time, gathered, world, rank):
+        assert gathered.is_contiguous() and tuple(gathered.shape) == (world, 6, self.g.cols)
+        self.g.yIterUpdateEnd(time, gathered.data_ptr(), world, rank)

@@ -171,6 +171,13 @@ int gs_grid2d_xiter(gs_grid2d *g, double time);           /* TwoDGrid.xIter :135
 int gs_grid2d_yiter(gs_grid2d *g, double time);           /* TwoDGrid.yIter :195-252 */
 int gs_grid2d_update(gs_grid2d *g);                       /* Grid.update :474-481 */
 int gs_grid2d_yiter_update(gs_grid2d *g, double time);    /* yIter + Grid.update fused (second half of iteration) */
+/* yIter + Grid.update of a row-sharded grid (this rank holds rows [r0, r1) of every column), split around the ranks'
+ * exchange; partitioned solver.  halo_prev / halo_next: device, cols doubles = the predict row above / below the
+ * local rows, NULL where this rank holds the physical boundary.  begin writes exported[6][cols] (device); the caller
+ * all-gathers it in rank order into gathered[nranks][6][cols] and calls end.  Replaces the column walk of
+ * TwoDGrid.yIter :195-252 when one column spans several GPUs. */
+int gs_grid2d_yiter_update_begin(gs_grid2d *g, double time, const void *halo_prev, const void *halo_next, void *exported);
+int gs_grid2d_yiter_update_end(gs_grid2d *g, double time, const void *gathered, int nranks, int rank);
 /* device-to-device copies of a whole row-major array on the context's stream (multi-GPU glue) */
 int gs_grid2d_copy_from_device(gs_grid2d *g, int which, const void *dptr);
 int gs_grid2d_copy_to_device(gs_grid2d *g, int which, void *dptr);

@@ -1,7 +1,7 @@
 """Row-sharded 2-D LOD step on N GPUs (torchrun): parity against a single-GPU run and throughput.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tools/run_sharded2d.py --size 4096 --coefs hermite --steps 5 [--check]
+      tools/run_sharded2d.py --size 4096 --coefs hermite --steps 5 [--mode spike|transpose] [--check]
 """
 import argparse, json, os, sys
 import numpy as np
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import gridsplines_b200 as gs
-from gridsplines_b200.sharded2d import GsLocalGrid, RowShardedTwoDGrid
+from gridsplines_b200.sharded2d import GsLocalGrid, RowShardedTwoDGrid, SpikeShardedTwoDGrid
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=4096)
@@ -17,6 +17,8 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--coefs", default="hermite")
 ap.add_argument("--solver", type=int, default=0)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--mode", default="spike", choices=["spike", "transpose"],
+                help="spike: y sweep stays row-sharded, 6 x cols doubles exchanged; transpose: three all-to-alls")
 a = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -42,7 +44,8 @@ bounds = {0: (0, 1, np.full(n, 7.0)), 1: (0, 1, np.full(n, 7.0)), 2: (0, 1, np.f
 with torch.cuda.stream(stream):
     ctx = gs.Context(local, stream=stream.cuda_stream)
     mk = lambda xv_, yv_: GsLocalGrid(gs, ctx, xv_, yv_, gs.RADIAL, gs.ORTHO, coefs_factory, solver=a.solver)
-    sg = RowShardedTwoDGrid(mk, xv, yv, bounds, world, rank)
+    Driver = SpikeShardedTwoDGrid if a.mode == "spike" else RowShardedTwoDGrid
+    sg = Driver(mk, xv, yv, bounds, world, rank)
     g0 = torch.Generator(device="cuda").manual_seed(1234)
     full = 7.0 + torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g0)   # same on every rank
     mine = full[sg.r0:sg.r0 + sg.rl].contiguous()
@@ -59,7 +62,7 @@ with torch.cuda.stream(stream):
     ms = torch.tensor([e0.elapsed_time(e1) / a.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    out = {"n": n, "coefs": a.coefs, "solver": a.solver, "n_gpus": world, "ms_per_step": float(ms.item()),
+    out = {"n": n, "coefs": a.coefs, "solver": a.solver, "mode": a.mode, "n_gpus": world, "ms_per_step": float(ms.item()),
            "updates_per_s": n * n / (float(ms.item()) * 1e-3)}
     if a.check:
         # rank 0 repeats the run on one GPU and compares its rows with everybody's (gathered) rows
@@ -70,7 +73,7 @@ with torch.cuda.stream(stream):
         else:
             gathered = [rows]
         if rank == 0:
-            ref = RowShardedTwoDGrid(mk, xv, yv, bounds, 1, 0)
+            ref = Driver(mk, xv, yv, bounds, 1, 0)
             ref.set_local_rows(full.clone(), full.clone())
             ref.iteration(900.0, nsteps=2 + a.steps)
             want, got = ref.local_rows(0), torch.cat(gathered)
