@@ -173,7 +173,7 @@ class SpikeShardedTwoDGrid:
             if self._edges is None:
                 self._edges = mine.new_empty((P,) + tuple(mine.shape))
             if P > 1:
-                dist.all_gather_into_tensor(self._edges, mine)
+                dist.all_gather_into_tensor(self._edges.view(-1, mine.shape[-1]), mine)   # rank-major concatenation
             else:
                 self._edges[0].copy_(mine)
             prev = self._edges[r - 1, 1] if r > 0 else None
@@ -182,7 +182,7 @@ class SpikeShardedTwoDGrid:
             if self._gathered is None:
                 self._gathered = exported.new_empty((P,) + tuple(exported.shape))
             if P > 1:
-                dist.all_gather_into_tensor(self._gathered, exported)
+                dist.all_gather_into_tensor(self._gathered.view(-1, exported.shape[-1]), exported)
             else:
                 self._gathered[0].copy_(exported)
             self.g.yIterUpdateEnd(time, self._gathered, P, r)
