@@ -1480,6 +1480,25 @@ static void k6_shape(gs_ctx *ctx, int n, int *m, int *S) {
   *m = mm;
   *S = (n + mm - 1) / mm;
 }
+// With fewer strips than half the SMs (a row shard of a larger grid, a small grid) a strip is given to a thread-block
+// cluster of 2 or 4 CTAs, each eliminating S of the line's csize * S segments.  Keeps csize = 1 unless the segments
+// divide evenly (an open last end tolerates no empty trailing segment).
+static int k6_cluster(gs_ctx *ctx, int n, int nlines, int *m, int *S) {
+  k6_shape(ctx, n, m, S);
+  if (!ctx->opt_k6_cluster) return 1;
+  const int ch = k6_chunk(ctx), strips = (nlines + 31) / 32;
+  int cs = 1;
+  while (cs < 4 && strips * cs * 2 <= ctx->sm_count) cs *= 2;
+  for (; cs > 1; cs /= 2) {
+    const int st = *S * cs;
+    const int mm = ((n + st - 1) / st + ch - 1) / ch * ch;
+    if (mm >= 2 * ch && (n + mm - 1) / mm == st) {
+      *m = mm;
+      return cs;
+    }
+  }
+  return 1;
+}
 static size_t k6_smem(gs_ctx *ctx, bool xdir, int S) {
   const int ch = k6_chunk(ctx);
   size_t tile = (size_t)ch * (xdir ? 33 : 32);
@@ -1517,7 +1536,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
   const int mode = split ? split->mode : K6_FUSED;
   const size_t nl_pad = ((size_t)nlines + 31) / 32 * 32;
-  if (split && !g->k6_split) GS_CUDA(cudaMalloc(&g->k6_split, (nl_pad + 16 * 3 * nl_pad) * sizeof(double)));
+  if (split && !g->k6_split) GS_CUDA(cudaMalloc(&g->k6_split, (nl_pad + 64 * 3 * nl_pad) * sizeof(double)));
   // 1. faces + end rows of this direction (reads predict, rhs; every spline evaluation of the sweep happens here)
   K6FacesParams fq;
   bool single;
@@ -1572,7 +1591,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   // 2. elimination sweep
   K6Params q;
   q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
-  k6_shape(ctx, n, &q.m, &q.S);
+  q.csize = k6_cluster(ctx, n, nlines, &q.m, &q.S);
   q.coefs = d.coefs;
   q.F = g->k6_F; q.first3 = fq.first3; q.last3 = fq.last3;
   q.rhs = p.rhs;
@@ -1598,7 +1617,19 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   else kern = ch16 ? (xdir ? k6_sweep<true, 16, K6_FUSED> : k6_sweep<false, 16, K6_FUSED>)
                    : (xdir ? k6_sweep<true, 8, K6_FUSED> : k6_sweep<false, 8, K6_FUSED>);
   GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, threads, smem, ctx->stream>>>(q);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks * q.csize);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = q.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
+  }
   ctx->launches += mode == K6_END ? 1 : 3;
   GS_CUDA(cudaGetLastError());
   return GS_OK;

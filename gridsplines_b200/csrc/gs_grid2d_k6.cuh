@@ -12,6 +12,7 @@
 // per-node work is only the elimination:  sub = cf0 F[i-1], sup = cf1 F[i], diag = -(sub+sup) - 1/tau,
 // Delta = diag + sub delta, one reciprocal, delta, lambda, omega and the composed map (P, Q, R) of the segment.
 #pragma once
+#include <cooperative_groups.h>
 
 // ---- faces -------------------------------------------------------------------------------------------------------
 struct K6FacesParams {
@@ -258,6 +259,7 @@ struct K6Params {
   double *exported;        // [6][nlines]: this rank as ONE segment: C, D, W of its last node and P, Q, R of its first
   const double *gathered;  // [nranks][6][nlines]
   int nranks, rank;
+  int csize;               // CTAs per strip (thread-block cluster): the line's segments are spread over csize x S warps
 };
 #define K6_FUSED 0
 #define K6_BEGIN 1
@@ -328,13 +330,26 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   constexpr int TD = CH * PITCH;
   const int S = q.S, m = q.m, n = q.n;
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-  const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
+  // A strip of 32 lines belongs to a cluster of csize CTAs (1 when there are strips enough to fill the chip): CTA
+  // `crank` of the cluster eliminates segments crank * S .. crank * S + S - 1 of every line; the reduced system of
+  // all csize * S segments is solved by the cluster's first CTA through distributed shared memory.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csz = q.csize, crank = csz > 1 ? (int)cluster.block_rank() : 0, ST = S * csz;
+  const int line0 = (blockIdx.x / csz) * 32, nl = min(32, q.nlines - line0);
   // shared: per CTA seg[6][S][32] (delta_e, omega_e, P, R, lambda_e, Q) ; per warp 2 x (tileT, tileF) + 2 x tabs
   double *segs = k6s;
   double *wbase = k6s + 6 * S * 32 + (size_t)k * (4 * TD + 4 * CH);
   double2 *tabs2 = reinterpret_cast<double2 *>(wbase);
   double *tiles = wbase + 4 * CH;
-  const int s = k * m, e = min(n, s + m) - 1;
+  const int s = (crank * S + k) * m, e = min(n, s + m) - 1;
+  auto sync_strip = [&]() { if (csz > 1) cluster.sync(); else __syncthreads(); };
+  // segment kk's slot column in whichever CTA of the cluster holds it
+  auto seg_at = [&](int kk) -> double * {
+    double *base = segs;
+    if (csz > 1) base = cluster.map_shared_rank(segs, kk / S);
+    return base + (size_t)(kk % S) * 32 + lane;
+  };
   const int nch = (e >= s) ? (e - s) / CH + 1 : 0;
   const bool act = lane < nl;
   const int line = line0 + (act ? lane : 0);
@@ -429,24 +444,25 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       sg[5 * S * 32] = Qa;
     }
   }
-  __syncthreads();
-  // ---- reduced system: warp 0, lane = line.  Unknowns E_k = x at the end of segment k:
+  sync_strip();
+  // ---- reduced system: first CTA's warp 0, lane = line.  Unknowns E_k = x at the end of segment k:
   //   (1 - de_k R_{k+1}) E_k - om_k E_{k-1} - de_k P_{k+1} E_{k+1} = la_k + de_k Q_{k+1}
   // eliminated forward into  E_k = c_k E_{k+1} + d_k + w_k L0  (L0 = x above node 0, X = x below node n-1; both absent
-  // on a closed line, where om_0 = 0 and de_{S-1} = 0 make w and the last c vanish by themselves).
-  // Slots afterwards: 4 = E_k, 2 = c_k, 3 = d_k, 1 = w_k; 5*S*32 + lane = L0.
-  if (k == 0) {
+  // on a closed line, where om_0 = 0 and de_last = 0 make w and the last c vanish by themselves).
+  // Slots afterwards: 4 = E_k, 2 = c_k, 3 = d_k, 1 = w_k; 5*S*32 + lane of every CTA = x above its first segment.
+  if (k == 0 && crank == 0) {
     double L0 = 0.0, Elast = 0.0;
     if (MODE != K6_END) {
       double c = 0.0, d = 0.0, w = 1.0;
       double Pc = 1.0, Qc = 0.0, Rc = 0.0;                  // E_0 = Pc E_k + Qc + Rc L0
       const double P0 = segs[2 * S * 32 + lane], Q0 = segs[5 * S * 32 + lane], R0 = segs[3 * S * 32 + lane];
-      for (int kk = 0; kk < S; ++kk) {
-        double *sg = segs + (size_t)kk * 32 + lane;
+      double *sg = seg_at(0);
+      for (int kk = 0; kk < ST; ++kk) {
+        double *sn = (kk + 1 < ST) ? seg_at(kk + 1) : sg;
         const double de = sg[0], om = sg[1 * S * 32], la = sg[4 * S * 32];
         double Pn = 0.0, Rn = 0.0, Qn = 0.0;
-        if (kk + 1 < S) { Pn = sg[2 * S * 32 + 32]; Rn = sg[3 * S * 32 + 32]; Qn = sg[5 * S * 32 + 32]; }
-        const double a = -om, b = (kk + 1 < S) ? 1.0 - de * Rn : 1.0, gg = (kk + 1 < S) ? -(de * Pn) : -de;
+        if (kk + 1 < ST) { Pn = sn[2 * S * 32]; Rn = sn[3 * S * 32]; Qn = sn[5 * S * 32]; }
+        const double a = -om, b = (kk + 1 < ST) ? 1.0 - de * Rn : 1.0, gg = (kk + 1 < ST) ? -(de * Pn) : -de;
         const double r = la + de * Qn;
         const double inv = 1.0 / (b + a * c);
         if (kk > 0) { Qc = fma(Pc, d, Qc); Rc = fma(Pc, w, Rc); Pc = Pc * c; }   // folds E_{kk-1} = c E_kk + d + w L0
@@ -456,6 +472,7 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
         sg[2 * S * 32] = c;        // P, R of segment kk were consumed at kk-1
         sg[3 * S * 32] = d;
         sg[1 * S * 32] = w;
+        sg = sn;
       }
       if (MODE == K6_BEGIN) {
         if (act) {
@@ -466,10 +483,10 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
           ex[4 * nlp] = fma(P0, Qc, Q0);
           ex[5 * nlp] = fma(P0, Rc, R0);
         }
-        for (int kk = 0; kk < S; ++kk) {
-          const double *sg = segs + (size_t)kk * 32 + lane;
+        for (int kk = 0; kk < ST; ++kk) {
+          const double *sk = seg_at(kk);
           double *o = q.cdw + (size_t)kk * 3 * cd_pitch + line0 + lane;
-          o[0] = sg[2 * S * 32]; o[cd_pitch] = sg[3 * S * 32]; o[2 * cd_pitch] = sg[1 * S * 32];
+          o[0] = sk[2 * S * 32]; o[cd_pitch] = sk[3 * S * 32]; o[2 * cd_pitch] = sk[1 * S * 32];
         }
       } else {
         Elast = d;   // closed line: X = L0 = 0
@@ -496,25 +513,26 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
         if (r == q.rank) Elast = x;
         if (r == q.rank - 1) L0 = x;
       }
-      for (int kk = 0; kk < S; ++kk) {
+      for (int kk = 0; kk < ST; ++kk) {
         const double *o = q.cdw + (size_t)kk * 3 * cd_pitch + line0 + lane;
-        double *sg = segs + (size_t)kk * 32 + lane;
-        sg[2 * S * 32] = o[0]; sg[3 * S * 32] = o[cd_pitch]; sg[1 * S * 32] = o[2 * cd_pitch];
+        double *sk = seg_at(kk);
+        sk[2 * S * 32] = o[0]; sk[3 * S * 32] = o[cd_pitch]; sk[1 * S * 32] = o[2 * cd_pitch];
       }
     }
     if (MODE != K6_BEGIN) {
       double x = Elast;
-      segs[4 * S * 32 + (size_t)(S - 1) * 32 + lane] = x;
-      for (int kk = S - 2; kk >= 0; --kk) {
-        double *sg = segs + (size_t)kk * 32 + lane;
-        x = fma(sg[2 * S * 32], x, fma(sg[1 * S * 32], L0, sg[3 * S * 32]));
-        sg[4 * S * 32] = x;
+      for (int kk = ST - 1; kk >= 0; --kk) {
+        double *sk = seg_at(kk);
+        if (kk < ST - 1) x = fma(sk[2 * S * 32], x, fma(sk[1 * S * 32], L0, sk[3 * S * 32]));
+        sk[4 * S * 32] = x;
+        // the value above the first segment of the CTA that follows
+        if (kk % S == S - 1 && kk + 1 < ST) seg_at(kk + 1)[5 * S * 32] = x;
       }
       segs[5 * S * 32 + lane] = L0;
     }
   }
+  sync_strip();
   if (MODE == K6_BEGIN) return;
-  __syncthreads();
   // ---- phase C ----
   if (nch == 0) return;
   const double L = (k > 0) ? segs[4 * S * 32 + (size_t)(k - 1) * 32 + lane] : segs[5 * S * 32 + lane];

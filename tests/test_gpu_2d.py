@@ -378,6 +378,34 @@ def test_k6_face_tiers(O, gs, ctx, field):
         ctx.set_option("k5", 1)
 
 
+@pytest.mark.parametrize("cols,rows", [(1024, 64), (64, 1024), (2048, 300)])
+def test_k6_clustered_strips(O, gs, ctx, cols, rows):
+    """Few lines in one direction: a strip of 32 lines is eliminated by a cluster of 2 or 4 CTAs whose reduced system
+    is solved through distributed shared memory.  Same answer as one CTA per strip, and as the reference."""
+    ctx.set_option("k5", 0)
+    try:
+        p = cases.bc_problem("TFTT", xdir=1, ydir=0, cols=cols, rows=rows, coefs="hermite")
+        r = np.random.default_rng(8)
+        p.grid0 = r.uniform(-10.0, 60.0, p.grid0.shape)
+        p.predict0 = p.grid0 + r.uniform(-2.0, 2.0, p.grid0.shape)
+        g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+        g.set_solver(gs.SOLVER_PARTITIONED)
+        g.iteration(900.0, nsteps=2)
+        for _ in range(2):
+            o.iteration(900.0)
+        O.set_ascending_fold(True)
+        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 clusters {cols}x{rows}", tol=tol)
+        ctx.set_option("k6_cluster", 0)
+        h = p.build_gs(gs)
+        h.set_solver(gs.SOLVER_PARTITIONED)
+        h.iteration(900.0, nsteps=2)
+        _compare_tol(cases.snapshot(g), cases.snapshot(h), "clusters vs single CTA", tol=tol)
+    finally:
+        ctx.set_option("k5", 1)
+        ctx.set_option("k6_cluster", 1)
+
+
 def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
     """K5 caches its line-independent tables per (grid, direction, time step): changing the coefficients, the time
     step or a bound's kind must rebuild them."""

@@ -47,13 +47,15 @@ def _split_step(gs, torch, locals_, time):
 
 
 @pytest.mark.parametrize("P", [1, 2, 4])
-@pytest.mark.parametrize("coefs,combo,ydir", [("const", "TTTT", 0), ("hermite", "TTTT", 0), ("hermite", "FTFT", 1),
-                                              ("dense", "TTTF", 0)])
-def test_split_y_sweep_equals_whole_grid(O, gs, ctx, coefs, combo, ydir, P):
+@pytest.mark.parametrize("coefs,combo,ydir,rows,cols", [
+    ("const", "TTTT", 0, 512, 96), ("hermite", "TTTT", 0, 512, 96), ("hermite", "FTFT", 1, 512, 96),
+    ("dense", "TTTF", 0, 512, 96),
+    ("hermite", "TTTT", 0, 4096, 40),      # two strips of columns: every strip goes to a cluster of CTAs
+])
+def test_split_y_sweep_equals_whole_grid(O, gs, ctx, coefs, combo, ydir, rows, cols, P):
     torch = pytest.importorskip("torch")
     ctx.set_option("k5", 0)   # literal constants would otherwise take K5 on the whole grid
     try:
-        rows, cols = 512, 96
         p = cases.bc_problem(combo, xdir=1, ydir=ydir, cols=cols, rows=rows, coefs=coefs)
         r = np.random.default_rng(3)
         p.grid0 = r.uniform(-10.0, 60.0, p.grid0.shape)

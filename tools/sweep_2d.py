@@ -7,6 +7,7 @@ import gridsplines_b200 as gs
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=4096)
+ap.add_argument("--rows", type=int, default=0, help="rows when not square (a row shard of a larger grid)")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--coefs", default="const")
 ap.add_argument("--solver", action="append", type=int, default=[])
@@ -17,7 +18,8 @@ ctx = gs.Context(0, stream=stream.cuda_stream)
 n = a.n
 r = np.random.default_rng(1)
 x = gs.XDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
-y = gs.YDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
+nr = a.rows or n
+y = gs.YDim(0.0, 0.01 * np.arange(1, nr + 1), 0.01 * (nr + 1), gs.ORTHO)
 if a.coefs == "const":
     coefs = gs.ConstantCoef(gs.Spline.const(1.5), gs.Spline.const(2.2e6), gs.Spline.const(1.5 / 2.2e6), ctx=ctx)
     kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Flow), left=(gs.Many, gs.Flow))
@@ -34,7 +36,7 @@ if a.coefs == "const":
     g.bounds.left.update(50.0); g.bounds.right.update(0.0)
 else:
     g.bounds.left.update(30.0); g.bounds.right.update(7.0)
-f = 7.0 + r.uniform(size=(n, n))
+f = 7.0 + r.uniform(size=(nr, n))
 g.grid.grid = f; g.grid.predict = f
 def timeit():
     with torch.cuda.stream(stream):
@@ -45,7 +47,7 @@ def timeit():
         torch.cuda.synchronize()
     return e0.elapsed_time(e1) / a.steps
 def report(tag, ms):
-    ups = n * n / (ms * 1e-3)
+    ups = nr * n / (ms * 1e-3)
     print(f"{tag:40s} {ms:8.3f} ms/step  {ups/1e9:8.2f} Gupd/s  {64*ups/6543.4e9*100:6.1f}% of HBM roofline", flush=True)
 for s in (a.solver or [0]):
     g.set_solver(s)
