@@ -23,6 +23,7 @@
 #pragma once
 
 #define K5_CH 16  // nodes per chunk
+static_assert(K5_CH == 16, "k5_sweep's unrolled y phase C handles a chunk as two halves of 8");
 
 struct K5Dir {
   int n, nlines, m, S;          // nodes per line, lines, segment length (multiple of K5_CH), segments
@@ -249,15 +250,20 @@ __device__ __forceinline__ void k5_load(const K5Params &q, const double *src, in
     // K5_CH = 16 columns per row piece: two rows per warp instruction (lanes 0-15 even rows, 16-31 odd rows)
     const int jj = lane & (K5_CH - 1);
     if (jj < len) {
-      const double *g = src + (size_t)line0 * q.cols + i0 + jj;
-#pragma unroll 4
-      for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) k5_cp8(&tile[jj * PITCH + r], g + (size_t)r * q.cols);
+      int r = lane / K5_CH;
+      const double *g = src + (size_t)(line0 + r) * q.cols + i0 + jj;
+      const size_t rs = (size_t)(32 / K5_CH) * q.cols;
+      double *sd = &tile[jj * PITCH + r];
+#pragma unroll
+      for (int u = 0; u < K5_CH; ++u, r += 32 / K5_CH, g += rs)
+        if (r < nl) k5_cp8(sd + u * (32 / K5_CH), g);
     }
   } else {
     if (lane < nl) {
       const double *g = src + (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
-#pragma unroll 8
-      for (int j = 0; j < len; ++j) k5_cp8(&tile[j * PITCH + lane], g + (size_t)j * q.pitch);
+#pragma unroll
+      for (int j = 0; j < K5_CH; ++j, g += q.pitch)
+        if (j < len) k5_cp8(&tile[j * PITCH + lane], g);
     }
   }
   k5_commit();
@@ -268,9 +274,13 @@ __device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int l
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
   const int jj = lane & (K5_CH - 1);
   if (jj < len) {
-    double *g = dst + (size_t)line0 * q.cols + i0 + jj;
-#pragma unroll 4
-    for (int r = lane / K5_CH; r < nl; r += 32 / K5_CH) g[(size_t)r * q.cols] = tile[jj * PITCH + r];
+    int r = lane / K5_CH;
+    double *g = dst + (size_t)(line0 + r) * q.cols + i0 + jj;
+    const size_t rs = (size_t)(32 / K5_CH) * q.cols;
+    const double *sd = &tile[jj * PITCH + r];
+#pragma unroll
+    for (int u = 0; u < K5_CH; ++u, r += 32 / K5_CH, g += rs)
+      if (r < nl) *g = sd[u * (32 / K5_CH)];
   }
 }
 
@@ -297,6 +307,9 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const double ex0 = d.e0a * d.bound_first[(size_t)line * q.bc_stride] + d.e0b;
   const double ex1 = d.e1a * d.bound_last[(size_t)line * q.bc_stride] + d.e1b;
 
+  // a chunk is `plain` when it is full and holds neither node 0 nor the segment's last node e (hence not n - 1): its
+  // loops run unrolled without per-node tests (all but two chunks of a segment)
+  auto plain = [&](int i0) { return i0 > 0 && i0 + K5_CH - 1 < e; };
   // ---- phase A ----  (chunk c+1 is in flight while chunk c is processed)
   double lam = 0.0, Qacc = 0.0;
   if (nch > 0) k5_load<XDIR>(q, q.rhs, line0, nl, s, min(K5_CH, e - s + 1), tile2, tabs2, lane);
@@ -313,12 +326,21 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       k5_wait<0>();
     }
     __syncwarp();
-    for (int j = 0; j < len; ++j) {
-      const double4 c4 = t[j];
-      lam = fma(tile[j * PITCH + lane], c4.x, lam * c4.y);
-      if (i0 + j == 0) lam += ex0;
-      if (i0 + j == n - 1) lam += ex1;
-      if (i0 + j < e) Qacc = fma(c4.w, lam, Qacc);
+    if (plain(i0)) {
+#pragma unroll
+      for (int j = 0; j < K5_CH; ++j) {
+        const double4 c4 = t[j];
+        lam = fma(tile[j * PITCH + lane], c4.x, lam * c4.y);
+        Qacc = fma(c4.w, lam, Qacc);
+      }
+    } else {
+      for (int j = 0; j < len; ++j) {
+        const double4 c4 = t[j];
+        lam = fma(tile[j * PITCH + lane], c4.x, lam * c4.y);
+        if (i0 + j == 0) lam += ex0;
+        if (i0 + j == n - 1) lam += ex1;
+        if (i0 + j < e) Qacc = fma(c4.w, lam, Qacc);
+      }
     }
     if (act) ckpt[(size_t)c * ck_pitch] = lam;   // (a narrower strip's idle lanes would hit the next CTA's slots)
     __syncwarp();
@@ -369,38 +391,100 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
     // lambda at the start of the chunk: phase A's checkpoint plus the left-neighbour term omega * L
     double lm = (c > 0) ? ck_next + d.omega_end[(i0 - 1) / K5_CH] * L : L;
     if (c > 1) ck_next = ckpt[(size_t)(c - 2) * ck_pitch];   // for the next iteration
-    for (int j = 0; j < len; ++j) {
-      const double4 c4 = t[j];
-      lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
-      if (i0 + j == 0) lm += ex0;
-      if (i0 + j == n - 1) lm += ex1;
-      tile[j * PITCH + lane] = lm;
-    }
-    if (XDIR) {
+    const bool pl = plain(i0);
+    if (XDIR && pl) {
+      // recompute the chunk's lambdas into registers, back-substitute, stage x for the transposed store
+      double lmv[K5_CH];
+#pragma unroll
+      for (int j = 0; j < K5_CH; ++j) {
+        const double4 c4 = t[j];
+        lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
+        lmv[j] = lm;
+      }
+#pragma unroll
+      for (int j = K5_CH - 1; j >= 0; --j) {
+        x = fma(t[j].z, x, lmv[j]);
+        tile[j * PITCH + lane] = x;
+      }
+      __syncwarp();
+      k5_store_x<XDIR>(q, q.out, line0, nl, i0, K5_CH, tile, lane);
+    } else if (XDIR) {
+      for (int j = 0; j < len; ++j) {
+        const double4 c4 = t[j];
+        lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
+        if (i0 + j == 0) lm += ex0;
+        if (i0 + j == n - 1) lm += ex1;
+        tile[j * PITCH + lane] = lm;
+      }
       for (int j = len - 1; j >= 0; --j) {
         if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
         tile[j * PITCH + lane] = x;
       }
       __syncwarp();
       k5_store_x<XDIR>(q, q.out, line0, nl, i0, len, tile, lane);
-      __syncwarp();
-    } else if (act) {
+    } else {
       const size_t off = (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
       double *G = q.grid_io + off, *P = q.predict_out + off;
-      // old grid values in batches of 8 (all loads of a batch in flight before its stores)
-      for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
-        double gold[8];
+      if (pl) {
+        // old grid values of the upper half are requested before the recomputation, those of the lower half before
+        // the upper half's back-substitution: their latency hides behind arithmetic
+        double ga[8], gb[8];
+        if (act) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.pitch] : 0.0;
+          for (int u = 0; u < 8; ++u) ga[u] = G[(size_t)(8 + u) * q.pitch];
+        }
 #pragma unroll
-        for (int u = 7; u >= 0; --u) {
-          const int j = jb + u;
-          if (j < len) {
-            if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
-            const double dl = x - gold[u];
+        for (int j = 0; j < K5_CH; ++j) {
+          const double4 c4 = t[j];
+          lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
+          tile[j * PITCH + lane] = lm;
+        }
+        if (act) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) gb[u] = G[(size_t)u * q.pitch];
+#pragma unroll
+          for (int u = 7; u >= 0; --u) {
+            const int j = 8 + u;
+            x = fma(t[j].z, x, tile[j * PITCH + lane]);
+            const double dl = x - ga[u];
             if (ONED) P[(size_t)j * q.pitch] = x + dl / 3.0;                            // arraygrid.aVal :85-87
             else P[(size_t)j * q.pitch] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;           // Grid.update :474-481, aVal :508-512
             G[(size_t)j * q.pitch] = x;
+          }
+#pragma unroll
+          for (int u = 7; u >= 0; --u) {
+            x = fma(t[u].z, x, tile[u * PITCH + lane]);
+            const double dl = x - gb[u];
+            if (ONED) P[(size_t)u * q.pitch] = x + dl / 3.0;
+            else P[(size_t)u * q.pitch] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
+            G[(size_t)u * q.pitch] = x;
+          }
+        }
+      } else {
+        for (int j = 0; j < len; ++j) {
+          const double4 c4 = t[j];
+          lm = fma(tile[j * PITCH + lane], c4.x, lm * c4.y);
+          if (i0 + j == 0) lm += ex0;
+          if (i0 + j == n - 1) lm += ex1;
+          tile[j * PITCH + lane] = lm;
+        }
+        if (act) {
+          // old grid values in batches of 8 (all loads of a batch in flight before its stores)
+          for (int jb = ((len - 1) / 8) * 8; jb >= 0; jb -= 8) {
+            double gold[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) gold[u] = (jb + u < len) ? G[(size_t)(jb + u) * q.pitch] : 0.0;
+#pragma unroll
+            for (int u = 7; u >= 0; --u) {
+              const int j = jb + u;
+              if (j < len) {
+                if (i0 + j != e) x = fma(t[j].z, x, tile[j * PITCH + lane]);
+                const double dl = x - gold[u];
+                if (ONED) P[(size_t)j * q.pitch] = x + dl / 3.0;
+                else P[(size_t)j * q.pitch] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;
+                G[(size_t)j * q.pitch] = x;
+              }
+            }
           }
         }
       }
