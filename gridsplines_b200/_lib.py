@@ -63,6 +63,12 @@ SIGNATURES = {
     "gs_grid2d_fill": (_vp, C.c_double),
     "gs_grid2d_upload": (_vp, C.c_int, _vp),
     "gs_grid2d_download": (_vp, C.c_int, _vp),
+    "gs_grid2d_get_row": (_vp, C.c_int, C.c_int, _dp),
+    "gs_grid2d_get_col": (_vp, C.c_int, C.c_int, _dp),
+    "gs_grid2d_set_row": (_vp, C.c_int, _dp),
+    "gs_grid2d_set_col": (_vp, C.c_int, _dp),
+    "gs_grid2d_update_x": (_vp, _dp),
+    "gs_grid2d_update_y": (_vp, _dp),
     "gs_grid2d_xiter": (_vp, C.c_double),
     "gs_grid2d_yiter": (_vp, C.c_double),
     "gs_grid2d_update": (_vp,),

@@ -239,6 +239,49 @@ class Spline:
     def trueUpperBound(self) -> float:
         return float(self.knots[-1])
 
+    # -- values and algebra.  Spline.apply on the host side of this package IS the device's (one arithmetic for
+    #    setup and stepping): the table is registered unclamped in the context's pool and evaluated there.
+    def apply(self, xs, ctx: Optional["Context"] = None) -> np.ndarray:
+        ctx = ctx or default_context()
+        xs = np.atleast_1d(_d(xs))
+        sid, out = C.c_int(), np.empty_like(xs)
+        L.check(L.lib().gs_spline_create(ctx._h, self.kind, self.size, _p(self.knots), _p(self.x0),
+                                         _p(np.ascontiguousarray(self.coefs)), -math.inf, math.inf, math.nan, math.nan,
+                                         C.byref(sid)))
+        L.check(L.lib().gs_spline_eval_apply(ctx._h, sid.value, len(xs), _p(xs), _p(out)))
+        return out
+
+    def _sum_arguments(self, other: "Spline", true_upper: bool):
+        """Spline.sumArguments (Spline.scala:198-205): both splines' piece bounds inside the common range, sorted,
+        duplicates dropped.  `upp` follows the same literal rule as `upperBound` unless true_upper."""
+        xs = [x for s in (other, self) for i in range(s.size) for x in (float(s.knots[i]), float(s.knots[i + 1]))]
+        ua = self.trueUpperBound if true_upper else self.upperBound
+        ub = other.trueUpperBound if true_upper else other.upperBound
+        mn, mx = max(self.lowerBound, other.lowerBound), min(ua, ub)
+        return sorted(set(x for x in xs if mn <= x <= mx))
+
+    def combine(self, other: "Spline", op, factory=None, ctx=None, true_upper: bool = False) -> Optional["Spline"]:
+        """Spline./ + - * (Spline.scala:207-225): resample `op(this(x), other(x))` at the merged piece bounds and
+        rebuild with `factory` (the implicit PieceFunFactory; default M1Hermite3).  None where the reference returns
+        None (fewer than two common points)."""
+        xs = self._sum_arguments(other, true_upper)
+        if len(xs) < 2:
+            return None
+        ya, yb = self.apply(xs, ctx), other.apply(xs, ctx)
+        return (factory or Spline.m1Hermite3)([(x, op(float(a), float(b))) for x, a, b in zip(xs, ya, yb)])
+
+    def __truediv__(self, other):
+        return self.combine(other, lambda a, b: a / b)
+
+    def __add__(self, other):
+        return self.combine(other, lambda a, b: a + b)
+
+    def __sub__(self, other):
+        return self.combine(other, lambda a, b: a - b)
+
+    def __mul__(self, other):
+        return self.combine(other, lambda a, b: a * b)
+
 
 class AlwaysDefinedSpline:
     """approximation.AlwaysDefinedSpline (AlwaysDefinedSpline.scala:4-46) registered in a context's
@@ -640,6 +683,54 @@ class TwoDGrid:
 
     def noHeatFlow(self, side: int):
         L.check(L.lib().gs_grid2d_no_heat_flow(self._h, side))
+
+    # ---- slices (TwoDGrid.row / col / left / right / upper / lower, updateRow / updateColumn :260-352; they address
+    #      `grid`), device-side gather / scatter + one contiguous copy
+    def row(self, rowNum: int, copyTo: Optional[np.ndarray] = None, which: int = GRID) -> np.ndarray:
+        out = np.empty(self.cols) if copyTo is None else copyTo
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= self.cols
+        L.check(L.lib().gs_grid2d_get_row(self._h, which, rowNum, _p(out)))
+        return out
+
+    def col(self, colNum: int, copyTo: Optional[np.ndarray] = None, which: int = GRID) -> np.ndarray:
+        out = np.empty(self.rows) if copyTo is None else copyTo
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= self.rows
+        L.check(L.lib().gs_grid2d_get_col(self._h, which, colNum, _p(out)))
+        return out
+
+    def left(self, colNum: int = 0, copyTo=None):
+        return self.col(colNum, copyTo)
+
+    def right(self, colNumFromRight: int = 0, copyTo=None):
+        return self.col(self.cols - 1 - colNumFromRight, copyTo)
+
+    def upper(self, rowNum: int = 0, copyTo=None):
+        return self.row(rowNum, copyTo)
+
+    def lower(self, rowFromLast: int = 0, copyTo=None):
+        return self.row(self.rows - 1 - rowFromLast, copyTo)
+
+    def updateRow(self, rowNum: int, copyFrom):
+        v = _d(copyFrom)
+        assert v.size >= self.cols
+        L.check(L.lib().gs_grid2d_set_row(self._h, rowNum, _p(v)))
+
+    def updateColumn(self, colNum: int, copyFrom):
+        v = _d(copyFrom)
+        assert v.size >= self.rows
+        L.check(L.lib().gs_grid2d_set_col(self._h, colNum, _p(v)))
+
+    def updateX(self, f):
+        """grid(col, row) = f(x_col) for every row (TwoDGrid.updateX :29-41; `grid` only).  The reference's
+        ColumnIterator bounds its walk by rowsNum * (colsNum - 1) (A/YDim.scala:42,51), which is the last row only on
+        square grids; this mirror fills every row of every column, the evident intent."""
+        v = _d([f(self.x.coord(c)) for c in range(self.cols)])
+        L.check(L.lib().gs_grid2d_update_x(self._h, _p(v)))
+
+    def updateY(self, f):
+        """grid(col, row) = f(y_row) for every column (TwoDGrid.updateY :47-58; `grid` only)."""
+        v = _d([f(self.y.coord(r)) for r in range(self.rows)])
+        L.check(L.lib().gs_grid2d_update_y(self._h, _p(v)))
 
     def _edge(self, side) -> float:
         out = C.c_double()

@@ -1774,6 +1774,82 @@ extern "C" int gs_grid2d_update_predicted(gs_grid2d *g) {
   return GS_OK;
 }
 
+// ---- row / column slices and coordinate-wise fills (TwoDGrid.row / col / updateRow / updateColumn :260-330,
+// updateX / updateY :29-58): strided gathers / scatters on the device, one contiguous copy across PCIe ----
+__global__ void k_scatter(double *a, long long start, long long stride, int count, const double *in) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) a[start + (long long)i * stride] = in[i];
+}
+// a[row][col] = per_col ? v[col] : v[row]
+__global__ void k_fill_lines(double *a, int cols, int rows, const double *v, int per_col) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) a[(size_t)row * cols + col] = per_col ? v[col] : v[row];
+}
+static int slice_geometry(gs_grid2d *g, bool is_row, int index, long long *start, long long *stride, int *len) {
+  GS_REQUIRE(index >= 0 && index < (is_row ? g->rows : g->cols), "row / column index out of range");
+  if (is_row) { *start = (long long)index * g->cols; *stride = 1; *len = g->cols; }
+  else { *start = index; *stride = g->cols; *len = g->rows; }
+  return GS_OK;
+}
+static int get_slice(gs_grid2d *g, int which, bool is_row, int index, double *host) {
+  GS_REQUIRE(g && host, "NULL argument");
+  GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
+  gs_ctx *ctx = g->ctx;
+  GS_TRY(gs_ctx_use(ctx));
+  long long start, stride;
+  int len;
+  GS_TRY(slice_geometry(g, is_row, index, &start, &stride, &len));
+  if (which == GS_RESULT) GS_TRY(materialise_result(g));
+  GS_TRY(gs_ctx_stage(ctx, (size_t)len * sizeof(double)));
+  k_gather<<<(len + 127) / 128, 128, 0, ctx->stream>>>(array2d(g, which), start, stride, len, ctx->stage);
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  GS_CUDA(cudaMemcpyAsync(host, ctx->stage, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+static int set_slice(gs_grid2d *g, bool is_row, int index, const double *host) {
+  GS_REQUIRE(g && host, "NULL argument");
+  gs_ctx *ctx = g->ctx;
+  GS_TRY(gs_ctx_use(ctx));
+  long long start, stride;
+  int len;
+  GS_TRY(slice_geometry(g, is_row, index, &start, &stride, &len));
+  GS_TRY(materialise_result(g));   // `result` stops mirroring `grid` once grid is edited
+  g->result_is_grid = false;
+  GS_TRY(gs_ctx_stage(ctx, (size_t)len * sizeof(double)));
+  GS_CUDA(cudaMemcpyAsync(ctx->stage, host, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_scatter<<<(len + 127) / 128, 128, 0, ctx->stream>>>(g->grid, start, stride, len, ctx->stage);
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  GS_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller may reuse `host` right away
+  return GS_OK;
+}
+extern "C" int gs_grid2d_get_row(gs_grid2d *g, int which, int row, double *host) { return get_slice(g, which, true, row, host); }
+extern "C" int gs_grid2d_get_col(gs_grid2d *g, int which, int col, double *host) { return get_slice(g, which, false, col, host); }
+extern "C" int gs_grid2d_set_row(gs_grid2d *g, int row, const double *host) { return set_slice(g, true, row, host); }
+extern "C" int gs_grid2d_set_col(gs_grid2d *g, int col, const double *host) { return set_slice(g, false, col, host); }
+static int fill_lines(gs_grid2d *g, const double *host, bool per_col) {
+  GS_REQUIRE(g && host, "NULL argument");
+  gs_ctx *ctx = g->ctx;
+  GS_TRY(gs_ctx_use(ctx));
+  const int len = per_col ? g->cols : g->rows;
+  GS_TRY(materialise_result(g));
+  g->result_is_grid = false;
+  GS_TRY(gs_ctx_stage(ctx, (size_t)len * sizeof(double)));
+  GS_CUDA(cudaMemcpyAsync(ctx->stage, host, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blocks((g->cols + 255) / 256, std::max(1, std::min(g->rows, 8 * ctx->sm_count)));
+  k_fill_lines<<<blocks, 256, 0, ctx->stream>>>(g->grid, g->cols, g->rows, ctx->stage, per_col ? 1 : 0);
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  GS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+// updateX(f): every node of column c gets f(x_c); updateY(f): every node of row r gets f(y_r).  The host evaluates f.
+extern "C" int gs_grid2d_update_x(gs_grid2d *g, const double *value_per_col) { return fill_lines(g, value_per_col, true); }
+extern "C" int gs_grid2d_update_y(gs_grid2d *g, const double *value_per_row) { return fill_lines(g, value_per_row, false); }
+
 // edge of `grid` into dst (device, side length)
 static int gather_edge(gs_grid2d *g, int side, double *dst) {
   gs_ctx *ctx = g->ctx;

@@ -307,6 +307,35 @@ class TwoDGrid {
     return out;
   }
   void setArray(int which, const std::vector<double> &v) { check(gs_grid2d_upload(h_, which, v.data())); }
+  // slices of `grid` and coordinate-wise fills (A/TwoDGrid.scala:29-58, 260-352)
+  std::vector<double> row(int rowNum) const {
+    std::vector<double> out((size_t)cols);
+    check(gs_grid2d_get_row(h_, GS_GRID, rowNum, out.data()));
+    return out;
+  }
+  std::vector<double> col(int colNum) const {
+    std::vector<double> out((size_t)rows);
+    check(gs_grid2d_get_col(h_, GS_GRID, colNum, out.data()));
+    return out;
+  }
+  std::vector<double> left(int colNum = 0) const { return col(colNum); }
+  std::vector<double> right(int colNumFromRight = 0) const { return col(cols - 1 - colNumFromRight); }
+  std::vector<double> upper(int rowNum = 0) const { return row(rowNum); }
+  std::vector<double> lower(int rowFromLast = 0) const { return row(rows - 1 - rowFromLast); }
+  void updateRow(int rowNum, const std::vector<double> &v) { check(gs_grid2d_set_row(h_, rowNum, v.data())); }
+  void updateColumn(int colNum, const std::vector<double> &v) { check(gs_grid2d_set_col(h_, colNum, v.data())); }
+  template <class F>
+  void updateX(const XDim &x, F f) {   // grid(col, row) = f(x_col)
+    std::vector<double> v((size_t)cols);
+    for (int c = 0; c < cols; ++c) v[c] = f(x.range[c]);
+    check(gs_grid2d_update_x(h_, v.data()));
+  }
+  template <class F>
+  void updateY(const YDim &y, F f) {   // grid(col, row) = f(y_row)
+    std::vector<double> v((size_t)rows);
+    for (int r = 0; r < rows; ++r) v[r] = f(y.range[r]);
+    check(gs_grid2d_update_y(h_, v.data()));
+  }
   const int cols, rows;
 
  private:

@@ -167,6 +167,15 @@ int gs_grid2d_get_bound(gs_grid2d *g, int side, double *out, int n);
 int gs_grid2d_fill(gs_grid2d *g, double value);          /* Grid.*=(v): grid and predict :488-495 */
 int gs_grid2d_upload(gs_grid2d *g, int which, const double *host);   /* row-major rows x cols */
 int gs_grid2d_download(gs_grid2d *g, int which, double *host);
+/* one row / column of an array (TwoDGrid.row / col / left / right / upper / lower(n, copyTo) :260-352 read `grid`) */
+int gs_grid2d_get_row(gs_grid2d *g, int which, int row, double *host);   /* cols values */
+int gs_grid2d_get_col(gs_grid2d *g, int which, int col, double *host);   /* rows values */
+int gs_grid2d_set_row(gs_grid2d *g, int row, const double *host);        /* updateRow :318-328: grid only */
+int gs_grid2d_set_col(gs_grid2d *g, int col, const double *host);        /* updateColumn :291-300: grid only */
+/* updateX(f) / updateY(f) :29-58 with f evaluated by the host: column c <- value_per_col[c] / row r <- value_per_row[r];
+ * grid only (`grid *= (i, v)` :497-499) */
+int gs_grid2d_update_x(gs_grid2d *g, const double *value_per_col);
+int gs_grid2d_update_y(gs_grid2d *g, const double *value_per_row);
 int gs_grid2d_xiter(gs_grid2d *g, double time);           /* TwoDGrid.xIter :135-193 */
 int gs_grid2d_yiter(gs_grid2d *g, double time);           /* TwoDGrid.yIter :195-252 */
 int gs_grid2d_update(gs_grid2d *g);                       /* Grid.update :474-481 */

@@ -58,6 +58,14 @@ int main() {
     printf("gridtest_dims %d %d\n", g.cols, g.rows);
     print("gridtest_grid0", v[0]);
     print("gridtest_grid1", v[1]);
+    // slices address the same doubles (TwoDGrid.row / col / left :260-352)
+    auto r1 = g.row(1), c1 = g.col(1), lf = g.left();
+    int same = r1[1] == v[(size_t)g.cols + 1] && c1[2] == v[(size_t)2 * g.cols + 1] && lf[3] == v[(size_t)3 * g.cols];
+    g.updateColumn(0, std::vector<double>((size_t)g.rows, 5.0));
+    g.updateY(y, [](double yy) { return yy; });
+    auto w = g.array(GS_GRID);
+    same = same && w[(size_t)4 * g.cols + 7] == y.range[4];
+    printf("gridtest_slices_ok %d\n", same);
   }
   return 0;
 }

@@ -33,3 +33,4 @@ def test_cpp_mirror_reproduces_kats(tmp_path):
     assert vals["gridtest_dims"] == ["137", "45"]
     assert float(vals["gridtest_grid0"][0]) == 54.44328715390563          # KAT R1
     assert float(vals["gridtest_grid1"][0]) == 53.94901954479779
+    assert vals["gridtest_slices_ok"] == ["1"]

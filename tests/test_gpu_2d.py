@@ -427,3 +427,58 @@ def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
     o.set_bound(O.LEFT, O.FLOW, O.DENSE, q)
     g.iteration(450.0); o.iteration(450.0)
     _compare_tol(cases.snapshot(g), cases.snapshot(o), "K5 cache invalidation")
+
+
+def test_slices_and_coordinate_fills(gs):
+    """row / col / left / right / upper / lower, updateRow / updateColumn, updateX / updateY (A/TwoDGrid.scala:29-58,
+    260-352): device-side gathers and scatters; the writers touch `grid` only."""
+    p = cases.bc_problem("TTTT", cols=37, rows=29, coefs="const")
+    g = p.build_gs(gs)
+    G, P = g.grid.grid.copy(), g.grid.predict.copy()
+    for r in (0, 11, 28):
+        assert_bit_equal(g.row(r), G[r])
+    for c in (0, 5, 36):
+        assert_bit_equal(g.col(c), G[:, c])
+    assert_bit_equal(g.left(), G[:, 0]); assert_bit_equal(g.right(1), G[:, -2])
+    assert_bit_equal(g.upper(2), G[2]); assert_bit_equal(g.lower(), G[-1])
+    buf = np.zeros(37); g.row(3, buf); assert_bit_equal(buf, G[3])
+    assert_bit_equal(g.row(4, which=gs.PREDICT), P[4])
+    g.updateRow(7, np.arange(37.0)); G[7] = np.arange(37.0)
+    g.updateColumn(9, -np.arange(29.0)); G[:, 9] = -np.arange(29.0)
+    assert_bit_equal(g.grid.grid, G); assert_bit_equal(g.grid.predict, P)
+    g.updateX(lambda x: 3.0 * x)
+    want = np.tile(np.array([3.0 * g.x.coord(c) for c in range(37)]), (29, 1))
+    assert_bit_equal(g.grid.grid, want); assert_bit_equal(g.grid.predict, P)
+    g.updateY(lambda y: 1.0 + y)
+    want = np.repeat(np.array([1.0 + g.y.coord(r) for r in range(29)])[:, None], 37, axis=1)
+    assert_bit_equal(g.grid.grid, want); assert_bit_equal(g.grid.predict, P)
+    with pytest.raises(gs.GsError):
+        g.row(29)
+    with pytest.raises(gs.GsError):
+        g.updateColumn(37, np.zeros(29))
+
+
+@pytest.mark.parametrize("which,factory", [(1, "lines"), (2, "m1Hermite3"), (3, "fHermite3")])
+def test_spline_quotient_matches_reference_resampling(O, gs, which, factory):
+    """Spline./ (P/Spline.scala:198-210): k(T) / c(T) resampled at the merged knots and rebuilt -- how the reference
+    derives the diffusivity table (ConstantCoef, A/TwoDGrid.scala:790-816)."""
+    rho = [0.598, 0.826, 1.121, 1.496, 1.966, 2.547, 3.258, 4.122, 5.156, 6.397, 7.862]
+    T = [-20.0 + 10.0 * i for i in range(11)]
+    kp = [(t, 1.0 + 0.1 * q) for t, q in zip(T, rho)]
+    cp = [(t + (2.5 if i % 3 == 1 else 0.0), 2.0e6 + 1.0e5 * q) for i, (t, q) in enumerate(zip(T, rho))]   # other knots
+    ok, oc = O.Spline.m1Hermite3(kp), O.Spline.m1Hermite3(cp)
+    gk, gc = gs.Spline.m1Hermite3(kp), gs.Spline.m1Hermite3(cp)
+    want = ok.div(oc, which=which)
+    got = gk.combine(gc, lambda a, b: a / b, factory=getattr(gs.Spline, factory))
+    pieces = want.pieces()
+    assert got.size == len(pieces)
+    xs = np.linspace(T[0], T[-2], 301)
+    assert_bit_equal(got.apply(xs), np.array([want(float(x)) for x in xs]))
+    # operators use the default (M1Hermite3) factory
+    if which == 2:
+        assert_bit_equal((gk / gc).apply(xs), got.apply(xs))
+        s = gk + gc
+        assert_bit_equal(s.apply(xs[:5]), gs.Spline.m1Hermite3([(x, float(a) + float(b)) for x, a, b in
+                         zip(gk._sum_arguments(gc, False), gk.apply(gk._sum_arguments(gc, False)),
+                             gc.apply(gk._sum_arguments(gc, False)))]).apply(xs[:5]))
+    assert gs.Spline.line(0.0, 1.0, 1.0, 2.0).combine(gs.Spline.line(5.0, 1.0, 6.0, 2.0), lambda a, b: a / b) is None
