@@ -1564,10 +1564,10 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   bool lit = single;
   for (int s4 = 0; s4 < 4 && lit; ++s4) lit = literal_const(ctx, p.maps.single_off[s4], nullptr);
   const bool tab = !lit && p.smem_pool;
-  const int eblocks = (nlines + 31) / 32;   // one warp per CTA: a few thousand serial threads, spread over all SMs
+  const int eblocks = (nlines + 127) / 128;   // (one warp per CTA measured slower: every CTA stages the pool)
 #define GS_FACES(XD, SG, TB)                                        \
   do {                                                              \
-    k6_ends<XD, SG><<<eblocks, 32, pool_smem, ctx->stream>>>(fq);   \
+    k6_ends<XD, SG><<<eblocks, 128, pool_smem, ctx->stream>>>(fq);  \
     int resident = 0;                                               \
     GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k6_faces<XD, SG, TB>, 256, pool_smem)); \
     dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * std::max(resident, 1) / fbx)));          \

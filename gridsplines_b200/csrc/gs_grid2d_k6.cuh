@@ -117,26 +117,31 @@ GS_DEV bool k6_face_fast(const K6Tab &z, double p0, double p1, double &v) {
   v = gs_div<true>(area, gs_rcp<true>(hi - lo, okd), okd);
   return good && okd;
 }
-// second tier (a few lanes): equal temperatures (average = apply) and intervals that straddle ONE knot, both
-// strictly inside the clamps and the knots.  Follows gs_ads_average / gs_spline_area term by term (same doubles),
-// native division.  Returns false for anything else.
+// second tier: what the straight-line path leaves out but is still one or two table pieces strictly inside the clamps
+// and the knots -- equal temperatures (average = apply), an interval that straddles ONE knot, and one-piece intervals
+// of tables the first tier does not take (Line / Const pieces, unevenly spaced knots).  Follows gs_ads_average /
+// gs_spline_area term by term (same doubles), native division.  Returns false for anything else.
 __device__ __noinline__ bool k6_face_mid(const double *h, double p0, double p1, double *out) {
   const GsSpline s = gs_spline_view(h, 0);
-  if (s.kind != GS_CUBIC) return false;
   const bool eq = p0 == p1;
   const double lo = eq ? gs_jmin(p0, p1) : (p0 < p1 ? p0 : p1), hi = eq ? gs_jmax(p0, p1) : (p0 < p1 ? p1 : p0);
   if (!(lo > s.lowerX && hi < s.upperX && lo >= s.knots[0] && hi <= s.knots[s.np])) return false;
   const int i = gs_knot_floor(s, lo);
   const double *pc = s.pieces + i * GS_PIECE;
   if (eq) {
-    *out = gs_piece_apply(GS_CUBIC, pc, lo);
+    *out = gs_piece_apply(s.kind, pc, lo);
     return true;
   }
-  if (i + 2 > s.np) return false;
+  if (!(lo < hi)) return false;
   const double kb = s.knots[i + 1];
-  if (!(hi > kb && hi < s.knots[i + 2])) return false;
-  double acc = 0.0 + (gs_cubic_antider(pc, kb) - gs_cubic_antider(pc, lo));
-  acc = acc + (gs_cubic_antider(pc + GS_PIECE, hi) - gs_cubic_antider(pc + GS_PIECE, kb));
+  double acc;
+  if (hi < kb) {
+    acc = 0.0 + gs_piece_area(s.kind, pc, lo, hi);                     // one piece
+  } else {
+    if (i + 2 > s.np || !(hi > kb && hi < s.knots[i + 2])) return false;
+    acc = 0.0 + gs_piece_area(s.kind, pc, lo, kb);                     // [lo, k_{i+1}] of piece i
+    acc = acc + gs_piece_area(s.kind, pc + GS_PIECE, kb, hi);          // [k_{i+1}, hi] of piece i + 1
+  }
   acc = 0.0 + acc + 0.0;
   bool ok = true;
   *out = gs_div<false>(acc, gs_rcp<false>(hi - lo, ok), ok);

@@ -3,7 +3,7 @@
 committed fixtures in tests/golden/ (generated from the oracle by tests/golden/make_golden.py)."""
 import numpy as np
 
-from helpers import README_RHO, README_T, hermite_coefs
+from helpers import README_RHO, README_T, hermite_coefs, uneven_coefs
 
 SEED = 20261019
 
@@ -125,6 +125,12 @@ class Problem2D:
             (ok, oc, oa), _ = hermite_coefs(O, gs_)
             ads = [O.AlwaysDefinedSpline(s) for s in (ok, oc, oa)]
             g.set_constant_coef(*ads)
+        elif self.coefs in ("lines_uneven", "hermite_uneven"):
+            import gridsplines_b200 as gs_
+
+            (ok, oc, oa), _ = uneven_coefs(O, gs_, "lines" if self.coefs == "lines_uneven" else "m1Hermite3")
+            ads = [O.AlwaysDefinedSpline(s) for s in (ok, oc, oa)]
+            g.set_constant_coef(*ads)
         elif self.coefs in ("per_row", "per_col", "dense"):
             pool, maps = self._var_pool(lambda v: O.AlwaysDefinedSpline(O.Spline.const(v)),
                                         lambda pts: O.AlwaysDefinedSpline(O.Spline.m1Hermite3(pts)))
@@ -172,6 +178,11 @@ class Problem2D:
             from oracle import oracle as O_
 
             _, (gk, gc, ga) = hermite_coefs(O_, gs)
+            g.set_coefs(gs.ConstantCoef(gk, gc, ga))
+        elif self.coefs in ("lines_uneven", "hermite_uneven"):
+            from oracle import oracle as O_
+
+            _, (gk, gc, ga) = uneven_coefs(O_, gs, "lines" if self.coefs == "lines_uneven" else "m1Hermite3")
             g.set_coefs(gs.ConstantCoef(gk, gc, ga))
         else:
             pool, maps = self._var_pool(lambda v: gs.AlwaysDefinedSpline(gs.Spline.const(v)),

@@ -49,3 +49,14 @@ def hermite_coefs(O, gs, ctx=None):
     ok, oc, oa = (O.Spline.m1Hermite3(p) for p in (kp, cp, ap))
     gk, gc, ga = (gs.Spline.m1Hermite3(p) for p in (kp, cp, ap))
     return (ok, oc, oa), (gk, gc, ga)
+
+
+def uneven_coefs(O, gs, factory="lines"):
+    """k(T), c(T), alpha(T) on UNEVENLY spaced knots, as piecewise-linear tables (Spline.lines) or M1Hermite3: the
+    tables the straight-line face path of K6 does not take."""
+    T = [-25.0, -11.0, -4.0, 3.0, 9.5, 21.0, 30.0, 44.0, 61.0, 90.0]
+    kp = [(t, 1.0 + 0.02 * i * i) for i, t in enumerate(T)]
+    cp = [(t, 2.0e6 + 3.0e4 * i) for i, t in enumerate(T)]
+    ap = [(x, k / c) for (x, k), (_, c) in zip(kp, cp)]
+    mk_o, mk_g = getattr(O.Spline, factory), getattr(gs.Spline, factory)
+    return tuple(mk_o(p) for p in (kp, cp, ap)), tuple(mk_g(p) for p in (kp, cp, ap))

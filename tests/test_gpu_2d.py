@@ -346,6 +346,25 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         ctx.set_option("k5", 1)
 
 
+@pytest.mark.parametrize("coefs", ["lines_uneven", "hermite_uneven"])
+def test_k6_tables_outside_the_fast_tier(O, gs, ctx, coefs):
+    """Piecewise-linear tables and unevenly spaced knots: every face goes through the second tier or the general walk."""
+    p = cases.bc_problem("TTFT", xdir=1, ydir=0, cols=160, rows=256, coefs=coefs)
+    r = np.random.default_rng(12)
+    p.grid0 = r.uniform(-20.0, 80.0, p.grid0.shape)
+    p.grid0[:40, :50] = 12.0
+    p.predict0 = p.grid0 + r.uniform(-1.0, 1.0, p.grid0.shape) * (p.grid0 != 12.0)
+    g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.iteration(900.0, nsteps=2)
+    for _ in range(2):
+        o.iteration(900.0)
+    O.set_ascending_fold(True)
+    tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs}", tol=tol)
+    assert g.status == 0
+
+
 @pytest.mark.parametrize("field", ["uniform", "clamped", "blocks", "knots"])
 def test_k6_face_tiers(O, gs, ctx, field):
     """The faces kernel answers the common face (two different temperatures inside one table piece) in straight-line
