@@ -1,0 +1,131 @@
+"""Parity at BASELINE.json's FULL sizes, through properties that do not need the oracle to walk the whole problem:
+
+* C2 (1 M lines x 256) and C5 (4096 lines x 65536): lines are independent, so any sample of lines must carry the
+  bits the oracle produces for those lines alone;
+* C3 (4096^2) and C4 (16384^2): the partitioned solvers (K5 / K6) against the bit-exact per-line Thomas kernels of the
+  same library on the same device (which the small-size tests pin to the oracle bit for bit), plus the oracle itself on
+  a row band where a whole line is cheap (x sweep), plus the discrete maximum principle.
+"""
+import numpy as np
+import pytest
+
+import cases
+from helpers import assert_bit_equal, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_lines(O, s, grid0, idx, steps):
+    g = grid0[idx].copy()
+    p = np.full_like(g, 4.0)
+    O.batch1d_step(0, s["leftX"], s["rangeX"], s["rightX"], O.Spline.const(1e-6), 1.0, g, p, s["leftT"][idx],
+                   s["rightT"][idx], 900.0, nsteps=steps, nthreads=4)
+    return g, p
+
+
+def test_c2_full_size_sampled_lines_are_bit_exact(O, gs):
+    nlines, n, steps = 1 << 20, 256, 3
+    r = np.random.default_rng(2026)
+    s = dict(leftX=0.0, rangeX=0.01 * np.arange(1, n + 1), rightX=0.01 * (n + 1),
+             leftT=r.uniform(10.0, 30.0, nlines), rightT=r.uniform(0.0, 10.0, nlines))
+    grid0 = r.uniform(0.0, 30.0, (nlines, n))
+    g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], gs.Spline.const(1e-6), 1.0, nlines=nlines)
+    g.upload(gs.GRID, grid0)
+    g.step(900.0, s["leftT"], s["rightT"], nsteps=steps)
+    out, pred = g.download(gs.GRID), g.download(gs.PREDICT)
+    assert g.status == 0
+    idx = np.unique(np.concatenate([[0, 31, 32, nlines - 1], r.integers(0, nlines, 200)]))
+    wg, wp = _sample_lines(O, s, grid0, idx, steps)
+    assert_bit_equal(out[idx], wg, "C2 sampled lines, grid")
+    assert_bit_equal(pred[idx], wp, "C2 sampled lines, predict")
+    assert out.min() >= 0.0 and out.max() <= 30.0            # discrete maximum principle
+
+
+def test_c5_full_size_long_lines(O, gs):
+    nlines, n, steps = 4096, 65536, 2
+    r = np.random.default_rng(2027)
+    s = dict(leftX=0.0, rangeX=1e-3 * np.arange(1, n + 1), rightX=1e-3 * (n + 1),
+             leftT=r.uniform(10.0, 30.0, nlines), rightT=r.uniform(0.0, 10.0, nlines))
+    grid0 = r.uniform(0.0, 30.0, (nlines, n))
+    outs = {}
+    for solver in (gs.SOLVER_AUTO, gs.SOLVER_THOMAS):
+        g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], gs.Spline.const(1e-6), 1.0, nlines=nlines)
+        g.set_solver(solver)
+        g.upload(gs.GRID, grid0)
+        g.step(900.0, s["leftT"], s["rightT"], nsteps=steps)
+        outs[solver] = (g.download(gs.GRID), g.download(gs.PREDICT))
+        assert g.status == 0
+        del g
+    idx = np.array([0, 1, 31, 32, 2047, 4095])
+    wg, wp = _sample_lines(O, s, grid0, idx, steps)
+    assert_bit_equal(outs[gs.SOLVER_THOMAS][0][idx], wg, "C5 per-line Thomas, sampled lines")
+    assert_bit_equal(outs[gs.SOLVER_THOMAS][1][idx], wp, "C5 per-line Thomas, sampled lines, predict")
+    for k in (0, 1):
+        assert max_rel_err(outs[gs.SOLVER_AUTO][k], outs[gs.SOLVER_THOMAS][k]) <= 1e-12    # K5 (segments) vs exact
+
+
+def _grid2d(gs, n, coefs, kinds, bvals, field, solver, xdir=0):
+    x = gs.XDim(0.05 if xdir else 0.0, (0.05 * 1.0005 ** np.arange(1, n + 1)) if xdir else 0.01 * np.arange(1, n + 1),
+                0.05 * 1.0005 ** (n + 1) if xdir else 0.01 * (n + 1), gs.RADIAL if xdir else gs.ORTHO)
+    y = gs.YDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
+    g = gs.TwoDGrid(x, y, coefs=coefs, **kinds)
+    for side, v in bvals.items():
+        getattr(g.bounds, side).update(v)
+    g.set_solver(solver)
+    g.grid.grid = field
+    g.grid.predict = field
+    return g
+
+
+def test_c3_full_size_partitioned_vs_exact_and_oracle(O, gs):
+    n = 4096
+    r = np.random.default_rng(2028)
+    field = 7.0 + r.uniform(size=(n, n))
+    field[100:164, 200:264] = 7.0
+    kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Flow), left=(gs.Many, gs.Flow))
+    bvals = dict(upp=20.0, low=4.0, left=50.0, right=0.0)
+    mk = lambda: gs.ConstantCoef(gs.Spline.const(1.5), gs.Spline.const(2.2e6), gs.Spline.const(1.5 / 2.2e6))
+    fast = _grid2d(gs, n, mk(), kinds, bvals, field, gs.SOLVER_AUTO)
+    exact = _grid2d(gs, n, mk(), kinds, bvals, field, gs.SOLVER_THOMAS)
+    # the oracle on a band of 8 rows: the x sweep solves whole rows, so its `result` rows are the reference's
+    exact.xIter(900.0)
+    band = slice(1000, 1008)
+    og = O.TwoDGrid(np.concatenate([[0.0], 0.01 * np.arange(1, n + 1), [0.01 * (n + 1)]]),
+                    np.concatenate([[0.0], 0.01 * np.arange(1, 9), [0.09]]), 0, 0)
+    ads = [O.AlwaysDefinedSpline(O.Spline.const(v)) for v in (1.5, 2.2e6, 1.5 / 2.2e6)]
+    og.set_constant_coef(*ads)
+    for side, kind, v, m in ((0, 0, 20.0, n), (1, 0, 4.0, n), (2, 1, 0.0, 8), (3, 1, 50.0, 8)):
+        og.set_bound(side, kind, 1, np.full(m, v))
+    og.grid[:] = field[band]; og.predict[:] = field[band]
+    og.xIter(900.0)
+    assert_bit_equal(np.stack([exact.row(rr, which=gs.RESULT) for rr in range(1000, 1008)]), og.result,
+                     "C3 x sweep rows vs oracle")
+    exact.yIterUpdate(900.0)
+    exact.iteration(900.0)
+    fast.iteration(900.0, nsteps=2)
+    for k, a, b in (("grid", fast.grid.grid, exact.grid.grid), ("predict", fast.grid.predict, exact.grid.predict)):
+        assert max_rel_err(a, b) <= 1e-12, k
+    assert fast.status == 0 and exact.status == 0
+
+
+def test_c4_full_size_tables_vs_exact(gs):
+    n = 16384
+    r = np.random.default_rng(2029)
+    field = 7.0 + r.uniform(size=(n, n))
+    rho = [0.598, 0.826, 1.121, 1.496, 1.966, 2.547, 3.258, 4.122, 5.156, 6.397, 7.862]
+    T = [-20.0 + 10.0 * i for i in range(11)]
+    kp = [(t, 1.0 + 0.1 * q) for t, q in zip(T, rho)]
+    cp = [(t, 2.0e6 + 1.0e5 * q) for t, q in zip(T, rho)]
+    k, c = gs.Spline.m1Hermite3(kp), gs.Spline.m1Hermite3(cp)
+    alpha = k / c                                           # Spline./ : how the reference derives the diffusivity
+    kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Temp), left=(gs.Many, gs.Temp))
+    bvals = dict(upp=7.0, low=7.0, right=7.0, left=30.0)
+    res = {}
+    for solver in (gs.SOLVER_AUTO, gs.SOLVER_THOMAS):
+        g = _grid2d(gs, n, gs.ConstantCoef(k, c, alpha), kinds, bvals, field, solver, xdir=1)
+        g.iteration(900.0)      # one step from the rough field: the reference's own 1-ulp sensitivity is ~1e-13 here
+        res[solver] = g.grid.grid
+        assert g.status == 0
+        g.close()
+    assert max_rel_err(res[gs.SOLVER_AUTO], res[gs.SOLVER_THOMAS]) <= 1e-12
+    assert res[gs.SOLVER_AUTO].min() >= 7.0 - 1e-9 and res[gs.SOLVER_AUTO].max() <= 30.0 + 1e-9
