@@ -176,7 +176,7 @@ def test_large_batch_properties(gs):
     assert g.status == 0
 
 
-@pytest.mark.parametrize("chunk_mb,spline", [(128, "const"), (1, "const"), (1, "hermite")])
+@pytest.mark.parametrize("chunk_mb,spline", [(64, "const"), (1, "const"), (1, "hermite")])
 def test_step_host_pipeline(O, gs, ctx, chunk_mb, spline):
     """gs_grid1d_step_host = the drop-in OneDGrid.step with the public `grid` array on the host: upload, step,
     download, pipelined over line chunks.  Two calls in a row (state: host grid + device-private predict)."""
@@ -197,7 +197,7 @@ def test_step_host_pipeline(O, gs, ctx, chunk_mb, spline):
         assert_bit_equal(g.download(gs.PREDICT), op, "device-private predict")
         assert g.status == 0
     finally:
-        ctx.set_option("host_chunk_mb", 128)
+        ctx.set_option("host_chunk_mb", 64)
 
 
 @pytest.mark.parametrize("nlines,n,solver", [(70, 300, 2), (33, 1000, 2), (40, 4099, 0), (64, 8192, 0), (5, 129, 2)])
