@@ -168,14 +168,26 @@ class SpikeShardedTwoDGrid:
     def iteration(self, time: float, nsteps: int = 1):
         P, r = self.world, self.rank
         for _ in range(nsteps):
-            self.g.xIter(time)
-            mine = self.g.predict_edges()
+            mine = self.g.predict_edges()          # predict is frozen until the end of the step
             if self._edges is None:
                 self._edges = mine.new_empty((P,) + tuple(mine.shape))
-            if P > 1:
-                dist.all_gather_into_tensor(self._edges.view(-1, mine.shape[-1]), mine)   # rank-major concatenation
+                self._side = torch.cuda.Stream() if mine.is_cuda else None
+            # the halo rows travel on a side stream while the x sweep runs (they are only needed by the y sweep)
+            ready = None
+            if P > 1 and self._side is not None:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    dist.all_gather_into_tensor(self._edges.view(-1, mine.shape[-1]), mine)   # rank-major concatenation
+                    ready = self._side.record_event()
+                mine.record_stream(self._side)
+            elif P > 1:
+                dist.all_gather_into_tensor(self._edges.view(-1, mine.shape[-1]), mine)
             else:
                 self._edges[0].copy_(mine)
+            self.g.xIter(time)
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
             prev = self._edges[r - 1, 1] if r > 0 else None
             nxt = self._edges[r + 1, 0] if r + 1 < P else None
             exported = self.g.yIterUpdateBegin(time, prev, nxt)
