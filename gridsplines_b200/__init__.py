@@ -4,6 +4,6 @@ from ._lib import (CONST, CUBIC, DENSE, FLAG_NONFINITE, FLAG_NOT_DOMINANT, FLAG_
                    INTERLEAVED, LEFT, LIB_PATH, LINE, LINE_MAJOR, LOW, MAP_DENSE, MAP_PER_COL, MAP_PER_ROW,
                    MAP_SINGLE, ORTHO, PREDICT, RADIAL, RESULT, RIGHT, SEL_APPLY, SEL_CAP, SEL_TEMPCOND, SEL_THERM,
                    SOLVER_AUTO, SOLVER_PARTITIONED, SOLVER_THOMAS, SPARSE, TEMP, UPP, GsError)
-from .api import (AlwaysDefinedSpline, BatchedOneDGrid, Coefficients, ConstantCoef, Context, DenseCoef, Flow, Many,
+from .api import (AlwaysDefinedSpline, BatchedOneDGrid, RaggedLines, Coefficients, ConstantCoef, Context, DenseCoef, Flow, Many,
                   One, OneDGrid, Ortho, Radial, Spline, Temp, TwoDGrid, VarXCoef, VarYCoef, XDim, YDim,
                   default_context)

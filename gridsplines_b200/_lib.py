@@ -88,6 +88,12 @@ SIGNATURES = {
     "gs_grid2d_clear_status": (_vp,),
     "gs_grid2d_device_ptr": (_vp, C.c_int, _vpp),
     "gs_grid2d_bytes_per_step": (_vp, _dp),
+    "gs_ragged_create": (_vp, C.c_int64, C.c_int, _ip, _ip, _dp, C.c_int, _ip, _vpp),
+    "gs_ragged_destroy": (_vp,),
+    "gs_ragged_upload": (_vp, C.c_int, _dp),
+    "gs_ragged_download": (_vp, C.c_int, _dp),
+    "gs_ragged_iteration": (_vp, C.c_double, _dp, _dp),
+    "gs_ragged_status": (_vp, C.POINTER(C.c_uint32)),
 }
 _SPECIAL = {"gs_version": (C.c_int, ()), "gs_last_error": (C.c_char_p, ())}
 

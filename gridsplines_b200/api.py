@@ -455,6 +455,67 @@ class OneDGrid(BatchedOneDGrid):
         return self.download(PREDICT)[0]
 
 
+class RaggedLines:
+    """A ragged batch of lines inside one flattened array: the fixed version of the reference's experimental
+    passion.iteration overload 3 (A/passion/package.scala:161-227).  `lines[l]` = the positions of line l's nodes in the
+    flattened matrix; `preDef[l]` = its (a, c) metric pairs (e.g. `predef(...)` of the line's coordinates);
+    `conductivity` = one Spline / AlwaysDefinedSpline, or per line a list of (left, right) pairs."""
+
+    def __init__(self, matrix_size: int, lines, preDef, conductivity, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.matrix_size = int(matrix_size)
+        lengths = np.array([len(l) for l in lines], dtype=np.int32)
+        indices = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.int32) for l in lines]))
+        pd = np.ascontiguousarray(np.concatenate([_d(p).reshape(-1, 2) for p in preDef]))
+        assert len(pd) == len(indices)
+        if isinstance(conductivity, (Spline, AlwaysDefinedSpline)):
+            self._splines = [_as_ads(conductivity, self.ctx)]
+            mode, ids = SPLINE_SINGLE, np.array([self._splines[0].id], dtype=np.int32)
+        else:
+            pairs = [pr for line in conductivity for pr in line]
+            self._splines = [(_as_ads(a, self.ctx), _as_ads(b, self.ctx)) for a, b in pairs]
+            mode = SPLINE_PER_NODE
+            ids = np.array([[a.id, b.id] for a, b in self._splines], dtype=np.int32).reshape(-1)
+            assert len(ids) == 2 * len(indices)
+        self.nlines = len(lengths)
+        self._h = C.c_void_p()
+        L.check(L.lib().gs_ragged_create(self.ctx._h, self.matrix_size, self.nlines, lengths.ctypes.data_as(L._ip),
+                                         indices.ctypes.data_as(L._ip), _p(pd), mode, ids.ctypes.data_as(L._ip),
+                                         C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().gs_ragged_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _get(self, which) -> np.ndarray:
+        out = np.empty(self.matrix_size)
+        L.check(L.lib().gs_ragged_download(self._h, which, _p(out)))
+        return out
+
+    def _set(self, which, values):
+        v = _d(values).reshape(-1)
+        assert v.size == self.matrix_size
+        L.check(L.lib().gs_ragged_upload(self._h, which, _p(v)))
+
+    grid = property(lambda s: s._get(GRID), lambda s, v: s._set(GRID, v))
+    predicted = property(lambda s: s._get(PREDICT), lambda s, v: s._set(PREDICT, v))
+    result = property(lambda s: s._get(RESULT), lambda s, v: s._set(RESULT, v))
+
+    def iteration(self, time: float, upper, lower):
+        u, lo = _d(upper), _d(lower)
+        assert u.size == self.nlines and lo.size == self.nlines
+        L.check(L.lib().gs_ragged_iteration(self._h, time, _p(u), _p(lo)))
+
+    @property
+    def status(self) -> int:
+        out = C.c_uint32()
+        L.check(L.lib().gs_ragged_status(self._h, C.byref(out)))
+        return out.value
+
+
 # ------------------------------------------------------------------------------------------
 # TwoDGrid
 # ------------------------------------------------------------------------------------------

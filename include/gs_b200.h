@@ -84,6 +84,7 @@ enum { GS_SOLVER_AUTO = 0, GS_SOLVER_THOMAS = 1, GS_SOLVER_PARTITIONED = 2 };
 typedef struct gs_ctx gs_ctx;
 typedef struct gs_grid1d gs_grid1d;
 typedef struct gs_grid2d gs_grid2d;
+typedef struct gs_ragged gs_ragged;
 
 int gs_version(void);
 const char *gs_last_error(void);
@@ -202,6 +203,20 @@ int gs_grid2d_status(gs_grid2d *g, uint32_t *flags);
 int gs_grid2d_clear_status(gs_grid2d *g);
 int gs_grid2d_device_ptr(gs_grid2d *g, int which, void **dptr);
 int gs_grid2d_bytes_per_step(gs_grid2d *g, double *bytes); /* 64 B per node */
+
+/* ---- ragged batch of lines in one flattened array: the fixed version of the experimental
+ * passion.iteration(time, indices, lengths, upper, grid, predicted, localResult, result, lower, preDef, conds,
+ * toPassion) A/passion/package.scala:161-227.  Line l owns lengths[l] consecutive entries of `indices` (positions in
+ * the flattened matrix), of predef[.][2] and -- in GS_SPLINE_PER_NODE mode -- of spline_ids[.][2]; its neighbours are
+ * the line's previous / next entries, its ends see upper[l] / lower[l].  Every line is passion.iteration overload 1
+ * (:52-95) on its gathered nodes; `result` is written at the same positions, the rest of it is left alone. ---- */
+int gs_ragged_create(gs_ctx *ctx, int64_t matrix_size, int nlines, const int *lengths, const int *indices,
+                     const double *predef, int spline_mode, const int *spline_ids, gs_ragged **out);
+int gs_ragged_destroy(gs_ragged *g);
+int gs_ragged_upload(gs_ragged *g, int which, const double *host);      /* GS_GRID / GS_PREDICT / GS_RESULT, matrix_size */
+int gs_ragged_download(gs_ragged *g, int which, double *host);
+int gs_ragged_iteration(gs_ragged *g, double time, const double *upper, const double *lower);   /* nlines each */
+int gs_ragged_status(gs_ragged *g, uint32_t *flags);
 
 #ifdef __cplusplus
 }

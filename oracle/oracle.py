@@ -291,6 +291,17 @@ def heatflow_geometry(direction: int, low: float, rng, upp: float) -> np.ndarray
     return out
 
 
+def passion_iteration(time, firstT, t, lastT, predict, preDef, conds) -> np.ndarray:
+    """passion.iteration overload 1 (A/passion/package.scala:52-95) on one line: t, predict [n]; preDef [n][2];
+    conds = n (left, right) AlwaysDefinedSpline pairs.  Returns result[n]."""
+    t, predict, pd = _d(t), _d(predict), _d(preDef).reshape(-1)
+    n = len(t)
+    arr = (C.c_void_p * (2 * n))(*[x._h for pair in conds for x in pair])
+    tp, res = np.zeros(2 * n), np.zeros(n)
+    lib.gso_passion_iteration(time, firstT, _p(t), n, lastT, _p(predict), _p(pd), arr, _p(tp), _p(res))
+    return res
+
+
 class OneDGrid:
     """approximation.OneDGrid (A/OneDGrid.scala:14-34); `conductivity` a Spline (companion apply)
     or a list of n (left, right) AlwaysDefinedSpline pairs."""
