@@ -6,4 +6,4 @@ from ._lib import (CONST, CUBIC, DENSE, FLAG_NONFINITE, FLAG_NOT_DOMINANT, FLAG_
                    SOLVER_AUTO, SOLVER_PARTITIONED, SOLVER_THOMAS, SPARSE, TEMP, UPP, GsError)
 from .api import (AlwaysDefinedSpline, BatchedOneDGrid, RaggedLines, Coefficients, ConstantCoef, Context, DenseCoef, Flow, Many,
                   One, OneDGrid, Ortho, Radial, Spline, Temp, TwoDGrid, VarXCoef, VarYCoef, XDim, YDim,
-                  default_context)
+                  default_context, discHeatFlow, discTWithFlow, getRadialMidPoint, radialHeatFlow)

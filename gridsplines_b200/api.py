@@ -824,3 +824,34 @@ class TwoDGrid:
         b = C.c_double()
         L.check(L.lib().gs_grid2d_bytes_per_step(self._h, C.byref(b)))
         return b.value
+
+
+# ------------------------------------------------------------------------------------------
+# Heat-flux helper formulas of object TwoDGrid (A/TwoDGrid.scala:1139-1181): pure host arithmetic
+# on values a user loop reads through the edge accessors (AT/GridTest.scala:51-66).  Operation order as written there.
+# ------------------------------------------------------------------------------------------
+def getRadialMidPoint(r0, r1, r2, t0, t1, k0=None, k1=None) -> float:
+    rAtHalf0 = (r0 + r1) / 2.0
+    rAtHalf1 = (r1 + r2) / 2.0
+    if k0 is None:
+        assert r2 - r1 == r1 - r0
+        return (t0 * rAtHalf0 + t1 * rAtHalf1) / (rAtHalf0 + rAtHalf1)
+    a = rAtHalf0 * k0 * (r1 - r0)
+    b = rAtHalf1 * k1 * (r2 - r1)
+    return (a * t0 + b * t1) / (a + b)
+
+
+def discHeatFlow(t0, t1, r0, r1, k) -> float:
+    rAtHalf = (r0 + r1) / 2.0
+    return k * rAtHalf * (t0 - t1) / (r1 - r0) * math.pi * 2.0
+
+
+def radialHeatFlow(t0, t1, r0, r1, k) -> float:
+    resist = math.log(r1 / r0) / (math.pi * 2.0 * k)
+    return (t0 - t1) / resist
+
+
+def discTWithFlow(heatFlow, t0, r0, r1, k) -> float:
+    rAtHalf = (r0 + r1) / 2.0
+    coef = k * rAtHalf / (r1 - r0) * math.pi * 2.0
+    return t0 - heatFlow / coef

@@ -343,4 +343,28 @@ class TwoDGrid {
   BoundSpec spec_[4];
 };
 
+// ---- heat-flux helper formulas of object TwoDGrid (A/TwoDGrid.scala:1139-1181), operation order as written there
+inline double getRadialMidPoint(double r0, double r1, double r2, double t0, double t1) {
+  const double h0 = (r0 + r1) / 2.0, h1 = (r1 + r2) / 2.0;
+  return (t0 * h0 + t1 * h1) / (h0 + h1);
+}
+inline double getRadialMidPoint(double r0, double r1, double r2, double k0, double k1, double t0, double t1) {
+  const double h0 = (r0 + r1) / 2.0, h1 = (r1 + r2) / 2.0;
+  const double a = h0 * k0 * (r1 - r0), b = h1 * k1 * (r2 - r1);
+  return (a * t0 + b * t1) / (a + b);
+}
+inline double discHeatFlow(double t0, double t1, double r0, double r1, double k) {
+  const double h = (r0 + r1) / 2.0;
+  return k * h * (t0 - t1) / (r1 - r0) * 3.141592653589793 * 2.0;
+}
+inline double radialHeatFlow(double t0, double t1, double r0, double r1, double k) {
+  const double resist = std::log(r1 / r0) / (3.141592653589793 * 2.0 * k);
+  return (t0 - t1) / resist;
+}
+inline double discTWithFlow(double heatFlow, double t0, double r0, double r1, double k) {
+  const double h = (r0 + r1) / 2.0;
+  const double coef = k * h / (r1 - r0) * 3.141592653589793 * 2.0;
+  return t0 - heatFlow / coef;
+}
+
 }  // namespace gridsplines
