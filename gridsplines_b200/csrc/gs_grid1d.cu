@@ -46,6 +46,7 @@ struct Line1d {
   const double *pool;   // spline pool
   const int *node_off;  // PER_NODE offsets
   GsSpline z;           // SINGLE spline
+  GsTab zt;             // ... and its fast-path view
   GsRcp rt;             // time step
   double inv_time;      // 1.0 / time
   int n;
@@ -63,8 +64,8 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
   double t1 = firstT, t2 = P[0], t3 = P[GS_LB];
   double condL, condR;
   if (MODE == GS_SPLINE_SINGLE) {
-    condL = gs_ads_apply(L.z, (t1 + t2) / 2.0, flags);   // cons :21-25
-    condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+    condL = gs_ads_apply(L.z, L.zt, (t1 + t2) / 2.0, flags);   // cons :21-25
+    condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
   } else {
     condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[0]), (t1 + t2) / 2.0, flags);
     condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[1]), (t2 + t3) / 2.0, flags);
@@ -84,7 +85,7 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
       // node i's left face is node i-1's right face evaluated with the same spline at the same
       // argument: the same double, so it is carried instead of re-evaluated
       condL = condR;
-      condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+      condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
     } else {
       condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
       condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
@@ -100,7 +101,7 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
   t3 = lastT;
   if (MODE == GS_SPLINE_SINGLE) {
     condL = condR;
-    condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+    condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
   } else {
     condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
     condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(256) k_step1d(Step1dParams p) {
   L.rt = gs_rcp_invariant(p.time, fast_allowed);
   GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
   L.inv_time = 1.0 / p.time;
-  if (MODE == GS_SPLINE_SINGLE) L.z = gs_spline_view(L.pool, p.single_off);
+  if (MODE == GS_SPLINE_SINGLE) {
+    L.z = gs_spline_view(L.pool, p.single_off);
+    L.zt = gs_tab_view(L.pool + p.single_off);
+  }
   unsigned flags = 0;
   const size_t block_elems = (size_t)n * GS_LB;
   double2 *sc = p.scratch + (size_t)warp * block_elems + lane;
@@ -265,8 +269,8 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
       t2 = sP[0];
       t3 = sP[GS_LB];
       if (MODE == GS_SPLINE_SINGLE) {
-        condL = gs_ads_apply(L.z, (t1 + t2) / 2.0, flags);   // cons :21-25
-        condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+        condL = gs_ads_apply(L.z, L.zt, (t1 + t2) / 2.0, flags);   // cons :21-25
+        condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
       } else {
         condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[0]), (t1 + t2) / 2.0, flags);
         condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[1]), (t2 + t3) / 2.0, flags);
@@ -290,7 +294,7 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
           // node i's left face is node i-1's right face evaluated with the same spline at the same
           // argument: the same double, so it is carried instead of re-evaluated
           condL = condR;
-          condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+          condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
         } else {
           condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
           condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
@@ -310,7 +314,7 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
       t3 = lastT;
       if (MODE == GS_SPLINE_SINGLE) {
         condL = condR;
-        condR = gs_ads_apply(L.z, (t2 + t3) / 2.0, flags);
+        condR = gs_ads_apply(L.z, L.zt, (t2 + t3) / 2.0, flags);
       } else {
         condL = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i]), (t1 + t2) / 2.0, flags);
         condR = gs_ads_apply(gs_spline_view(L.pool, L.node_off[2 * i + 1]), (t2 + t3) / 2.0, flags);
@@ -334,8 +338,9 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
   return ok;
 }
 
-template <int MODE, int CH, int NSI>
-__global__ void __launch_bounds__(128) k_step1d_tma(Step1dParams p) {
+// MINB: resident CTAs per SM the register allocation must allow (1: no constraint, 96 registers)
+template <int MODE, int CH, int NSI, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_step1d_tma(Step1dParams p) {
   typedef Pipe1d<CH, NSI> PP;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = p.n;
@@ -373,7 +378,10 @@ __global__ void __launch_bounds__(128) k_step1d_tma(Step1dParams p) {
   L.rt = gs_rcp_invariant(p.time, fast_allowed);
   GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
   L.inv_time = 1.0 / p.time;
-  if (MODE == GS_SPLINE_SINGLE) L.z = gs_spline_view(L.pool, p.single_off);
+  if (MODE == GS_SPLINE_SINGLE) {
+    L.z = gs_spline_view(L.pool, p.single_off);
+    L.zt = gs_tab_view(L.pool + p.single_off);
+  }
   unsigned flags = 0;
   const size_t block_elems = (size_t)n * GS_LB;
   double2 *Sblk = p.scratch + (size_t)warp * block_elems;
@@ -1563,7 +1571,7 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
   // resident line threads per SM: measured optimum per path on B200 (profiles/): the hoisted kernel is
   // DRAM-bound from 7 warps/SM on, the general one wants every warp its shared-memory ring allows
   const bool hoist_path = g->all_const && ctx->opt_const_hoist && ctx->opt_pipeline;
-  int64_t tps = ctx->opt_threads_per_sm_1d > 0 ? ctx->opt_threads_per_sm_1d : 384;
+  int64_t tps = ctx->opt_threads_per_sm_1d > 0 ? ctx->opt_threads_per_sm_1d : ((hoist_path || g->all_const) ? 384 : 768);
   long long want_warps = (long long)ctx->sm_count * std::max<int64_t>(32, tps) / 32;
   long long nwarps = std::min<long long>(nblocks, want_warps);
   size_t need = (size_t)nwarps * (size_t)g->n * GS_LB;
@@ -1703,10 +1711,10 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
     int pblock = (int)std::max<int64_t>(32, std::min<int64_t>(128, ctx->opt_block_1d / 32 * 32));
     int blocks = (int)((nwarps + pblock / 32 - 1) / (pblock / 32));
     const bool single = g->spline_mode == GS_SPLINE_SINGLE;
-#define GS_LAUNCH_PIPE(CH, NSI)                                                                             \
+#define GS_LAUNCH_PIPE(CH, NSI, MINB)                                                                       \
   do {                                                                                                      \
     size_t psmem = smem + (size_t)(pblock / 32) * Pipe1d<CH, NSI>::kWarpBytes;                              \
-    auto kern = single ? k_step1d_tma<GS_SPLINE_SINGLE, CH, NSI> : k_step1d_tma<GS_SPLINE_PER_NODE, CH, NSI>; \
+    auto kern = single ? k_step1d_tma<GS_SPLINE_SINGLE, CH, NSI, MINB> : k_step1d_tma<GS_SPLINE_PER_NODE, CH, NSI, MINB>; \
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));            \
     int per_sm = 0;                                                                                         \
     GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pblock, psmem));                    \
@@ -1715,10 +1723,16 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
     blocks = (int)((p.nwarps + pblock / 32 - 1) / (pblock / 32));                                            \
     kern<<<blocks, pblock, psmem, ctx->stream>>>(p);                                                         \
   } while (0)
-    switch (ctx->opt_pipe_cfg) {
-      case 1: GS_LAUNCH_PIPE(4, 6); break;
-      case 2: GS_LAUNCH_PIPE(8, 4); break;
-      default: GS_LAUNCH_PIPE(4, 3); break;
+    // ring shape: constant tables are DRAM-bound on the (delta, lambda) round trip and want long stages; real tables
+    // are bound by the dependent FP64 chain of one line per thread and want every warp the SM can hold, i.e. short
+    // stages and a register cap (measured, B200, C2 shape: M1Hermite3 4.36 ms with (4, 3) x 12 warps/SM, 3.77 ms
+    // with (2, 3) x 24 warps/SM; constants 3.0 ms against 3.5 ms the other way round)
+    switch (ctx->opt_pipe_cfg ? ctx->opt_pipe_cfg : (g->all_const ? 5 : 3)) {
+      case 1: GS_LAUNCH_PIPE(4, 6, 1); break;
+      case 2: GS_LAUNCH_PIPE(8, 4, 1); break;
+      case 3: GS_LAUNCH_PIPE(2, 3, 6); break;
+      case 4: GS_LAUNCH_PIPE(2, 4, 6); break;
+      default: GS_LAUNCH_PIPE(4, 3, 1); break;
     }
 #undef GS_LAUNCH_PIPE
   } else {

@@ -74,24 +74,9 @@ __global__ void __launch_bounds__(128) k6_ends(K6FacesParams q) {
   if (flags) atomicOr(p.status, flags);
 }
 
-// What the straight-line face path needs of one table (shared-memory copy of the pool)
-struct K6Tab {
-  double lowerX, upperX, k0, inv_h;
-  int np, fast;                 // fast: cubic pieces on equally spaced knots
-  const double *knots, *pieces;
-};
-GS_DEV K6Tab k6_tab(const double *h) {
-  K6Tab z;
-  z.np = (int)h[1];
-  z.lowerX = h[2];
-  z.upperX = h[3];
-  z.inv_h = h[6];
-  z.fast = ((int)h[0] == GS_CUBIC) && (z.inv_h != 0.0);
-  z.knots = h + GS_HDR;
-  z.k0 = z.knots[0];
-  z.pieces = z.knots + (z.np + 1);
-  return z;
-}
+// (GsTab / gs_tab_view of gs_device.cuh: what the straight-line face path needs of one table)
+typedef GsTab K6Tab;
+GS_DEV K6Tab k6_tab(const double *h) { return gs_tab_view(h); }
 // takeAverage for the common interior face: two different, ordered-able temperatures strictly inside the clamps and
 // inside ONE cubic piece.  AlwaysDefinedSpline.average then is  (0.0 + (antider(hi) - antider(lo)) + 0.0) / (hi - lo)
 // (gs_ads_average's one-piece case); the same doubles are produced here without a data-dependent branch.  Returns
