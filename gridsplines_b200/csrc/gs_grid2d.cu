@@ -1281,10 +1281,44 @@ static void k5_shape(int n, int *m, int *S) {
   *m = mm;
   *S = (n + mm - 1) / mm;
 }
-static size_t k5_smem(bool xdir, int m, int S) {
+static size_t k5_smem(bool xdir, int m, int S, int cs = 1) {
   size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
   (void)m;
-  return ((size_t)3 * S * 32 + (size_t)S * (2 * tile + 8 * K5_CH)) * sizeof(double);
+  // clustered strips: the first CTA gathers lambda_e and Q of all cs * S segments (every CTA of the launch is sized alike)
+  size_t gather = cs > 1 ? (size_t)2 * S * cs * 32 : 0;
+  return ((size_t)3 * S * 32 + (size_t)S * (2 * tile + 8 * K5_CH) + gather) * sizeof(double);
+}
+// With fewer strips than half the SMs a strip is given to a cluster of 2 / 4 / 8 CTAs (S segments each)
+static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int nlines, int *m, int *S) {
+  k5_shape(n, m, S);
+  if (!ctx->opt_k5_cluster) return 1;
+  const int strips = (nlines + 31) / 32;
+  int cs = 1;
+  while (cs < 8 && strips * cs * 2 <= ctx->sm_count) cs *= 2;
+  for (; cs > 1; cs /= 2) {
+    const int st = *S * cs;
+    const int mm = ((n + st - 1) / st + K5_CH - 1) / K5_CH * K5_CH;
+    const size_t smem = k5_smem(xdir, mm, *S, cs);
+    if (!(mm >= 2 * K5_CH && (n + mm - 1) / mm == st && smem <= ctx->smem_optin)) continue;
+    // every cluster must be resident at once (a cluster needs cs free SMs in ONE GPC: with one CTA per SM, 8-CTA
+    // clusters leave SMs of every GPC unused and the strips would run in two waves)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) continue;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(strips * cs);
+    cfg.blockDim = dim3(32 * *S);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int resident = 0;
+    if (cudaOccupancyMaxActiveClusters(&resident, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (resident < strips) continue;
+    *m = mm;
+    return cs;
+  }
+  return 1;
 }
 
 static bool use_k5(gs_grid2d *g, bool xdir) {
@@ -1310,15 +1344,15 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
   if (kd.valid && kd.time == time && kd.kind_first == g->b[sf].kind && kd.kind_last == g->b[sl].kind &&
       kd.pool_gen == ctx->spline_off.size())
     return GS_OK;
-  k5_shape(n, &kd.m, &kd.S);
+  kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false> : k5_sweep<false, false>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
     GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
-    GS_CUDA(cudaMalloc(&kd.seg, 64 * sizeof(double4)));
+    GS_CUDA(cudaMalloc(&kd.seg, 128 * sizeof(double4)));
     GS_CUDA(cudaMalloc(&kd.ends, 4 * sizeof(double)));
   }
   K5Setup q;
-  q.n = n; q.m = kd.m; q.S = kd.S; q.dir_x = xdir ? 1 : 0;
+  q.n = n; q.m = kd.m; q.S = kd.S * kd.cs; q.dir_x = xdir ? 1 : 0;
   q.coefs = d.coefs;
   q.firstVol = d.hf[0]; q.fC = d.hf[1]; q.lastVol = d.hf[2]; q.lA = d.hf[3];
   q.kind_first = g->b[sf].kind; q.kind_last = g->b[sl].kind;
@@ -1340,6 +1374,22 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
   kd.kind_first = q.kind_first;
   kd.kind_last = q.kind_last;
   kd.pool_gen = ctx->spline_off.size();
+  return GS_OK;
+}
+
+static int k5_launch(void (*kern)(K5Params), int strips, int threads, size_t smem, cudaStream_t stream, const K5Params &q) {
+  GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(strips * q.csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = q.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
   return GS_OK;
 }
 
@@ -1373,13 +1423,16 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     }
     q.ckpt = g->k5_ckpt;
   }
-  size_t smem = k5_smem(xdir, kd.m, kd.S);
+  size_t smem = k5_smem(xdir, kd.m, kd.S, kd.cs);
   int blocks = (q.d.nlines + 31) / 32, threads = 32 * kd.S;
   q.cta_stride = 32;        // y sweep: a CTA owns 32 adjacent columns
   q.pitch = g->cols;
   q.bc_stride = 1;
   q.strip = 32;
-  if (xdir && ctx->opt_k5_xstrip > 0 && ctx->opt_k5_xstrip <= 32) {
+  q.csize = kd.cs;
+  if (kd.cs > 1) {
+    // clustered strips: full 32-line strips
+  } else if (xdir && ctx->opt_k5_xstrip > 0 && ctx->opt_k5_xstrip <= 32) {
     // x sweep: rows per CTA may be fewer than 32 so that the number of CTAs matches the SM count
     q.strip = (int)ctx->opt_k5_xstrip;
     blocks = (q.d.nlines + q.strip - 1) / q.strip;
@@ -1388,13 +1441,7 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     q.strip = std::max(24, (q.d.nlines + ctx->sm_count - 1) / ctx->sm_count);
     blocks = (q.d.nlines + q.strip - 1) / q.strip;
   }
-  if (xdir) {
-    GS_CUDA(cudaFuncSetAttribute(k5_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k5_sweep<true, false><<<blocks, threads, smem, ctx->stream>>>(q);
-  } else {
-    GS_CUDA(cudaFuncSetAttribute(k5_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k5_sweep<false, false><<<blocks, threads, smem, ctx->stream>>>(q);
-  }
+  GS_TRY(k5_launch(xdir ? k5_sweep<true, false> : k5_sweep<false, false>, blocks, threads, smem, ctx->stream, q));
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
@@ -1419,17 +1466,17 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   gs_k5dir &kd = g->k5;
   const int n = g->n;
   if (!(kd.valid && kd.time == time)) {
-    k5_shape(n, &kd.m, &kd.S);
+    kd.cs = k5_cluster(ctx, k5_sweep<false, true>, false, n, (int)g->nlines, &kd.m, &kd.S);
     if (!kd.tab) {
       GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
       GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
-      GS_CUDA(cudaMalloc(&kd.seg, 64 * sizeof(double4)));
+      GS_CUDA(cudaMalloc(&kd.seg, 128 * sizeof(double4)));
       GS_CUDA(cudaMalloc(&kd.ends, 4 * sizeof(double)));
       size_t need = ((size_t)n / K5_CH + 2) * (size_t)g->pitch;
       GS_CUDA(cudaMalloc(&g->k5_ckpt, need * sizeof(double)));
     }
     K5Setup1d q;
-    q.n = n; q.m = kd.m; q.S = kd.S; q.mode = g->spline_mode;
+    q.n = n; q.m = kd.m; q.S = kd.S * kd.cs; q.mode = g->spline_mode;
     q.predef = g->predef; q.pool = ctx->pool_dev; q.single_off = g->single_off; q.node_off = g->node_off;
     q.time = time;
     q.tab = kd.tab; q.omega_end = kd.omega_end; q.seg = kd.seg; q.ends = kd.ends; q.status = g->status;
@@ -1459,12 +1506,12 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   q.pitch = 32;
   q.strip = 32;
   q.bc_stride = g->bc_stride;
+  q.csize = kd.cs;
   q.status = g->status;
-  size_t smem = k5_smem(false, kd.m, kd.S);
+  size_t smem = k5_smem(false, kd.m, kd.S, kd.cs);
   int blocks = (int)(g->pitch / 32), threads = 32 * kd.S;
-  GS_CUDA(cudaFuncSetAttribute(k5_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int s = 0; s < nsteps; ++s) {
-    k5_sweep<false, true><<<blocks, threads, smem, ctx->stream>>>(q);
+    GS_TRY(k5_launch(k5_sweep<false, true>, blocks, threads, smem, ctx->stream, q));
     ctx->launches++;
   }
   GS_CUDA(cudaGetLastError());

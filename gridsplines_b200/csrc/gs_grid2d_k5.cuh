@@ -21,6 +21,7 @@
 // DRAM traffic: x: read grid (A) + re-read (C, L2) + write result; y: read result (A) + re-read (C) + read grid +
 // write grid', predict'  =>  48 B/node when the re-reads hit L2, against 64 algorithmic bytes.
 #pragma once
+#include <cooperative_groups.h>
 
 #define K5_CH 16  // nodes per chunk
 static_assert(K5_CH == 16, "k5_sweep's unrolled y phase C handles a chunk as two halves of 8");
@@ -46,6 +47,7 @@ struct K5Params {
   long long cta_stride, pitch;
   int strip;             // lines per CTA (<= 32): 28 puts 147 CTAs on the 148 SMs for 4096 lines (x sweep only)
   int bc_stride;         // bound_first/last index = line * bc_stride (1-D batches: 0 = one value for all lines)
+  int csize;             // CTAs per strip (thread-block cluster): the line's csize * S segments are spread over them
   unsigned *status;
 };
 
@@ -260,7 +262,7 @@ __device__ __forceinline__ void k5_load(const K5Params &q, const double *src, in
     }
   } else {
     if (lane < nl) {
-      const double *g = src + (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
+      const double *g = src + (size_t)(blockIdx.x / q.csize) * q.cta_stride + (size_t)i0 * q.pitch + lane;
 #pragma unroll
       for (int j = 0; j < K5_CH; ++j, g += q.pitch)
         if (j < len) k5_cp8(&tile[j * PITCH + lane], g);
@@ -290,15 +292,23 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
   const K5Dir &d = q.d;
   const int S = d.S, m = d.m, n = d.n;
-  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment k
-  const int line0 = blockIdx.x * q.strip, nl = min(q.strip, d.nlines - line0);
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment crank * S + k
+  // With few strips (a shard of a batch, a small grid) a strip belongs to a cluster of csize CTAs: CTA `crank` owns
+  // segments crank * S .. crank * S + S - 1, the first CTA's warp 0 solves the reduced system of all of them through
+  // distributed shared memory.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csz = q.csize, crank = csz > 1 ? (int)cluster.block_rank() : 0, ST = S * csz;
+  const int strip_id = blockIdx.x / csz;
+  const int line0 = strip_id * q.strip, nl = min(q.strip, d.nlines - line0);
+  auto sync_strip = [&]() { if (csz > 1) cluster.sync(); else __syncthreads(); };
   // shared memory: per CTA lamE[S][32], Q[S][32], E[S][32]; per warp tile[DOUBLES] + ckpt[nch_max][32]
   double *lamE = k5sm, *Qs = lamE + S * 32, *Es = Qs + S * 32;
   double *wbase = Es + S * 32 + (size_t)k * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH);
   double4 *tabs2 = reinterpret_cast<double4 *>(wbase);         // 2 x chunk table entries (coalesced load, LDS broadcast)
   double *tile2 = wbase + 8 * K5_CH;
   const size_t ck_pitch = (size_t)((d.nlines + 31) / 32) * 32;
-  const int s = k * m, e = min(n, s + m) - 1;
+  const int s = (crank * S + k) * m, e = min(n, s + m) - 1;
   double *ckpt = q.ckpt + (size_t)(s / K5_CH) * ck_pitch + line0 + lane;   // [chunk * ck_pitch]
   const int nch = (e >= s) ? (e - s) / K5_CH + 1 : 0;
   const bool act = lane < nl;
@@ -345,28 +355,45 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
     if (act) ckpt[(size_t)c * ck_pitch] = lam;   // (a narrower strip's idle lanes would hit the next CTA's slots)
     __syncwarp();
   }
-  lamE[k * 32 + lane] = lam;
-  Qs[k * 32 + lane] = Qacc;
-  __syncthreads();
-  // ---- reduced system (warp 0; lane = line) ----
-  if (k == 0) {
+  // segment results go where the reduced system is solved: this CTA's arrays, or -- clustered strips -- the first
+  // CTA's [ST][32] gather arrays through distributed shared memory (posted remote stores; the solver then reads locally)
+  double *allLam = k5sm + 3 * S * 32 + (size_t)S * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH), *allQ = allLam + ST * 32;
+  if (csz > 1) {
+    const int kg = crank * S + k;
+    cluster.map_shared_rank(allLam, 0)[kg * 32 + lane] = lam;
+    cluster.map_shared_rank(allQ, 0)[kg * 32 + lane] = Qacc;
+  } else {
+    lamE[k * 32 + lane] = lam;
+    Qs[k * 32 + lane] = Qacc;
+  }
+  sync_strip();
+  // ---- reduced system (first CTA's warp 0; lane = line).  Afterwards Es[k] = x at the end of segment k and
+  //      Qs[0 * 32 + lane] of every CTA = x just above its first segment ----
+  if (k == 0 && crank == 0) {
+    double *gl = csz > 1 ? allLam : lamE, *gq = csz > 1 ? allQ : Qs;
     double dp = 0.0;
-    for (int kk = 0; kk < S; ++kk) {
+    for (int kk = 0; kk < ST; ++kk) {
       const double4 sg = d.seg[kk];
-      double rhs = lamE[kk * 32 + lane] + ((kk + 1 < S) ? sg.x * Qs[(kk + 1) * 32 + lane] : 0.0);
+      double rhs = gl[kk * 32 + lane] + ((kk + 1 < ST) ? sg.x * gq[(kk + 1) * 32 + lane] : 0.0);
       dp = (rhs - sg.y * dp) * sg.z;
-      Es[kk * 32 + lane] = dp;
+      gl[kk * 32 + lane] = dp;
     }
     double x = 0.0;
-    for (int kk = S - 1; kk >= 0; --kk) {
-      x = Es[kk * 32 + lane] - d.seg[kk].w * x;
-      Es[kk * 32 + lane] = x;
+    for (int kk = ST - 1; kk >= 0; --kk) {
+      x = gl[kk * 32 + lane] - d.seg[kk].w * x;
+      if (csz > 1) {
+        cluster.map_shared_rank(Es, kk / S)[(kk % S) * 32 + lane] = x;
+        if (kk % S == S - 1 && kk + 1 < ST) cluster.map_shared_rank(Qs, (kk + 1) / S)[lane] = x;
+      } else {
+        Es[kk * 32 + lane] = x;
+      }
     }
+    Qs[lane] = 0.0;
   }
-  __syncthreads();
+  sync_strip();
   // ---- phase C ----
   if (nch == 0) return;
-  const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : 0.0;
+  const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : Qs[lane];
   double x = Es[k * 32 + lane];   // x_e
   unsigned bad = 0;
   {
@@ -423,7 +450,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       __syncwarp();
       k5_store_x<XDIR>(q, q.out, line0, nl, i0, len, tile, lane);
     } else {
-      const size_t off = (size_t)blockIdx.x * q.cta_stride + (size_t)i0 * q.pitch + lane;
+      const size_t off = (size_t)strip_id * q.cta_stride + (size_t)i0 * q.pitch + lane;
       double *G = q.grid_io + off, *P = q.predict_out + off;
       if (pl) {
         // old grid values of the upper half are requested before the recomputation, those of the lower half before

@@ -62,6 +62,7 @@ struct gs_ctx {
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
   int64_t opt_k5_xstrip = 0;   // 0 = automatic
+  int opt_k5_cluster = 1;      // K5: clusters of 2 / 4 / 8 CTAs per strip when strips alone would not fill the chip
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k6_chunk = 8;
@@ -80,7 +81,7 @@ int gs_ctx_stage(gs_ctx *ctx, size_t bytes); // make sure ctx->stage holds at le
 struct gs_k5dir {
   bool valid = false;
   double time = 0.0;
-  int kind_first = -1, kind_last = -1, m = 0, S = 0;
+  int kind_first = -1, kind_last = -1, m = 0, S = 0, cs = 1;   // S: segments (warps) per CTA, cs: CTAs per strip
   size_t pool_gen = 0;
   double4 *tab = nullptr, *seg = nullptr;
   double *omega_end = nullptr, *ends = nullptr;

@@ -425,6 +425,27 @@ def test_k6_clustered_strips(O, gs, ctx, cols, rows):
         ctx.set_option("k6_cluster", 1)
 
 
+@pytest.mark.parametrize("cols,rows,combo", [(2048, 64, "TTFF"), (64, 2048, "TFTT"), (4096, 200, "TTTT")])
+def test_k5_clustered_strips(O, gs, ctx, cols, rows, combo):
+    """Constant coefficients, few lines in one direction: a strip's segments are spread over a cluster of up to 8
+    CTAs (distributed shared memory for the reduced system).  Same answer as one CTA per strip, and as the reference."""
+    p = cases.bc_problem(combo, xdir=1, ydir=0, cols=cols, rows=rows, coefs="const")
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.iteration(900.0, nsteps=2)
+    for _ in range(2):
+        o.iteration(900.0)
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K5 clusters {cols}x{rows}")
+    ctx.set_option("k5_cluster", 0)
+    try:
+        h = p.build_gs(gs)
+        h.set_solver(gs.SOLVER_PARTITIONED)
+        h.iteration(900.0, nsteps=2)
+        _compare_tol(cases.snapshot(g), cases.snapshot(h), "clusters vs single CTA")
+    finally:
+        ctx.set_option("k5_cluster", 1)
+
+
 def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
     """K5 caches its line-independent tables per (grid, direction, time step): changing the coefficients, the time
     step or a bound's kind must rebuild them."""
