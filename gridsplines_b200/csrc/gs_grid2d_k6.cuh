@@ -142,9 +142,9 @@ __device__ __noinline__ double k6_face_general(const double *pool, int off, doub
 }
 
 // Interior faces F[i], 1 <= i <= n - 2, of every line.  TAB (table-driven maps, pool staged in shared memory): every
-// warp walks (row, 32-column group) tiles  t = warp + k * nwarps  in row-major order, the column group rotated by the
-// row so that no warp keeps the same columns (a boundary layer along one edge makes those columns' faces take the
-// slower tiers); loads run D tiles ahead of the arithmetic.  Otherwise (literal constants, oversized pools): blocks
+// warp walks (row, 64-column group) tiles  t = warp + k * nwarps  in row-major order (two faces per lane and tile), the
+// column group rotated by the row so that no warp keeps the same columns (a boundary layer along one edge makes those
+// columns' faces take the slower tiers); the next tile's loads are in flight during a tile's arithmetic.  Otherwise (literal constants, oversized pools): blocks
 // of 256 columns x a stride of rows with the generic evaluation.
 template <bool XDIR, class SEL, bool TAB>
 __global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
@@ -158,28 +158,29 @@ __global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
     for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) k6sm[i] = p.pool[i];
     __syncthreads();
     constexpr bool single = SEL::single;
-    constexpr int D = 2;
+    constexpr int U = 2;                         // faces per lane per tile: a tile is one row x 32 * U columns
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int ncg = (p.cols + 31) >> 5, nrows = r_hi - r_lo;
+    const int ncg = (p.cols + 32 * U - 1) / (32 * U), nrows = r_hi - r_lo;
     const int dj = W % ncg, drow = W / ncg, drm = drow % ncg;
     // tile walker: j = t % ncg, row = t / ncg (relative to r_lo), rmod = row % ncg
     int j = w % ncg, row = w / ncg, rmod = row % ncg;
     int off = p.maps.single_off[GS_SEL_APPLY];
     K6Tab z = k6_tab(k6sm + off);
-    double q0[D], q1[D];
-    int qrow[D], qcol[D];
-    auto fetch = [&](int d) {   // loads of the walker's tile into slot d, then advances the walker
+    // loads of the walker's tile (nothing for columns outside the interior), then one step of the walker
+    auto fetch = [&](double (&a0)[U], double (&a1)[U], int (&cl)[U], int &rw) {
       int cg = j + rmod;
       if (cg >= ncg) cg -= ncg;
-      const int col = cg * 32 + lane;
-      qrow[d] = row;
-      qcol[d] = (col >= c_lo && col < c_hi) ? col : -1;
-      q0[d] = q1[d] = 0.0;
-      if (row < nrows && qcol[d] >= 0) {
-        const double *pp = p.predict + (size_t)(row + r_lo) * p.cols + col;
-        q0[d] = pp[0];
-        q1[d] = pp[nb];
+      rw = row;
+      const int col0 = cg * (32 * U) + lane;
+      const double *pp = p.predict + (size_t)(row + r_lo) * p.cols + col0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = col0 + 32 * u;
+        const bool okc = row < nrows && col >= c_lo && col < c_hi;
+        cl[u] = okc ? col : -1;
+        a0[u] = a1[u] = 0.0;
+        if (okc) { a0[u] = pp[32 * u]; a1[u] = pp[32 * u + nb]; }
       }
       j += dj;
       const int c = j >= ncg;
@@ -188,28 +189,30 @@ __global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
       rmod += drm + c;
       if (rmod >= ncg) rmod -= ncg;
     };
-#pragma unroll
-    for (int d = 0; d < D; ++d) fetch(d);
+    double c0[U], c1[U], n0[U], n1[U];
+    int ccol[U], ncol[U], crow, nrow;
+    fetch(c0, c1, ccol, crow);
 #pragma unroll 1
-    while (qrow[0] < nrows) {
+    while (crow < nrows) {
+      fetch(n0, n1, ncol, nrow);                 // the next tile's loads fly during this tile's arithmetic
+      double *frow = q.F + (size_t)(crow + r_lo) * p.cols;
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int rw = qrow[d] + r_lo, col = qcol[d];
-        const bool live = qrow[d] < nrows;
-        const double c0 = q0[d], c1 = q1[d];
-        fetch(d);
-        if (live && col >= 0) {
+      for (int u = 0; u < U; ++u) {
+        if (ccol[u] >= 0) {
           if (!single) {
-            off = map_off(p.maps, GS_SEL_APPLY, col, rw, p.cols);
+            off = map_off(p.maps, GS_SEL_APPLY, ccol[u], crow + r_lo, p.cols);
             z = k6_tab(k6sm + off);
           }
           double v;
-          if (!k6_face_fast(z, c0, c1, v)) {
-            if (!k6_face_mid(k6sm + off, c0, c1, &v)) v = k6_face_general(p.pool, off, c0, c1, p.status);
+          if (!k6_face_fast(z, c0[u], c1[u], v)) {
+            if (!k6_face_mid(k6sm + off, c0[u], c1[u], &v)) v = k6_face_general(p.pool, off, c0[u], c1[u], p.status);
           }
-          q.F[(size_t)rw * p.cols + col] = v;
+          frow[ccol[u]] = v;
         }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { c0[u] = n0[u]; c1[u] = n1[u]; ccol[u] = ncol[u]; }
+      crow = nrow;
     }
   } else {
     const double *pool = stage_pool(p, k6sm);
