@@ -4,9 +4,9 @@
 // The expensive part of the reference's row assembly is the material property at every cell face: an interval
 // average of a spline table (A/Dim.scala:67-83 -> A/AlwaysDefinedSpline.scala:43-46), ~100+ instructions with a
 // division.  It depends on `predict` only, which is frozen during a step, so it is NOT part of the Thomas
-// recurrence: k6_faces evaluates every face of a direction in one fully parallel, coalesced pass
+// recurrence: k6_faces evaluates every interior face of a direction in one fully parallel, coalesced pass
 //     F[i] = co(predict_i, predict_{i+1}, z_i)        (Dim.general's `co`; the carry out of the first node at i = 0)
-// with the reference's own formulas (same doubles), and assembles the two end rows of every line (Dirichlet or
+// with the reference's own formulas (same doubles); k6_ends assembles the two end rows of every line (Dirichlet or
 // heat-flow, A/Dim.scala:28-64, 86-128) into small per-line arrays.  k6_sweep then is K5's one-CTA-per-strip
 // pipeline (phase A -> reduced system -> phase C, cp.async double-buffered chunks, checkpoints per chunk) whose
 // per-node work is only the elimination:  sub = cf0 F[i-1], sup = cf1 F[i], diag = -(sub+sup) - 1/tau,
