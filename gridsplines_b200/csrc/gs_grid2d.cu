@@ -1546,10 +1546,12 @@ static int k6_cluster(gs_ctx *ctx, int n, int nlines, int *m, int *S) {
   }
   return 1;
 }
-static size_t k6_smem(gs_ctx *ctx, bool xdir, int S) {
+// ff: fused faces -- the second tile of a buffer holds ch + 1 rows of predict, and the spline pool is staged as well
+static size_t k6_smem(gs_ctx *ctx, bool xdir, int S, bool ff = false, int pool_len = 0) {
   const int ch = k6_chunk(ctx);
-  size_t tile = (size_t)ch * (xdir ? 33 : 32);
-  return ((size_t)6 * S * 32 + (size_t)S * (4 * tile + 4 * ch)) * sizeof(double);
+  const size_t pitch = xdir ? 33 : 32;
+  const size_t buf = (size_t)ch * pitch + (size_t)(ff ? ch + 1 : ch) * pitch;
+  return ((size_t)6 * S * 32 + (size_t)S * (2 * buf + 4 * ch) + (ff ? (size_t)pool_len : 0)) * sizeof(double);
 }
 static bool use_k6(gs_grid2d *g, bool xdir) {
   gs_ctx *ctx = g->ctx;
@@ -1612,9 +1614,17 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   for (int s4 = 0; s4 < 4 && lit; ++s4) lit = literal_const(ctx, p.maps.single_off[s4], nullptr);
   const bool tab = !lit && p.smem_pool;
   const int eblocks = (nlines + 127) / 128;   // (one warp per CTA measured slower: every CTA stages the pool)
+  // fused faces: the sweep evaluates the interior faces itself (phase A), only the end rows need their own kernel
+  const bool ff = tab && ctx->opt_k6_fuse && k6_chunk(ctx) == 8;
+  {
+    int m_, S_;
+    k6_shape(ctx, n, &m_, &S_);
+    GS_REQUIRE(!ff || k6_smem(ctx, xdir, S_, true, p.pool_len) <= ctx->smem_optin, "K6 shared memory");
+  }
 #define GS_FACES(XD, SG, TB)                                        \
   do {                                                              \
     k6_ends<XD, SG><<<eblocks, 128, pool_smem, ctx->stream>>>(fq);  \
+    if (ff) break;                                                  \
     int resident = 0;                                               \
     GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k6_faces<XD, SG, TB>, 256, pool_smem)); \
     dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * std::max(resident, 1) / fbx)));          \
@@ -1655,14 +1665,19 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   q.gathered = split ? split->gathered : nullptr;
   q.nranks = split ? split->nranks : 1;
   q.rank = split ? split->rank : 0;
-  size_t smem = k6_smem(ctx, xdir, q.S);
+  q.predict = p.predict; q.Fout = g->k6_F; q.pool = p.pool; q.pool_len = p.pool_len; q.maps = p.maps;
+  size_t smem = k6_smem(ctx, xdir, q.S, ff, p.pool_len);
   int blocks = (nlines + 31) / 32, threads = 32 * q.S;
   void (*kern)(K6Params);
   const bool ch16 = k6_chunk(ctx) == 16;
-  if (mode == K6_BEGIN) kern = ch16 ? k6_sweep<false, 16, K6_BEGIN> : k6_sweep<false, 8, K6_BEGIN>;
-  else if (mode == K6_END) kern = ch16 ? k6_sweep<false, 16, K6_END> : k6_sweep<false, 8, K6_END>;
-  else kern = ch16 ? (xdir ? k6_sweep<true, 16, K6_FUSED> : k6_sweep<false, 16, K6_FUSED>)
-                   : (xdir ? k6_sweep<true, 8, K6_FUSED> : k6_sweep<false, 8, K6_FUSED>);
+  if (ff) {
+    if (mode == K6_BEGIN) kern = k6_sweep<false, 8, K6_BEGIN, true>;
+    else if (mode == K6_END) kern = k6_sweep<false, 8, K6_END, true>;
+    else kern = xdir ? k6_sweep<true, 8, K6_FUSED, true> : k6_sweep<false, 8, K6_FUSED, true>;
+  } else if (mode == K6_BEGIN) kern = ch16 ? k6_sweep<false, 16, K6_BEGIN, false> : k6_sweep<false, 8, K6_BEGIN, false>;
+  else if (mode == K6_END) kern = ch16 ? k6_sweep<false, 16, K6_END, false> : k6_sweep<false, 8, K6_END, false>;
+  else kern = ch16 ? (xdir ? k6_sweep<true, 16, K6_FUSED, false> : k6_sweep<false, 16, K6_FUSED, false>)
+                   : (xdir ? k6_sweep<true, 8, K6_FUSED, false> : k6_sweep<false, 8, K6_FUSED, false>);
   GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     cudaLaunchConfig_t cfg = {};
@@ -1677,7 +1692,7 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
     cfg.numAttrs = 1;
     GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
   }
-  ctx->launches += mode == K6_END ? 1 : 3;
+  ctx->launches += mode == K6_END ? 1 : (ff ? 2 : 3);
   GS_CUDA(cudaGetLastError());
   return GS_OK;
 }

@@ -253,21 +253,38 @@ struct K6Params {
   const double *gathered;  // [nranks][6][nlines]
   int nranks, rank;
   int csize;               // CTAs per strip (thread-block cluster): the line's segments are spread over csize x S warps
+  // fused faces (FF): phase A reads `predict` instead of F, evaluates the faces along its lines itself and writes F
+  // for phase C -- no separate faces pass
+  const double *predict;
+  double *Fout;            // = F
+  const double *pool;      // spline pool (global) and its length; staged into shared memory
+  int pool_len;
+  Maps2d maps;
 };
 #define K6_FUSED 0
 #define K6_BEGIN 1
 #define K6_END 2
 
-template <bool XDIR, int CH>
+// PRED: the second tile receives `predict` of nodes i0 .. i0 + len (one more than the chunk, when that node exists)
+// instead of the face values F of nodes i0 .. i0 + len - 1
+template <bool XDIR, int CH, bool PRED = false>
 __device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, int i0, int len, double *tileT,
                                         double *tileF, double2 *tabs, int lane) {
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
   if (lane < len) k5_cp16(tabs + lane, q.coefs + 2 * (size_t)(i0 + lane));   // (cf0, cf1) of the chunk's nodes
+  const double *second = PRED ? q.predict : q.F;
+  if (PRED && i0 + len < q.n) {   // the node after the chunk
+    if (XDIR) {
+      if (lane < nl) k5_cp8(&tileF[len * PITCH + lane], second + (size_t)(line0 + lane) * q.cols + i0 + len);
+    } else {
+      if (lane < nl) k5_cp8(&tileF[len * PITCH + lane], second + (size_t)(i0 + len) * q.cols + line0 + lane);
+    }
+  }
   if (XDIR) {
     const int jj = lane & (CH - 1);
     if (jj < len) {
       const size_t off = (size_t)line0 * q.cols + i0 + jj;
-      const double *gT = q.rhs + off, *gF = q.F + off;
+      const double *gT = q.rhs + off, *gF = second + off;
       const size_t rs = (size_t)(32 / CH) * q.cols;
       int r = lane / CH;
       gT += (size_t)r * q.cols; gF += (size_t)r * q.cols;
@@ -284,7 +301,7 @@ __device__ __forceinline__ void k6_load(const K6Params &q, int line0, int nl, in
   } else {
     if (lane < nl) {
       const size_t off = (size_t)i0 * q.cols + line0 + lane;
-      const double *gT = q.rhs + off, *gF = q.F + off;
+      const double *gT = q.rhs + off, *gF = second + off;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         if (j < len) {
@@ -316,11 +333,19 @@ __device__ __forceinline__ double k6_rcp(double b) {
 // MODE K6_FUSED: the whole solve.  K6_BEGIN: phase A and the condensation of this rank's rows into one segment
 // (exported for the all-gather).  K6_END: the ranks' reduced system (every rank solves all of it, a few unknowns per
 // line), the local back-substitution and phase C.
-template <bool XDIR, int CH, int MODE>
+// FF: phase A evaluates the faces itself (see K6Params); the second tile of a buffer then has CH + 1 rows.  Saves the
+// faces pass and 8 B/node of traffic per direction, but MEASURED (B200, 4096^2, M1Hermite3): 0.564 ms/step against
+// 0.545 ms with the separate k6_faces pass -- at 16 warps and 128 registers per SM the ~90 instructions per face run
+// slower inside the sweep than in the 32-warp faces kernel, and all CTAs are in phase A at the same time, so nothing
+// overlaps with the bandwidth-bound phase C.  Kept behind the option `k6_fuse` (default off) as a tested variant: the
+// next step is to give the faces to dedicated producer warps.
+template <bool XDIR, int CH, int MODE, bool FF>
 __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   extern __shared__ __align__(16) double k6s[];
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
   constexpr int TD = CH * PITCH;
+  constexpr int TD2 = FF ? (CH + 1) * PITCH : TD;     // second tile: F [CH] or predict [CH + 1]
+  constexpr int BUF = TD + TD2;                        // one buffer = (t tile, second tile)
   const int S = q.S, m = q.m, n = q.n;
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
   // A strip of 32 lines belongs to a cluster of csize CTAs (1 when there are strips enough to fill the chip): CTA
@@ -332,9 +357,14 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   const int line0 = (blockIdx.x / csz) * 32, nl = min(32, q.nlines - line0);
   // shared: per CTA seg[6][S][32] (delta_e, omega_e, P, R, lambda_e, Q) ; per warp 2 x (tileT, tileF) + 2 x tabs
   double *segs = k6s;
-  double *wbase = k6s + 6 * S * 32 + (size_t)k * (4 * TD + 4 * CH);
+  double *wbase = k6s + 6 * S * 32 + (size_t)k * (2 * BUF + 4 * CH);
   double2 *tabs2 = reinterpret_cast<double2 *>(wbase);
   double *tiles = wbase + 4 * CH;
+  double *poolsm = k6s + 6 * S * 32 + (size_t)S * (2 * BUF + 4 * CH);   // FF: the spline pool
+  if (FF && MODE != K6_END) {
+    for (int i = threadIdx.x; i < q.pool_len; i += blockDim.x) poolsm[i] = q.pool[i];
+    __syncthreads();
+  }
   const int s = (crank * S + k) * m, e = min(n, s + m) - 1;
   auto sync_strip = [&]() { if (csz > 1) cluster.sync(); else __syncthreads(); };
   // segment kk's slot column in whichever CTA of the cluster holds it
@@ -383,30 +413,120 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   auto plain = [&](int i0) { return i0 > 0 && i0 + CH - 1 < e; };
 
   const size_t cd_pitch = ck_pitch;
+  // FF: one face along the line, between a node and its successor, from their predicted temperatures (the tiers of
+  // k6_faces; `i` = position of the first of the two on the line, for coefficient maps that vary over the grid)
+  const bool single_map = !FF || q.maps.mode[GS_SEL_APPLY] == GS_MAP_SINGLE;
+  int zoff = FF ? q.maps.single_off[GS_SEL_APPLY] : 0;
+  K6Tab ztab = {};
+  if (FF && MODE != K6_END) ztab = k6_tab(poolsm + zoff);
+  auto face = [&](double p0, double p1, int i) -> double {
+    if (!single_map) {
+      zoff = map_off(q.maps, GS_SEL_APPLY, XDIR ? i : line, XDIR ? line : i, q.cols);
+      ztab = k6_tab(poolsm + zoff);
+    }
+    double v;
+    if (!k6_face_fast(ztab, p0, p1, v)) {
+      if (!k6_face_mid(poolsm + zoff, p0, p1, &v)) v = k6_face_general(q.pool, zoff, p0, p1, q.status);
+    }
+    return v;
+  };
+  // which faces the sweep evaluates itself: all but the ones k6_ends owns (the carry out of a closed first node, the
+  // last node's: 0, or the face to the rank below)
+  auto own_face = [&](int i) { return (i >= 1 || open_first) && i <= n - 2; };
   // face below the segment's left neighbour (the rank above holds that neighbour when the first end is open)
-  const double f_seg = (s > 0 && s < n) ? q.F[lbase + (size_t)(s - 1) * lstride] : ((s == 0 && open_first) ? q.fm1[line] : 0.0);
+  double f_seg;
+  if (s > 0 && s < n) {
+    if (FF && MODE != K6_END && own_face(s - 1)) {
+      f_seg = act ? face(q.predict[lbase + (size_t)(s - 1) * lstride], q.predict[lbase + (size_t)s * lstride], s - 1) : 0.0;
+    } else {
+      f_seg = q.F[lbase + (size_t)(s - 1) * lstride];
+    }
+  } else {
+    f_seg = (s == 0 && open_first) ? q.fm1[line] : 0.0;
+  }
   if (MODE != K6_END) {
     // ---- phase A ----
     K6State st;
     st.delta = 0.0; st.lambda = 0.0; st.omega = (s > 0 || open_first) ? 1.0 : 0.0;
     st.fprev = f_seg;
     double P = 1.0, Qa = 0.0, R = 0.0;
-    if (nch > 0) k6_load<XDIR, CH>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
+    if (nch > 0) k6_load<XDIR, CH, FF>(q, line0, nl, s, min(CH, e - s + 1), tiles, tiles + TD, tabs2, lane);
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
       const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
-      double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
+      double *tT = tiles + (c & 1) * BUF, *tF = tT + TD;
       const double2 *cf = tabs2 + (c & 1) * CH;
       if (c + 1 < nch) {
         const int i1 = i0 + CH;
-        double *nT = tiles + ((c + 1) & 1) * 2 * TD;
-        k6_load<XDIR, CH>(q, line0, nl, i1, min(CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * CH, lane);
+        double *nT = tiles + ((c + 1) & 1) * BUF;
+        k6_load<XDIR, CH, FF>(q, line0, nl, i1, min(CH, e - i1 + 1), nT, nT + TD, tabs2 + ((c + 1) & 1) * CH, lane);
         k5_wait<1>();
       } else {
         k5_wait<0>();
       }
       __syncwarp();
-      if (plain(i0)) {
+      const bool pl = plain(i0);
+      if (FF) {
+        // the chunk's faces, from the predict tile (rows 0 .. len), into registers and out to F for phase C
+        double Fv[CH];
+        if (pl) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            Fv[j] = act ? face(tF[j * PITCH + lane], tF[(j + 1) * PITCH + lane], i0 + j) : 0.0;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            Fv[j] = 0.0;
+            if (j < len && act) {
+              const int i = i0 + j;
+              Fv[j] = own_face(i) ? face(tF[j * PITCH + lane], tF[(j + 1) * PITCH + lane], i)
+                                  : __ldcg(q.F + lbase + (size_t)i * lstride);
+            }
+          }
+        }
+        __syncwarp();
+        if (XDIR) {
+          // through the tile for a transposed store (rows of F are lines here)
+#pragma unroll
+          for (int j = 0; j < CH; ++j) tF[j * PITCH + lane] = Fv[j];
+          __syncwarp();
+          const int jj = lane & (CH - 1);
+          if (jj < len) {
+            int r = lane / CH;
+            double *gq = q.Fout + (size_t)(line0 + r) * q.cols + i0 + jj;
+            const size_t rs = (size_t)(32 / CH) * q.cols;
+#pragma unroll
+            for (int u = 0; u < CH; ++u, r += 32 / CH, gq += rs)
+              if (r < nl) *gq = tF[jj * PITCH + r];
+          }
+        } else if (act) {
+          double *gq = q.Fout + (size_t)i0 * q.cols + line0 + lane;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (j < len) gq[(size_t)j * q.cols] = Fv[j];
+        }
+        if (pl) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            node_mid(tT[j * PITCH + lane], Fv[j], cf[j], st);
+            Qa = fma(P, st.lambda, Qa);
+            R = fma(P, st.omega, R);
+            P = P * st.delta;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (j < len) {
+              node_any(i0 + j, tT[j * PITCH + lane], Fv[j], cf[j], st);
+              if (i0 + j < e) {
+                Qa = fma(P, st.lambda, Qa);
+                R = fma(P, st.omega, R);
+                P = P * st.delta;
+              }
+            }
+          }
+        }
+      } else if (pl) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           node_mid(tT[j * PITCH + lane], tF[j * PITCH + lane], cf[j], st);
@@ -532,14 +652,14 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
   double x = segs[4 * S * 32 + (size_t)k * 32 + lane];
   {
     const int il = s + (nch - 1) * CH;
-    double *nT = tiles + ((nch - 1) & 1) * 2 * TD;
+    double *nT = tiles + ((nch - 1) & 1) * BUF;
     k6_load<XDIR, CH>(q, line0, nl, il, min(CH, e - il + 1), nT, nT + TD, tabs2 + ((nch - 1) & 1) * CH, lane);
   }
   double4 ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : make_double4(0.0, 0.0, 0.0, 0.0);
 #pragma unroll 1
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * CH, len = min(CH, e - i0 + 1);
-    double *tT = tiles + (c & 1) * 2 * TD, *tF = tT + TD;
+    double *tT = tiles + (c & 1) * BUF, *tF = tT + TD;
     const double2 *cf = tabs2 + (c & 1) * CH;
     // old grid values of the chunk (fused Grid.update): issued ahead of the arithmetic
     double gold[CH];
@@ -549,7 +669,7 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       for (int u = 0; u < CH; ++u) gold[u] = (act && u < len) ? q.grid_io[yoff + (size_t)u * q.cols] : 0.0;
     }
     if (c > 0) {
-      double *nT = tiles + ((c - 1) & 1) * 2 * TD;
+      double *nT = tiles + ((c - 1) & 1) * BUF;
       k6_load<XDIR, CH>(q, line0, nl, i0 - CH, CH, nT, nT + TD, tabs2 + ((c - 1) & 1) * CH, lane);
       k5_wait<1>();
     } else {

@@ -66,6 +66,7 @@ struct gs_ctx {
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k6_chunk = 8;
+  int opt_k6_fuse = 0;          // K6: the sweep evaluates the faces along its lines itself (no separate faces pass); measured slower, off
   int opt_k6_cluster = 1;       // K6: give a strip to a cluster of 2 / 4 CTAs when strips alone would not fill the chip
   int64_t opt_host_chunk_mb = 64;
   int64_t opt_ck_block = 16;

@@ -346,6 +346,32 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         ctx.set_option("k5", 1)
 
 
+@pytest.mark.parametrize("coefs,combo,cols,rows", [("hermite", "TTTT", 300, 260), ("dense", "TFFT", 257, 301),
+                                                   ("hermite", "FTTF", 1024, 64)])
+def test_k6_fused_faces_variant(O, gs, ctx, coefs, combo, cols, rows):
+    """Option k6_fuse: phase A of the sweep evaluates the faces along its lines itself (no faces pass)."""
+    ctx.set_option("k5", 0)
+    ctx.set_option("k6_fuse", 1)
+    try:
+        p = cases.bc_problem(combo, xdir=1, ydir=0, cols=cols, rows=rows, coefs=coefs)
+        r = np.random.default_rng(13)
+        p.grid0 = r.uniform(-15.0, 70.0, p.grid0.shape)
+        p.grid0[:30, :40] = 11.0
+        p.predict0 = p.grid0 + r.uniform(-3.0, 3.0, p.grid0.shape) * (p.grid0 != 11.0)
+        g, o = p.build_gs(gs), p.build_oracle(O, ascending=False)
+        g.set_solver(gs.SOLVER_PARTITIONED)
+        g.iteration(900.0, nsteps=3)
+        for _ in range(3):
+            o.iteration(900.0)
+        O.set_ascending_fold(True)
+        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 3))
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 fused faces {coefs}", tol=tol)
+        assert g.status == 0
+    finally:
+        ctx.set_option("k5", 1)
+        ctx.set_option("k6_fuse", 0)
+
+
 @pytest.mark.parametrize("coefs", ["lines_uneven", "hermite_uneven"])
 def test_k6_tables_outside_the_fast_tier(O, gs, ctx, coefs):
     """Piecewise-linear tables and unevenly spaced knots: every face goes through the second tier or the general walk."""
