@@ -116,6 +116,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "k5")) ctx->opt_k5 = value;
   else if (!strcmp(name, "k5_xstrip")) ctx->opt_k5_xstrip = value;
   else if (!strcmp(name, "k5_cluster")) ctx->opt_k5_cluster = value != 0;
+  else if (!strcmp(name, "k5_nb")) ctx->opt_k5_nb = (int)value;
   else if (!strcmp(name, "k6")) ctx->opt_k6 = value;
   else if (!strcmp(name, "faces1d")) ctx->opt_faces1d = value;
   else if (!strcmp(name, "k6_chunk")) ctx->opt_k6_chunk = value;

@@ -1281,12 +1281,19 @@ static void k5_shape(int n, int *m, int *S) {
   *m = mm;
   *S = (n + mm - 1) / mm;
 }
-static size_t k5_smem(bool xdir, int m, int S, int cs = 1) {
+static size_t k5_smem(bool xdir, int m, int S, int cs = 1, int nb = 2) {
   size_t tile = (size_t)K5_CH * (xdir ? 33 : 32);
   (void)m;
   // clustered strips: the first CTA gathers lambda_e and Q of all cs * S segments (every CTA of the launch is sized alike)
   size_t gather = cs > 1 ? (size_t)2 * S * cs * 32 : 0;
-  return ((size_t)3 * S * 32 + (size_t)S * (2 * tile + 8 * K5_CH) + gather) * sizeof(double);
+  return ((size_t)2 * S * 32 + (size_t)S * nb * (tile + 4 * K5_CH) + gather) * sizeof(double);
+}
+// tile buffers per warp: two.  Three (option k5_nb = 3; lane <-> line sweeps without clusters, where they fit) were
+// MEASURED slower on B200: C3 4096^2 0.236 ms against 0.220 ms, C5 2.01 ms against 1.78 ms -- a second chunk in flight
+// per warp is not what these sweeps lack.
+static int k5_nb(gs_ctx *ctx, bool xdir, int m, int S, int cs) {
+  if (ctx->opt_k5_nb != 3 || xdir || cs > 1) return 2;
+  return k5_smem(xdir, m, S, cs, 3) <= ctx->smem_optin ? 3 : 2;
 }
 // With fewer strips than half the SMs a strip is given to a cluster of 2 / 4 / 8 CTAs (S segments each)
 static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int nlines, int *m, int *S) {
@@ -1344,7 +1351,7 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
   if (kd.valid && kd.time == time && kd.kind_first == g->b[sf].kind && kd.kind_last == g->b[sl].kind &&
       kd.pool_gen == ctx->spline_off.size())
     return GS_OK;
-  kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false> : k5_sweep<false, false>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
+  kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false, 2> : k5_sweep<false, false, 2>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
     GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
@@ -1423,7 +1430,8 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     }
     q.ckpt = g->k5_ckpt;
   }
-  size_t smem = k5_smem(xdir, kd.m, kd.S, kd.cs);
+  const int nb = k5_nb(ctx, xdir, kd.m, kd.S, kd.cs);
+  size_t smem = k5_smem(xdir, kd.m, kd.S, kd.cs, nb);
   int blocks = (q.d.nlines + 31) / 32, threads = 32 * kd.S;
   q.cta_stride = 32;        // y sweep: a CTA owns 32 adjacent columns
   q.pitch = g->cols;
@@ -1441,7 +1449,8 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     q.strip = std::max(24, (q.d.nlines + ctx->sm_count - 1) / ctx->sm_count);
     blocks = (q.d.nlines + q.strip - 1) / q.strip;
   }
-  GS_TRY(k5_launch(xdir ? k5_sweep<true, false> : k5_sweep<false, false>, blocks, threads, smem, ctx->stream, q));
+  GS_TRY(k5_launch(xdir ? k5_sweep<true, false, 2> : (nb == 3 ? k5_sweep<false, false, 3> : k5_sweep<false, false, 2>), blocks, threads,
+                   smem, ctx->stream, q));
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
@@ -1466,7 +1475,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   gs_k5dir &kd = g->k5;
   const int n = g->n;
   if (!(kd.valid && kd.time == time)) {
-    kd.cs = k5_cluster(ctx, k5_sweep<false, true>, false, n, (int)g->nlines, &kd.m, &kd.S);
+    kd.cs = k5_cluster(ctx, k5_sweep<false, true, 2>, false, n, (int)g->nlines, &kd.m, &kd.S);
     if (!kd.tab) {
       GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
       GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
@@ -1508,10 +1517,11 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   q.bc_stride = g->bc_stride;
   q.csize = kd.cs;
   q.status = g->status;
-  size_t smem = k5_smem(false, kd.m, kd.S, kd.cs);
+  const int nb = k5_nb(ctx, false, kd.m, kd.S, kd.cs);
+  size_t smem = k5_smem(false, kd.m, kd.S, kd.cs, nb);
   int blocks = (int)(g->pitch / 32), threads = 32 * kd.S;
   for (int s = 0; s < nsteps; ++s) {
-    GS_TRY(k5_launch(k5_sweep<false, true>, blocks, threads, smem, ctx->stream, q));
+    GS_TRY(k5_launch(nb == 3 ? k5_sweep<false, true, 3> : k5_sweep<false, true, 2>, blocks, threads, smem, ctx->stream, q));
     ctx->launches++;
   }
   GS_CUDA(cudaGetLastError());

@@ -286,7 +286,8 @@ __device__ __forceinline__ void k5_store_x(const K5Params &q, double *dst, int l
   }
 }
 
-template <bool XDIR, bool ONED>
+// NB: tile buffers per warp (chunks c+1 .. c+NB-1 are in flight while chunk c is processed)
+template <bool XDIR, bool ONED, int NB>
 __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   extern __shared__ __align__(16) double k5sm[];
   constexpr int PITCH = K5Tile<XDIR>::PITCH;
@@ -302,11 +303,21 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const int strip_id = blockIdx.x / csz;
   const int line0 = strip_id * q.strip, nl = min(q.strip, d.nlines - line0);
   auto sync_strip = [&]() { if (csz > 1) cluster.sync(); else __syncthreads(); };
-  // shared memory: per CTA lamE[S][32], Q[S][32], E[S][32]; per warp tile[DOUBLES] + ckpt[nch_max][32]
-  double *lamE = k5sm, *Qs = lamE + S * 32, *Es = Qs + S * 32;
-  double *wbase = Es + S * 32 + (size_t)k * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH);
-  double4 *tabs2 = reinterpret_cast<double4 *>(wbase);         // 2 x chunk table entries (coalesced load, LDS broadcast)
-  double *tile2 = wbase + 8 * K5_CH;
+  // shared memory: per CTA lamE[S][32] (overwritten by E: x at the segment ends), Q[S][32]; per warp NB x (chunk table
+  // entries, tile)
+  double *lamE = k5sm, *Qs = lamE + S * 32, *Es = lamE;
+  constexpr int WD = NB * (K5Tile<XDIR>::DOUBLES + 4 * K5_CH);
+  double *wbase = Qs + S * 32 + (size_t)k * WD;
+  double4 *tabs2 = reinterpret_cast<double4 *>(wbase);         // NB x chunk table entries (coalesced load, LDS broadcast)
+  double *tile2 = wbase + NB * 4 * K5_CH;
+  auto tile_of = [&](int c) { return tile2 + (c % NB) * K5Tile<XDIR>::DOUBLES; };
+  auto tabs_of = [&](int c) { return tabs2 + (c % NB) * K5_CH; };
+  // waits until chunk c's copy group has landed: `rem` younger groups may still be in flight
+  auto wait_for = [&](int rem) {
+    if (NB >= 3 && rem >= 2) k5_wait<2>();
+    else if (rem >= 1) k5_wait<1>();
+    else k5_wait<0>();
+  };
   const size_t ck_pitch = (size_t)((d.nlines + 31) / 32) * 32;
   const int s = (crank * S + k) * m, e = min(n, s + m) - 1;
   double *ckpt = q.ckpt + (size_t)(s / K5_CH) * ck_pitch + line0 + lane;   // [chunk * ck_pitch]
@@ -322,19 +333,19 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   auto plain = [&](int i0) { return i0 > 0 && i0 + K5_CH - 1 < e; };
   // ---- phase A ----  (chunk c+1 is in flight while chunk c is processed)
   double lam = 0.0, Qacc = 0.0;
-  if (nch > 0) k5_load<XDIR>(q, q.rhs, line0, nl, s, min(K5_CH, e - s + 1), tile2, tabs2, lane);
+  for (int c = 0; c < min(NB - 1, nch); ++c) {
+    const int i1 = s + c * K5_CH;
+    k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile_of(c), tabs_of(c), lane);
+  }
   for (int c = 0; c < nch; ++c) {
     const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
-    double *tile = tile2 + (c & 1) * K5Tile<XDIR>::DOUBLES;
-    const double4 *t = tabs2 + (c & 1) * K5_CH;
-    if (c + 1 < nch) {
-      const int i1 = i0 + K5_CH;
-      k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile2 + ((c + 1) & 1) * K5Tile<XDIR>::DOUBLES,
-                    tabs2 + ((c + 1) & 1) * K5_CH, lane);
-      k5_wait<1>();
-    } else {
-      k5_wait<0>();
+    double *tile = tile_of(c);
+    const double4 *t = tabs_of(c);
+    if (c + NB - 1 < nch) {
+      const int i1 = i0 + (NB - 1) * K5_CH;
+      k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile_of(c + NB - 1), tabs_of(c + NB - 1), lane);
     }
+    wait_for(min(NB - 1, nch - 1 - c));
     __syncwarp();
     if (plain(i0)) {
 #pragma unroll
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   }
   // segment results go where the reduced system is solved: this CTA's arrays, or -- clustered strips -- the first
   // CTA's [ST][32] gather arrays through distributed shared memory (posted remote stores; the solver then reads locally)
-  double *allLam = k5sm + 3 * S * 32 + (size_t)S * (2 * K5Tile<XDIR>::DOUBLES + 8 * K5_CH), *allQ = allLam + ST * 32;
+  double *allLam = k5sm + 2 * S * 32 + (size_t)S * WD, *allQ = allLam + ST * 32;
   if (csz > 1) {
     const int kg = crank * S + k;
     cluster.map_shared_rank(allLam, 0)[kg * 32 + lane] = lam;
@@ -396,24 +407,20 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
   const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : Qs[lane];
   double x = Es[k * 32 + lane];   // x_e
   unsigned bad = 0;
-  {
-    const int il = s + (nch - 1) * K5_CH;
-    k5_load<XDIR>(q, q.rhs, line0, nl, il, min(K5_CH, e - il + 1), tile2 + ((nch - 1) & 1) * K5Tile<XDIR>::DOUBLES,
-                  tabs2 + ((nch - 1) & 1) * K5_CH, lane);
+  for (int c = nch - 1; c >= max(0, nch - (NB - 1)); --c) {
+    const int i1 = s + c * K5_CH;
+    k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile_of(c), tabs_of(c), lane);
   }
   double ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : 0.0;   // checkpoint before the last chunk
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
-    double *tile = tile2 + (c & 1) * K5Tile<XDIR>::DOUBLES;
-    const double4 *t = tabs2 + (c & 1) * K5_CH;
-    if (c > 0) {
-      const int i1 = i0 - K5_CH;
-      k5_load<XDIR>(q, q.rhs, line0, nl, i1, K5_CH, tile2 + ((c - 1) & 1) * K5Tile<XDIR>::DOUBLES,
-                    tabs2 + ((c - 1) & 1) * K5_CH, lane);
-      k5_wait<1>();
-    } else {
-      k5_wait<0>();
+    double *tile = tile_of(c);
+    const double4 *t = tabs_of(c);
+    if (c - (NB - 1) >= 0) {
+      const int i1 = i0 - (NB - 1) * K5_CH;
+      k5_load<XDIR>(q, q.rhs, line0, nl, i1, K5_CH, tile_of(c - (NB - 1)), tabs_of(c - (NB - 1)), lane);
     }
+    wait_for(min(NB - 1, c));
     __syncwarp();
     // lambda at the start of the chunk: phase A's checkpoint plus the left-neighbour term omega * L
     double lm = (c > 0) ? ck_next + d.omega_end[(i0 - 1) / K5_CH] * L : L;

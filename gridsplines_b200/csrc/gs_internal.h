@@ -62,6 +62,7 @@ struct gs_ctx {
   int64_t opt_hoist_ck = 1;
   int64_t opt_k5 = 1;
   int64_t opt_k5_xstrip = 0;   // 0 = automatic
+  int opt_k5_nb = 2;           // K5: tile buffers per warp (3: triple buffer where it fits; measured slower)
   int opt_k5_cluster = 1;      // K5: clusters of 2 / 4 / 8 CTAs per strip when strips alone would not fill the chip
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)

@@ -472,6 +472,21 @@ def test_k5_clustered_strips(O, gs, ctx, cols, rows, combo):
         ctx.set_option("k5_cluster", 1)
 
 
+def test_k5_triple_buffer_variant(O, gs, ctx):
+    """Option k5_nb = 3: three tile buffers per warp on the y sweep (measured slower, kept as a tested variant)."""
+    ctx.set_option("k5_nb", 3)
+    try:
+        p = cases.bc_problem("TTFF", xdir=0, ydir=0, cols=200, rows=1500, coefs="const")
+        g, o = p.build_gs(gs), p.build_oracle(O)
+        g.set_solver(gs.SOLVER_PARTITIONED)
+        g.iteration(900.0, nsteps=2)
+        for _ in range(2):
+            o.iteration(900.0)
+        _compare_tol(cases.snapshot(g), cases.snapshot(o), "K5 triple buffer")
+    finally:
+        ctx.set_option("k5_nb", 2)
+
+
 def test_k5_tables_follow_coefficient_and_bound_changes(O, gs):
     """K5 caches its line-independent tables per (grid, direction, time step): changing the coefficients, the time
     step or a bound's kind must rebuild them."""
