@@ -412,6 +412,8 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
     k5_load<XDIR>(q, q.rhs, line0, nl, i1, min(K5_CH, e - i1 + 1), tile_of(c), tabs_of(c), lane);
   }
   double ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : 0.0;   // checkpoint before the last chunk
+  double ga[8];             // y sweeps: old grid values of a chunk's upper half, requested a chunk ahead
+  bool ga_ready = false;
   for (int c = nch - 1; c >= 0; --c) {
     const int i0 = s + c * K5_CH, len = min(K5_CH, e - i0 + 1);
     double *tile = tile_of(c);
@@ -460,12 +462,16 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
       const size_t off = (size_t)strip_id * q.cta_stride + (size_t)i0 * q.pitch + lane;
       double *G = q.grid_io + off, *P = q.predict_out + off;
       if (pl) {
-        // old grid values of the upper half are requested before the recomputation, those of the lower half before
-        // the upper half's back-substitution: their latency hides behind arithmetic
-        double ga[8], gb[8];
+        // old grid values (Grid.update): the upper half's were requested one chunk ago (after the previous chunk's
+        // upper half), the lower half's are requested before the recomputation -- their latency hides behind arithmetic
+        double gb[8];
         if (act) {
+          if (!ga_ready) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) ga[u] = G[(size_t)(8 + u) * q.pitch];
+            for (int u = 0; u < 8; ++u) ga[u] = G[(size_t)(8 + u) * q.pitch];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) gb[u] = G[(size_t)u * q.pitch];
         }
 #pragma unroll
         for (int j = 0; j < K5_CH; ++j) {
@@ -475,8 +481,6 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
         }
         if (act) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) gb[u] = G[(size_t)u * q.pitch];
-#pragma unroll
           for (int u = 7; u >= 0; --u) {
             const int j = 8 + u;
             x = fma(t[j].z, x, tile[j * PITCH + lane]);
@@ -484,6 +488,13 @@ __global__ void __launch_bounds__(512) k5_sweep(K5Params q) {
             if (ONED) P[(size_t)j * q.pitch] = x + dl / 3.0;                            // arraygrid.aVal :85-87
             else P[(size_t)j * q.pitch] = (fabs(dl) > 1.5) ? x : x + dl / 2.0;           // Grid.update :474-481, aVal :508-512
             G[(size_t)j * q.pitch] = x;
+          }
+          // the next (= previous on the line) chunk's upper half, if that chunk will take this path too
+          ga_ready = c > 0 && plain(i0 - K5_CH);
+          if (ga_ready) {
+            const double *Gn = G - (size_t)K5_CH * q.pitch;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ga[u] = Gn[(size_t)(8 + u) * q.pitch];
           }
 #pragma unroll
           for (int u = 7; u >= 0; --u) {
