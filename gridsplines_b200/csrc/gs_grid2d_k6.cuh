@@ -142,12 +142,12 @@ __device__ __noinline__ double k6_face_general(const double *pool, int off, doub
 }
 
 // Interior faces F[i], 1 <= i <= n - 2, of every line.  TAB (table-driven maps, pool staged in shared memory): every
-// warp walks (row, 64-column group) tiles  t = warp + k * nwarps  in row-major order (two faces per lane and tile), the
+// warp walks (row, 128-column group) tiles  t = warp + k * nwarps  in row-major order (four faces per lane and tile), the
 // column group rotated by the row so that no warp keeps the same columns (a boundary layer along one edge makes those
 // columns' faces take the slower tiers); the next tile's loads are in flight during a tile's arithmetic.  Otherwise (literal constants, oversized pools): blocks
 // of 256 columns x a stride of rows with the generic evaluation.
 template <bool XDIR, class SEL, bool TAB>
-__global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
+__global__ void __launch_bounds__(256, 3) k6_faces(K6FacesParams q) {
   extern __shared__ double k6sm[];
   const Sweep2dParams &p = q.sw;
   // an open first end has no boundary row: face 0 is an ordinary interior face
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, 4) k6_faces(K6FacesParams q) {
     for (int i = threadIdx.x; i < p.pool_len; i += blockDim.x) k6sm[i] = p.pool[i];
     __syncthreads();
     constexpr bool single = SEL::single;
-    constexpr int U = 2;                         // faces per lane per tile: a tile is one row x 32 * U columns
+    constexpr int U = 4;                         // faces per lane per tile: a tile is one row x 32 * U columns
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int ncg = (p.cols + 32 * U - 1) / (32 * U), nrows = r_hi - r_lo;
