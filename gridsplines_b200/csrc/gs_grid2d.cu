@@ -1529,7 +1529,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
 }
 
 // ---- K6: faces kernel + elimination sweeps for temperature-dependent tables --------------------------------
-static int k6_chunk(gs_ctx *ctx) { return ctx->opt_k6_chunk == 16 ? 16 : 8; }
+static int k6_chunk(gs_ctx *) { return 8; }   // nodes per chunk: 16 warps per CTA (16-node chunks / 8 warps measured slower)
 static void k6_shape(gs_ctx *ctx, int n, int *m, int *S) {
   const int ch = k6_chunk(ctx);
   int s = std::max(2, std::min(ch == 16 ? 8 : 16, n / 64));
@@ -1679,15 +1679,13 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   size_t smem = k6_smem(ctx, xdir, q.S, ff, p.pool_len);
   int blocks = (nlines + 31) / 32, threads = 32 * q.S;
   void (*kern)(K6Params);
-  const bool ch16 = k6_chunk(ctx) == 16;
   if (ff) {
     if (mode == K6_BEGIN) kern = k6_sweep<false, 8, K6_BEGIN, true>;
     else if (mode == K6_END) kern = k6_sweep<false, 8, K6_END, true>;
     else kern = xdir ? k6_sweep<true, 8, K6_FUSED, true> : k6_sweep<false, 8, K6_FUSED, true>;
-  } else if (mode == K6_BEGIN) kern = ch16 ? k6_sweep<false, 16, K6_BEGIN, false> : k6_sweep<false, 8, K6_BEGIN, false>;
-  else if (mode == K6_END) kern = ch16 ? k6_sweep<false, 16, K6_END, false> : k6_sweep<false, 8, K6_END, false>;
-  else kern = ch16 ? (xdir ? k6_sweep<true, 16, K6_FUSED, false> : k6_sweep<false, 16, K6_FUSED, false>)
-                   : (xdir ? k6_sweep<true, 8, K6_FUSED, false> : k6_sweep<false, 8, K6_FUSED, false>);
+  } else if (mode == K6_BEGIN) kern = k6_sweep<false, 8, K6_BEGIN, false>;
+  else if (mode == K6_END) kern = k6_sweep<false, 8, K6_END, false>;
+  else kern = xdir ? k6_sweep<true, 8, K6_FUSED, false> : k6_sweep<false, 8, K6_FUSED, false>;
   GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     cudaLaunchConfig_t cfg = {};
