@@ -811,6 +811,7 @@ __global__ void __launch_bounds__(128, 5) k_part_C(PartParams q) {
 }
 
 #include "gs_grid2d_k6.cuh"
+#include "gs_grid2d_k7.cuh"
 
 // ---------------------------------------------------------------------------------
 // small kernels: Grid.update, edges, reductions
@@ -942,6 +943,7 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
   cudaFree(g->k6_ends);
   cudaFree(g->k6_ckpt);
   cudaFree(g->k6_split);
+  cudaFree(g->k7_scratch);
   for (gs_k5dir *kd : {&g->k5x, &g->k5y}) {
     cudaFree(kd->tab);
     cudaFree(kd->omega_end);
@@ -1582,22 +1584,16 @@ struct K6Split {
   int nranks, rank;
 };
 
-static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split = nullptr) {
+// 1. faces + end rows of a direction (reads predict, rhs; every spline evaluation of the sweep happens here).  Shared by
+// K6 (tolerance solver) and K7 (exact solver).  `skip_faces`: the sweep evaluates the interior faces itself (k6_fuse).
+static int launch_faces(gs_grid2d *g, double time, bool xdir, const K6Split *split, K6FacesParams &fq, bool *ff_out) {
   gs_ctx *ctx = g->ctx;
-  GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
-  GS_TRY(gs_ctx_sync_pool(ctx));
   const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
   const size_t cells = (size_t)g->cols * g->rows;
   if (!g->k6_F) GS_CUDA(cudaMalloc(&g->k6_F, cells * sizeof(double)));
   const size_t ends_need = 6 * (size_t)std::max(g->cols, g->rows);
   if (!g->k6_ends) GS_CUDA(cudaMalloc(&g->k6_ends, ends_need * sizeof(double)));
-  const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / 8 + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
-  if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
   const int mode = split ? split->mode : K6_FUSED;
-  const size_t nl_pad = ((size_t)nlines + 31) / 32 * 32;
-  if (split && !g->k6_split) GS_CUDA(cudaMalloc(&g->k6_split, (nl_pad + 64 * 3 * nl_pad) * sizeof(double)));
-  // 1. faces + end rows of this direction (reads predict, rhs; every spline evaluation of the sweep happens here)
-  K6FacesParams fq;
   bool single;
   fill_common(g, fq.sw, time, single);
   Sweep2dParams &p = fq.sw;
@@ -1625,21 +1621,24 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   const bool tab = !lit && p.smem_pool;
   const int eblocks = (nlines + 127) / 128;   // (one warp per CTA measured slower: every CTA stages the pool)
   // fused faces: the sweep evaluates the interior faces itself (phase A), only the end rows need their own kernel
-  const bool ff = tab && ctx->opt_k6_fuse && k6_chunk(ctx) == 8;
-  {
+  const bool ff = ff_out && tab && ctx->opt_k6_fuse && k6_chunk(ctx) == 8;
+  if (ff_out) *ff_out = ff;
+  if (ff) {
     int m_, S_;
     k6_shape(ctx, n, &m_, &S_);
-    GS_REQUIRE(!ff || k6_smem(ctx, xdir, S_, true, p.pool_len) <= ctx->smem_optin, "K6 shared memory");
+    GS_REQUIRE(k6_smem(ctx, xdir, S_, true, p.pool_len) <= ctx->smem_optin, "K6 shared memory");
   }
 #define GS_FACES(XD, SG, TB)                                        \
   do {                                                              \
     k6_ends<XD, SG><<<eblocks, 128, pool_smem, ctx->stream>>>(fq);  \
+    ctx->launches++;                                                \
     if (ff) break;                                                  \
     int resident = 0;                                               \
     GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k6_faces<XD, SG, TB>, 256, pool_smem)); \
     dim3 fblocks(fbx, std::max(1, std::min(g->rows, ctx->sm_count * std::max(resident, 1) / fbx)));          \
     if (TB) fblocks = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(resident, 1), (cells / 32 + 7) / 8)), 1); \
     k6_faces<XD, SG, TB><<<fblocks, 256, pool_smem, ctx->stream>>>(fq); \
+    ctx->launches++;                                                \
   } while (0)
   if (mode == K6_END) {
     // the faces and end rows of the begin call are still in place
@@ -1655,6 +1654,25 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
     else GS_FACES(false, CoefSel<false>, false);
   }
 #undef GS_FACES
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
+static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split = nullptr) {
+  gs_ctx *ctx = g->ctx;
+  GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
+  GS_TRY(gs_ctx_sync_pool(ctx));
+  const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
+  const size_t ck_need = ((size_t)std::max(g->cols, g->rows) / 8 + 2) * (((size_t)std::max(g->cols, g->rows) + 31) / 32 * 32);
+  if (!g->k6_ckpt) GS_CUDA(cudaMalloc(&g->k6_ckpt, ck_need * sizeof(double4)));
+  const int mode = split ? split->mode : K6_FUSED;
+  const size_t nl_pad = ((size_t)nlines + 31) / 32 * 32;
+  if (split && !g->k6_split) GS_CUDA(cudaMalloc(&g->k6_split, (nl_pad + 64 * 3 * nl_pad) * sizeof(double)));
+  K6FacesParams fq;
+  bool ff = false;
+  GS_TRY(launch_faces(g, time, xdir, split, fq, &ff));
+  Sweep2dParams &p = fq.sw;
+  const gs_dim2d &d = xdir ? g->x : g->y;
   // 2. elimination sweep
   K6Params q;
   q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
@@ -1700,7 +1718,57 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
     cfg.numAttrs = 1;
     GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
   }
-  ctx->launches += mode == K6_END ? 1 : (ff ? 2 : 3);
+  ctx->launches++;
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
+// ---- K7: exact sweeps (faces pass + one thread per line in the reference's order) -----------------------------
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool use_k7(gs_grid2d *g, bool xdir) {
+  gs_ctx *ctx = g->ctx;
+  if (!ctx->opt_k7 || g->solver == GS_SOLVER_PARTITIONED) return false;
+  const int n = xdir ? g->cols : g->rows;
+  // bulk copies move 16-byte units: row pieces must start and end on even columns
+  if (n < 4 || (g->cols & 1)) return false;
+  return aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
+}
+static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
+  gs_ctx *ctx = g->ctx;
+  GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
+  GS_TRY(gs_ctx_sync_pool(ctx));
+  const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
+  const int strips = (nlines + 31) / 32;
+  const size_t need = (size_t)strips * 32 * (size_t)n;
+  if (g->k7_scratch_elems < need) {
+    GS_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(g->k7_scratch);
+    g->k7_scratch = nullptr;
+    g->k7_scratch_elems = 0;
+    const size_t want = (size_t)((std::max(g->cols, g->rows) + 31) / 32) * 32 * (size_t)std::max(g->cols, g->rows);
+    const size_t both = (size_t)((g->rows + 31) / 32) * 32 * (size_t)g->cols;
+    const size_t both2 = (size_t)((g->cols + 31) / 32) * 32 * (size_t)g->rows;
+    const size_t elems = std::max(need, std::min(want, std::max(both, both2)));
+    GS_CUDA(cudaMalloc(&g->k7_scratch, elems * sizeof(double2)));
+    g->k7_scratch_elems = elems;
+  }
+  K6FacesParams fq;
+  GS_TRY(launch_faces(g, time, xdir, nullptr, fq, nullptr));
+  K7Params q;
+  q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
+  q.coefs = (xdir ? g->x : g->y).coefs;
+  q.F = fq.F; q.first3 = fq.first3; q.last3 = fq.last3;
+  q.rhs = fq.sw.rhs;
+  q.out = g->result;
+  q.grid_io = g->grid;
+  q.predict_out = g->predict;
+  q.scratch = g->k7_scratch;
+  q.time = time;
+  q.status = g->status;
+  if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
+  else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
+  else k7_sweep<false, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
+  ctx->launches++;
   GS_CUDA(cudaGetLastError());
   return GS_OK;
 }
@@ -1708,12 +1776,14 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
 static int sweep_x(gs_grid2d *g, double time) {
   if (use_k5(g, true)) return launch_k5(g, time, true);
   if (use_k6(g, true)) return launch_k6(g, time, true);
-  return use_partitioned(g, g->cols) ? launch_part(g, time, true, false) : launch_xsweep(g, time);
+  if (use_partitioned(g, g->cols)) return launch_part(g, time, true, false);
+  return use_k7(g, true) ? launch_k7(g, time, true, false) : launch_xsweep(g, time);
 }
 static int sweep_y(gs_grid2d *g, double time, bool fuse) {
   if (fuse && use_k5(g, false)) return launch_k5(g, time, false);   // K5's / K6's y sweeps are always fused with Grid.update
   if (fuse && use_k6(g, false)) return launch_k6(g, time, false);
-  return use_partitioned(g, g->rows) ? launch_part(g, time, false, fuse) : launch_ysweep(g, time, fuse);
+  if (use_partitioned(g, g->rows)) return launch_part(g, time, false, fuse);
+  return use_k7(g, false) ? launch_k7(g, time, false, fuse) : launch_ysweep(g, time, fuse);
 }
 
 extern "C" int gs_grid2d_xiter(gs_grid2d *g, double time) {

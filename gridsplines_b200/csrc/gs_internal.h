@@ -69,6 +69,7 @@ struct gs_ctx {
   int64_t opt_k6_chunk = 8;
   int opt_k6_fuse = 0;          // K6: the sweep evaluates the faces along its lines itself (no separate faces pass); measured slower, off
   int opt_k6_cluster = 1;       // K6: give a strip to a cluster of 2 / 4 CTAs when strips alone would not fill the chip
+  int64_t opt_k7 = 1;           // K7: exact sweeps from precomputed faces (0: first-draft k_xsweep / k_ysweep)
   int64_t opt_host_chunk_mb = 64;
   int64_t opt_ck_block = 16;
 };
@@ -157,6 +158,8 @@ struct gs_grid2d {
   double *k6_F = nullptr, *k6_ends = nullptr;   // K6: face values, end rows
   double4 *k6_ckpt = nullptr;
   double *k6_split = nullptr;                    // split y sweep: fm1 [nlines] + cdw [S][3][nlines padded]
+  double2 *k7_scratch = nullptr;                 // K7: (delta, lambda) [strips][n][32]
+  size_t k7_scratch_elems = 0;
   bool k6_split_open = false;                    // a begin call is waiting for its end call
   unsigned *status = nullptr;
   int solver = GS_SOLVER_AUTO;
