@@ -14,6 +14,7 @@
 //       padded 33-column tiles = conflict-free transposed reads); results leave through the same
 //       transposed tiles.
 // Both keep the reference's operation order exactly (GS_SOLVER_THOMAS, bit-exact).
+#include <cuda.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -1733,6 +1734,40 @@ static bool use_k7(gs_grid2d *g, bool xdir) {
   if (n < 4 || (g->cols & 1)) return false;
   return aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
 }
+// tensor map of a row-major rows x cols array of doubles with K7's box: x sweep 16 columns x 32 rows, 128-byte swizzle
+// (the transposing tile); y sweep 32 columns x 16 rows.  cuTensorMapEncodeTiled is a driver entry point: fetched through
+// the runtime, libcuda is not linked.
+typedef CUresult (*gs_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static_assert(sizeof(CUtensorMap) == sizeof(K7Map), "CUtensorMap is a 128-byte blob");
+static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox) {
+  static gs_tmap_encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      gs_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return GS_ERR_CUDA;
+    }
+    encode = reinterpret_cast<gs_tmap_encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(double)};
+  const cuuint32_t box[2] = {xbox ? 16u : 32u, xbox ? 32u : 16u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base),
+                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       xbox ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    gs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%d x %d)", (int)rc, rows, cols);
+    return GS_ERR_CUDA;
+  }
+  return GS_OK;
+}
+
 static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   gs_ctx *ctx = g->ctx;
   GS_REQUIRE(!ctx->spline_off.empty(), "no spline has been created in this context");
@@ -1745,10 +1780,9 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     cudaFree(g->k7_scratch);
     g->k7_scratch = nullptr;
     g->k7_scratch_elems = 0;
-    const size_t want = (size_t)((std::max(g->cols, g->rows) + 31) / 32) * 32 * (size_t)std::max(g->cols, g->rows);
-    const size_t both = (size_t)((g->rows + 31) / 32) * 32 * (size_t)g->cols;
-    const size_t both2 = (size_t)((g->cols + 31) / 32) * 32 * (size_t)g->rows;
-    const size_t elems = std::max(need, std::min(want, std::max(both, both2)));
+    // enough for either direction
+    const size_t ex = (size_t)((g->rows + 31) / 32) * 32 * (size_t)g->cols, ey = (size_t)((g->cols + 31) / 32) * 32 * (size_t)g->rows;
+    const size_t elems = std::max(ex, ey);
     GS_CUDA(cudaMalloc(&g->k7_scratch, elems * sizeof(double2)));
     g->k7_scratch_elems = elems;
   }
@@ -1757,17 +1791,21 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   K7Params q;
   q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
   q.coefs = (xdir ? g->x : g->y).coefs;
-  q.F = fq.F; q.first3 = fq.first3; q.last3 = fq.last3;
-  q.rhs = fq.sw.rhs;
+  q.first3 = fq.first3; q.last3 = fq.last3;
   q.out = g->result;
   q.grid_io = g->grid;
   q.predict_out = g->predict;
   q.scratch = g->k7_scratch;
   q.time = time;
   q.status = g->status;
-  if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
-  else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
-  else k7_sweep<false, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q);
+  K7Maps tm;
+  GS_TRY(k7_encode(&tm.F, fq.F, g->cols, g->rows, xdir));
+  GS_TRY(k7_encode(&tm.rhs, fq.sw.rhs, g->cols, g->rows, xdir));
+  GS_TRY(k7_encode(&tm.gold, g->grid, g->cols, g->rows, xdir));
+  GS_TRY(k7_encode(&tm.out, g->result, g->cols, g->rows, xdir));
+  if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
+  else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
+  else k7_sweep<false, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
   return GS_OK;

@@ -9,14 +9,18 @@
 //   * k7_sweep then runs ONE THREAD PER LINE in the reference's operation order -- per node the very operations of
 //     Dim.general + forwardUnit, with the shared-reciprocal division of gs_device.cuh (correctly rounded: same bits
 //     as `/`; a warp whose operands leave the fast divider's range repeats its lines with native division) --
-//     fed by a per-warp ring of cp.async.bulk stages guarded by mbarriers:
-//        forward : stage = 16 nodes x 32 lines of (F, rhs) + the nodes' (cf0, cf1);  (delta, lambda) = toPassion
-//                  goes to a blocked scratch array [strip][node][lane] (512 B contiguous per node and warp);
-//        backward: stage = 16 nodes of (delta, lambda) (ONE 8 KB bulk copy) + (fused y sweep) the old grid rows;
-//                  x_i = delta_i * x_{i+1} + lambda_i, Grid.update (:474-481) applied on the way out (y), results
-//                  of the x sweep leave through transposed shared-memory tiles and per-row bulk stores.
-//   y sweep: lane <-> column (a node row of the strip is one 256 B segment);  x sweep: lane <-> row, a stage holds a
-//   32 x 16 tile whose rows arrive as one 128 B bulk copy each (pitch 144 B: conflict-free 16-byte reads).
+//     fed by a per-warp ring of TMA stages guarded by mbarriers.  Every tile is ONE tensor-map instruction
+//     (cp.async.bulk.tensor.2d, UTMALDG / UTMASTG) issued by lane 0:
+//        forward : stage = a 16-node x 32-line box of F and of the right-hand side + the nodes' (cf0, cf1);
+//                  (delta, lambda) = toPassion goes to a blocked scratch array [strip][node][lane] (512 B contiguous
+//                  per node and warp);
+//        backward: stage = 16 nodes of (delta, lambda) (one 8 KB bulk copy) + (fused y sweep) the box of old grid
+//                  values; x_i = delta_i * x_{i+1} + lambda_i, Grid.update (:474-481) applied on the way out (y);
+//                  the x sweep's results leave as one box store per chunk.
+//   y sweep: lane <-> column, box = 32 columns x 16 rows (a node row of the strip is 256 contiguous bytes);
+//   x sweep: lane <-> row, box = 16 columns x 32 rows -- the TMA/shared-memory tiled transpose: the box lands with
+//            the 128-byte swizzle, so a lane reads its own row 16 bytes at a time without bank conflicts.
+//   Boxes that stick out of the array (last strip, last chunk) are zero-filled on load and clipped on store.
 // One warp per CTA (46 KB of shared memory): 4096 lines = 128 CTAs, 16384 lines = 512 CTAs, all resident at once.
 //
 // Cost model (B200): the dependent chain of a node is a*delta, +diag, reciprocal (MUFU + 5 DFMA), quotient (3 DFMA)
@@ -29,18 +33,25 @@
 
 #define K7_CH 16                         // nodes per stage
 #define K7_NS 3                          // ring depth
-#define K7_XP 18                         // x tiles: doubles per row (16 + 2: 144 B pitch, 16 B aligned)
-#define K7_STAGE 12288                   // bytes per stage = max(forward, backward) footprint
-#define K7_OUT (32 * K7_XP * 8)          // one transposed output tile of the x sweep
-#define K7_SMEM (128 + K7_NS * K7_STAGE + 2 * K7_OUT)
+#define K7_TILE 4096                     // one box: 16 x 32 doubles
+#define K7_STAGE 12288                   // bytes per stage = max(forward 2 tiles + cf, backward 8 KB + tile)
+#define K7_SMEM (1024 + 1024 + K7_NS * K7_STAGE + 2 * K7_TILE)   // alignment slack + barriers + stages + output tiles
+
+// CUtensorMap is an opaque 128-byte, 64-byte aligned blob (cuda.h); kept as bytes here so that device code does not
+// need the driver header
+struct __align__(64) K7Map {
+  unsigned char b[128];
+};
+struct K7Maps {
+  K7Map F, rhs, gold, out;   // boxes of k6_F, the right-hand side, the old grid (fused y) and the result (x)
+};
 
 struct K7Params {
   int n, nlines, cols, rows;
   const double *coefs;             // Dim.coefs [2n]
-  const double *F, *first3, *last3;   // k6_faces / k6_ends
-  const double *rhs;               // x: grid, y: result
-  double *out;                     // x, unfused y: result
-  double *grid_io;                 // fused y: old grid in / new grid out
+  const double *first3, *last3;    // k6_ends
+  double *out;                     // unfused y: result
+  double *grid_io;                 // fused y: new grid out
   double *predict_out;             // fused y: new predict
   double2 *scratch;                // [strips][n][32] (delta, lambda)
   double time;
@@ -57,56 +68,45 @@ struct K7Ring {
   int tail;      // stage of the next chunk to be issued
 };
 GS_DEV unsigned char *k7_stage(const K7Ring &r, int s) { return r.stages + (size_t)s * K7_STAGE; }
-GS_DEV void k7_wait(K7Ring &r) {
-  gs_mbar_wait(&r.bars[r.head], (r.phase >> r.head) & 1u);
+GS_DEV void k7_wait(K7Ring &r, unsigned *status) {
+  gs_mbar_wait_bounded(&r.bars[r.head], (r.phase >> r.head) & 1u, status);
   r.phase ^= 1u << r.head;
 }
 GS_DEV void k7_advance(int &s) { s = (s == K7_NS - 1) ? 0 : s + 1; }
 
-// forward stage layout:  y: F [16][32] | rhs [16][32] | cf [16][2];   x: F [32][18] | rhs [32][18] | cf [16][2]
-template <bool XDIR>
-struct K7Fwd {
-  static constexpr int kTile = XDIR ? 32 * K7_XP * 8 : K7_CH * 256;
-  static constexpr int kCf = 2 * kTile;
-};
+// element (row r, column j) of a 32 x 16 box that landed with CU_TENSOR_MAP_SWIZZLE_128B (tile base 1024 B aligned):
+// the 16-byte unit index j / 2 is XORed with r % 8
+GS_DEV int k7_swz(int r, int j) { return r * 128 + ((((j >> 1) ^ (r & 7)) << 4) | ((j & 1) << 3)); }
 
+// forward stage layout:  F tile | rhs tile | cf [16][2]
+//   y: tile = [16 nodes][32 lines];   x: tile = [32 lines][16 nodes], swizzled
 template <bool XDIR>
-GS_DEV void k7_issue_fwd(const K7Params &q, K7Ring &r, int c, int line0, int nl, int lane) {
-  const int i0 = c * K7_CH, len = min(K7_CH, q.n - i0);
-  unsigned char *st = k7_stage(r, r.tail);
-  uint64_t *bar = &r.bars[r.tail];
-  if (lane == 0) gs_mbar_expect_tx(bar, (uint32_t)(2 * nl * len * 8 + len * 16));
-  __syncwarp();
-  if (XDIR) {
-    if (lane < nl) {
-      const size_t g = (size_t)(line0 + lane) * q.cols + i0;
-      gs_bulk_g2s(st + lane * (K7_XP * 8), q.F + g, (uint32_t)len * 8u, bar);
-      gs_bulk_g2s(st + K7Fwd<true>::kTile + lane * (K7_XP * 8), q.rhs + g, (uint32_t)len * 8u, bar);
-    }
-  } else {
-    const int j = lane & (K7_CH - 1);
-    if (j < len) {
-      const size_t g = (size_t)(i0 + j) * q.cols + line0;
-      if (lane < K7_CH) gs_bulk_g2s(st + j * 256, q.F + g, (uint32_t)nl * 8u, bar);
-      else gs_bulk_g2s(st + K7Fwd<false>::kTile + j * 256, q.rhs + g, (uint32_t)nl * 8u, bar);
-    }
+GS_DEV void k7_issue_fwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, int line0, int lane) {
+  if (lane == 0) {
+    const int i0 = c * K7_CH, len = min(K7_CH, q.n - i0);
+    unsigned char *st = k7_stage(r, r.tail);
+    uint64_t *bar = &r.bars[r.tail];
+    gs_mbar_expect_tx(bar, (uint32_t)(2 * K7_TILE + len * 16));
+    const int c0 = XDIR ? i0 : line0, c1 = XDIR ? line0 : i0;
+    gs_tma_load_2d(st, &tm.F, c0, c1, bar);
+    gs_tma_load_2d(st + K7_TILE, &tm.rhs, c0, c1, bar);
+    gs_bulk_g2s(st + 2 * K7_TILE, q.coefs + 2 * (size_t)i0, (uint32_t)len * 16u, bar);
   }
-  if (lane == 0) gs_bulk_g2s(st + K7Fwd<XDIR>::kCf, q.coefs + 2 * (size_t)i0, (uint32_t)len * 16u, bar);
   k7_advance(r.tail);
 }
 
 // The forward walk of one line (lane) over all chunks; toPassion -> scratch.  Returns the sticky range predicate of
 // the shared-reciprocal division (always true when !FAST).
 template <bool XDIR, bool FAST>
-GS_DEV bool k7_forward(const K7Params &q, K7Ring &r, int line0, int nl, int lane, int rl, GsRcp rt,
-                                        double inv_time, double2 *sc, unsigned &flags) {
+GS_DEV bool k7_forward(const K7Params &q, const K7Maps &tm, K7Ring &r, int line0, int lane, int rl, GsRcp rt,
+                       double inv_time, double2 *sc, unsigned &flags) {
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
   const size_t line = (size_t)(line0 + rl);
   const double f_diag = q.first3[3 * line], f_sup = q.first3[3 * line + 1], f_rhs = q.first3[3 * line + 2];
   const double l_sub = q.last3[3 * line], l_diag = q.last3[3 * line + 1], l_rhs = q.last3[3 * line + 2];
   bool ok = true;
   double delta = 0.0, lambda = 0.0, fprev = 0.0;
-  for (int c = 0; c < min(K7_NS, NC); ++c) k7_issue_fwd<XDIR>(q, r, c, line0, nl, lane);
+  for (int c = 0; c < min(K7_NS, NC); ++c) k7_issue_fwd<XDIR>(q, tm, r, c, line0, lane);
   // Dim.general :67-83 + forwardUnit :257-265 of an interior node
   auto node_mid = [&](double t, double F, double cf0, double cf1) {
     const double a = cf0 * fprev;
@@ -118,18 +118,19 @@ GS_DEV bool k7_forward(const K7Params &q, K7Ring &r, int line0, int nl, int lane
 #pragma unroll 1
   for (int c = 0; c < NC; ++c) {
     const int i0 = c * K7_CH, len = min(K7_CH, n - i0);
-    k7_wait(r);
+    k7_wait(r, q.status);
     const unsigned char *st = k7_stage(r, r.head);
-    const double2 *cf = reinterpret_cast<const double2 *>(st + K7Fwd<XDIR>::kCf);
+    const double2 *cf = reinterpret_cast<const double2 *>(st + 2 * K7_TILE);
     double2 *so = sc + (size_t)i0 * 32 + lane;
     if (c != 0 && i0 + K7_CH < n) {
       // a full chunk holding neither node 0 nor node n - 1
       if (XDIR) {
-        const double2 *rF = reinterpret_cast<const double2 *>(st + rl * (K7_XP * 8));
-        const double2 *rT = reinterpret_cast<const double2 *>(st + K7Fwd<true>::kTile + rl * (K7_XP * 8));
+        const unsigned char *rF = st + rl * 128, *rT = st + K7_TILE + rl * 128;
+        const int sw = rl & 7;
 #pragma unroll
         for (int j = 0; j < K7_CH; j += 2) {
-          const double2 f2 = rF[j >> 1], t2 = rT[j >> 1];
+          const int u = ((j >> 1) ^ sw) << 4;
+          const double2 f2 = *reinterpret_cast<const double2 *>(rF + u), t2 = *reinterpret_cast<const double2 *>(rT + u);
           node_mid(t2.x, f2.x, cf[j].x, cf[j].y);
           so[(size_t)j * 32] = make_double2(delta, lambda);
           node_mid(t2.y, f2.y, cf[j + 1].x, cf[j + 1].y);
@@ -137,7 +138,7 @@ GS_DEV bool k7_forward(const K7Params &q, K7Ring &r, int line0, int nl, int lane
         }
       } else {
         const double *cF = reinterpret_cast<const double *>(st) + rl;
-        const double *cT = reinterpret_cast<const double *>(st + K7Fwd<false>::kTile) + rl;
+        const double *cT = reinterpret_cast<const double *>(st + K7_TILE) + rl;
 #pragma unroll
         for (int j = 0; j < K7_CH; ++j) {
           node_mid(cT[j * 32], cF[j * 32], cf[j].x, cf[j].y);
@@ -150,11 +151,11 @@ GS_DEV bool k7_forward(const K7Params &q, K7Ring &r, int line0, int nl, int lane
         const int i = i0 + j;
         double F, t;
         if (XDIR) {
-          F = reinterpret_cast<const double *>(st)[rl * K7_XP + j];
-          t = reinterpret_cast<const double *>(st + K7Fwd<true>::kTile)[rl * K7_XP + j];
+          F = *reinterpret_cast<const double *>(st + k7_swz(rl, j));
+          t = *reinterpret_cast<const double *>(st + K7_TILE + k7_swz(rl, j));
         } else {
           F = reinterpret_cast<const double *>(st)[j * 32 + rl];
-          t = reinterpret_cast<const double *>(st + K7Fwd<false>::kTile)[j * 32 + rl];
+          t = reinterpret_cast<const double *>(st + K7_TILE)[j * 32 + rl];
         }
         if (i == 0) {
           gs_forward_first<FAST>(f_diag, f_sup, f_rhs, delta, lambda, ok);   // the row k6_ends assembled (:28-64)
@@ -169,28 +170,30 @@ GS_DEV bool k7_forward(const K7Params &q, K7Ring &r, int line0, int nl, int lane
     }
     k7_advance(r.head);
     __syncwarp();
-    if (c + K7_NS < NC) k7_issue_fwd<XDIR>(q, r, c + K7_NS, line0, nl, lane);
+    if (c + K7_NS < NC) k7_issue_fwd<XDIR>(q, tm, r, c + K7_NS, line0, lane);
   }
   return ok;
 }
 
-// backward stage layout: (delta, lambda) [16][32] double2 (8 KB) | old grid [16][32] (fused y sweep)
-template <bool XDIR, bool FUSE>
-GS_DEV void k7_issue_bwd(const K7Params &q, K7Ring &r, int c, int line0, int nl, int lane, const double2 *sc) {
-  const int i0 = c * K7_CH, len = min(K7_CH, q.n - i0);
-  unsigned char *st = k7_stage(r, r.tail);
-  uint64_t *bar = &r.bars[r.tail];
-  if (lane == 0) gs_mbar_expect_tx(bar, (uint32_t)(len * 512 + (FUSE ? len * nl * 8 : 0)));
-  __syncwarp();
-  if (lane == 0) gs_bulk_g2s(st, sc + (size_t)i0 * 32, (uint32_t)len * 512u, bar);
-  if (FUSE && lane < len)
-    gs_bulk_g2s(st + K7_CH * 512 + lane * 256, q.grid_io + (size_t)(i0 + lane) * q.cols + line0, (uint32_t)nl * 8u, bar);
+// backward stage layout: (delta, lambda) [16][32] double2 (8 KB) | old grid tile [16][32] (fused y sweep)
+template <bool FUSE>
+GS_DEV void k7_issue_bwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, int line0, int lane, const double2 *sc) {
+  if (lane == 0) {
+    const int i0 = c * K7_CH, len = min(K7_CH, q.n - i0);
+    unsigned char *st = k7_stage(r, r.tail);
+    uint64_t *bar = &r.bars[r.tail];
+    gs_mbar_expect_tx(bar, (uint32_t)(len * 512 + (FUSE ? K7_TILE : 0)));
+    gs_bulk_g2s(st, sc + (size_t)i0 * 32, (uint32_t)len * 512u, bar);
+    if (FUSE) gs_tma_load_2d(st + K7_CH * 512, &tm.gold, line0, i0, bar);
+  }
   k7_advance(r.tail);
 }
 
 template <bool XDIR, bool FUSE>
-__global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
-  extern __shared__ __align__(128) unsigned char k7s[];
+__global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
+  extern __shared__ unsigned char k7raw[];
+  // the swizzled boxes need a 1024-byte aligned base
+  unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
   const int lane = threadIdx.x;
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
   const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
@@ -198,13 +201,17 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
   const int rl = act ? lane : nl - 1;      // lanes past the last line shadow it (their stores are suppressed)
   K7Ring r;
   r.bars = reinterpret_cast<uint64_t *>(k7s);
-  r.stages = k7s + 128;
+  r.stages = k7s + 1024;
   r.phase = 0;
   r.head = r.tail = 0;
-  unsigned char *otile = k7s + 128 + K7_NS * K7_STAGE;
+  unsigned char *otile = k7s + 1024 + K7_NS * K7_STAGE;
   if (lane == 0) {
     for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&r.bars[s], 1);
     gs_mbar_init_fence();
+    gs_tma_prefetch_desc(&tm.F);
+    gs_tma_prefetch_desc(&tm.rhs);
+    if (FUSE) gs_tma_prefetch_desc(&tm.gold);
+    if (XDIR) gs_tma_prefetch_desc(&tm.out);
   }
   gs_fence_proxy_async();
   __syncwarp();
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
     bool ok = false;
     unsigned fl = 0;
     if (fast_allowed) {
-      ok = k7_forward<XDIR, true>(q, r, line0, nl, lane, rl, rt, inv_time, sc, fl);
+      ok = k7_forward<XDIR, true>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
       ok = __all_sync(0xffffffffu, ok);
     }
     if (!ok) {
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
       // in this warp's lines: the same walk with the native division
       fl = 0;
       __syncwarp();
-      k7_forward<XDIR, false>(q, r, line0, nl, lane, rl, rt, inv_time, sc, fl);
+      k7_forward<XDIR, false>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
     }
     flags |= fl;
   }
@@ -237,13 +244,13 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
   __syncwarp();
 
   // ---- backward (backwardRow :303-322 / backwardColumn :324-342 [+ Grid.update :474-481]) ----
-  for (int k = 0; k < min(K7_NS, NC); ++k) k7_issue_bwd<XDIR, FUSE>(q, r, NC - 1 - k, line0, nl, lane, sc);
+  for (int k = 0; k < min(K7_NS, NC); ++k) k7_issue_bwd<FUSE>(q, tm, r, NC - 1 - k, line0, lane, sc);
   double u = 0.0;
   int ot = 0;
 #pragma unroll 1
   for (int c = NC - 1; c >= 0; --c) {
     const int i0 = c * K7_CH, len = min(K7_CH, n - i0);
-    k7_wait(r);
+    k7_wait(r, q.status);
     const unsigned char *st = k7_stage(r, r.head);
     const double2 *dl = reinterpret_cast<const double2 *>(st) + lane;
     double xs[K7_CH];
@@ -266,14 +273,20 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
       }
     }
     if (XDIR) {
-      // this lane's row of the output tile: written here, read by this lane's own bulk store
-      double *orow = reinterpret_cast<double *>(otile + ot * K7_OUT) + lane * K7_XP;
-      gs_bulk_wait_read<1>();            // the store issued from this tile two chunks ago has read it
+      // transposed (swizzled) output tile: every lane writes its row, lane 0 stores the box
+      unsigned char *orow = otile + ot * K7_TILE + lane * 128;
+      if (lane == 0) gs_bulk_wait_read<1>();    // the store issued from this tile two chunks ago has read it
+      __syncwarp();
+      const int sw = lane & 7;
 #pragma unroll
-      for (int j = 0; j < K7_CH; j += 2) *reinterpret_cast<double2 *>(orow + j) = make_double2(xs[j], xs[j + 1]);
+      for (int j = 0; j < K7_CH; j += 2)
+        *reinterpret_cast<double2 *>(orow + (((j >> 1) ^ sw) << 4)) = make_double2(xs[j], xs[j + 1]);
       gs_fence_proxy_async_smem();
-      if (act) gs_bulk_s2g(q.out + (size_t)(line0 + lane) * q.cols + i0, orow, (uint32_t)len * 8u);
-      gs_bulk_commit();
+      __syncwarp();
+      if (lane == 0) {
+        gs_tma_store_2d(&tm.out, i0, line0, otile + ot * K7_TILE);
+        gs_bulk_commit();
+      }
       ot ^= 1;
     } else if (act) {
       const size_t g0 = (size_t)i0 * q.cols + line0 + lane;
@@ -296,9 +309,9 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q) {
     }
     k7_advance(r.head);
     __syncwarp();
-    if (c - K7_NS >= 0) k7_issue_bwd<XDIR, FUSE>(q, r, c - K7_NS, line0, nl, lane, sc);
+    if (c - K7_NS >= 0) k7_issue_bwd<FUSE>(q, tm, r, c - K7_NS, line0, lane, sc);
   }
-  if (XDIR) gs_bulk_wait_read<0>();
+  if (XDIR && lane == 0) gs_bulk_wait_read<0>();
   if (act && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
   gs_raise(q.status, flags);
 }

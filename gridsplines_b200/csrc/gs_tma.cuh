@@ -77,3 +77,44 @@ GS_TMA_DEV void gs_bulk_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, u
                "r"(gs_smem_u32(ssrc)), "r"(bytes), "l"(policy)
                : "memory");
 }
+
+// ---- tensor-map TMA (cp.async.bulk.tensor): one instruction moves a 2-D box between a row-major global array and
+// shared memory; parts of the box outside the array are zero-filled on loads (the mbarrier still counts the whole
+// box) and clipped on stores.  `tmap` points to a CUtensorMap (128 B, 64 B aligned) in kernel-parameter space
+// (__grid_constant__); c0 = innermost coordinate (column), c1 = row.
+GS_TMA_DEV void gs_tma_load_2d(void *sdst, const void *tmap, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          gs_smem_u32(sdst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(gs_smem_u32(bar))
+      : "memory");
+}
+GS_TMA_DEV void gs_tma_store_2d(const void *tmap, int c0, int c1, const void *ssrc) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(gs_smem_u32(ssrc))
+               : "memory");
+}
+GS_TMA_DEV void gs_tma_prefetch_desc(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// mbarrier wait that cannot hang the device: after ~2^32 cycles without completion it raises bit 31 of *status and traps
+GS_TMA_DEV void gs_mbar_wait_bounded(uint64_t *bar, uint32_t parity, unsigned *status) {
+  uint32_t addr = gs_smem_u32(bar), done;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > (1ll << 32)) {
+      atomicOr(status, 0x80000000u);
+      __trap();
+    }
+  }
+}
