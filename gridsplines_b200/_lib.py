@@ -40,6 +40,7 @@ SIGNATURES = {
     "gs_spline_create": (_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _ip),
     "gs_spline_eval_apply": (_vp, C.c_int, C.c_int, _dp, _dp),
     "gs_spline_eval_average": (_vp, C.c_int, C.c_int, _dp, _dp, _dp),
+    "gs_spline_eval_status": (_vp, C.POINTER(C.c_uint32)),
     "gs_predef": (_vp, C.c_int, C.c_double, _dp, C.c_int, C.c_double, C.c_double, _dp),
     "gs_heatflow_geometry": (_vp, C.c_int, C.c_double, _dp, C.c_int, C.c_double, _dp),
     "gs_grid1d_create": (_vp, C.c_int64, C.c_int, C.c_int, C.c_double, _dp, C.c_double, C.c_double, C.c_int, _ip, _dp, _vpp),

@@ -310,10 +310,18 @@ class AlwaysDefinedSpline:
                                          _p(np.ascontiguousarray(spl.coefs)), lx, ux, ly, uy, C.byref(out)))
         return out.value
 
+    def _eval_flags(self) -> int:
+        f = C.c_uint32()
+        L.check(L.lib().gs_spline_eval_status(self.ctx._h, C.byref(f)))
+        return f.value
+
     def _eval_apply(self, sid, xs) -> np.ndarray:
         xs = _d(xs)
         out = np.empty_like(xs)
         L.check(L.lib().gs_spline_eval_apply(self.ctx._h, sid, len(xs), _p(xs), _p(out)))
+        if self._eval_flags() & 1:
+            # "Spline is not defined at point ..." RuntimeException (P/intervaltree/AbsITree.scala:475-479)
+            raise RuntimeError("spline is not defined at one of the arguments (NaN or outside the knots)")
         return out
 
     def __call__(self, x):
@@ -325,6 +333,8 @@ class AlwaysDefinedSpline:
         lo_a, hi_a = np.atleast_1d(_d(lo)), np.atleast_1d(_d(hi))
         out = np.empty_like(lo_a)
         L.check(L.lib().gs_spline_eval_average(self.ctx._h, self.id, len(lo_a), _p(lo_a), _p(hi_a), _p(out)))
+        if self._eval_flags() & 1:
+            raise RuntimeError("spline is not defined at one of the arguments (NaN or outside the knots)")
         return out if np.ndim(lo) else float(out[0])
 
 
@@ -598,9 +608,92 @@ class VarYCoef(_VarCoef):
 
 
 class VarXCoef(_VarCoef):
-    """per-column splines.  The reference indexes VarXCoef by y+1 as well (:835-847, App. B Q2); the
-    flattening host decides what `coefs(col,row)` returns, here the per-column reading."""
+    """The reference's VarXCoef, literally: its arrays are built per COLUMN interval (xDim.values.sliding(2), cols + 1
+    entries, :878-893) but every member indexes them by y + 1 (:862-874) -- so it behaves as a per-row
+    map over the first rows + 1 entries and throws (ArrayIndexOutOfBounds -> IndexError here) when rows > cols.  Kept
+    literal for parity; `VarXCoefByColumn` is the per-column reading the name suggests."""
+    mode = MAP_PER_ROW
+
+    def maps(self, cols, rows):
+        n = rows + 1
+        if min(len(self.therm), len(self.cap), len(self.tempcond)) < n:
+            raise IndexError("VarXCoef indexes its per-column arrays by y + 1 (TwoDGrid.scala:862-874): "
+                             f"{n} entries needed, {len(self.tempcond)} given")
+        ids = lambda lst: [s.id for s in lst[:n]]
+        return {SEL_APPLY: (MAP_PER_ROW, ids(self.tempcond)), SEL_THERM: (MAP_PER_ROW, ids(self.therm)),
+                SEL_CAP: (MAP_PER_ROW, ids(self.cap)), SEL_TEMPCOND: (MAP_PER_ROW, ids(self.tempcond))}
+
+
+class VarXCoefByColumn(_VarCoef):
+    """per-column splines, index col + 1: what VarXCoef's constructor arguments describe (not what the reference's
+    members return, see VarXCoef)."""
     mode = MAP_PER_COL
+
+
+class _PatchCoef(Coefficients):
+    """PatchXCoef / PatchYCoef (:895-1089): per-interval arrays that apply inside rangeX x rangeY only (`contains`,
+    closed-open index intervals).  Only meaningful inside a Patched*Coef."""
+    apply_by_x = False
+
+    def __init__(self, therm: Sequence, cap: Sequence, tempcond: Sequence, rangeX, rangeY, ctx=None):
+        ctx = ctx or default_context()
+        self.therm = [_as_ads(s, ctx) for s in therm]
+        self.cap = [_as_ads(s, ctx) for s in cap]
+        self.tempcond = [_as_ads(s, ctx) for s in tempcond]
+        self.rangeX, self.rangeY = tuple(rangeX), tuple(rangeY)
+
+    def contains(self, x: int, y: int) -> bool:    # Interval.contains on CsdOpn: lower <= i < upper
+        return self.rangeX[0] <= x < self.rangeX[1] and self.rangeY[0] <= y < self.rangeY[1]
+
+    def member(self, sel: int, x: int, y: int) -> AlwaysDefinedSpline:
+        if sel == SEL_THERM:
+            return self.therm[y + 1]
+        if sel == SEL_CAP:
+            return self.cap[y + 1]
+        if sel == SEL_TEMPCOND:
+            return self.tempcond[y + 1]
+        return self.tempcond[(x if self.apply_by_x else y) + 1]
+
+
+class PatchXCoef(_PatchCoef):
+    """:895-947 -- every member, `apply` included, indexes by y + 1."""
+
+
+class PatchYCoef(_PatchCoef):
+    """:1019-1056 -- thermConductivity / capacity / tempConductivity index by y + 1, `apply` by x + 1 (:1056)."""
+    apply_by_x = True
+
+
+class _PatchedCoef(Coefficients):
+    """PatchedXCoef(xCoefs, path) / PatchedYCoef(yCoefs, path) (:1091-1137): the patch where it `contains` the node,
+    the base map elsewhere.  Flattened to DENSE id maps (what a Scala host does by calling coefs(col, row) for every
+    index from -1)."""
+
+    def __init__(self, base: _VarCoef, path: _PatchCoef):
+        self.base, self.path = base, path
+
+    def maps(self, cols, rows):
+        base = self.base.maps(cols, rows)
+        out = {}
+        for sel in (SEL_APPLY, SEL_THERM, SEL_CAP, SEL_TEMPCOND):
+            mode, ids = base[sel]
+            a = np.empty((rows + 1, cols + 1), dtype=np.int32)
+            for y in range(-1, rows):
+                for x in range(-1, cols):
+                    if self.path.contains(x, y):
+                        a[y + 1, x + 1] = self.path.member(sel, x, y).id
+                    else:
+                        a[y + 1, x + 1] = ids[(y if mode == MAP_PER_ROW else x) + 1]
+            out[sel] = (MAP_DENSE, a.ravel())
+        return out
+
+
+class PatchedXCoef(_PatchedCoef):
+    pass
+
+
+class PatchedYCoef(_PatchedCoef):
+    pass
 
 
 class DenseCoef(Coefficients):

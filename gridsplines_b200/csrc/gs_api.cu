@@ -263,10 +263,20 @@ static int eval_common(gs_ctx *ctx, int id, int n, const double *a, const double
   ctx->launches++;
   GS_CUDA(cudaGetLastError());
   GS_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned hstatus = 0;
+  GS_CUDA(cudaMemcpyAsync(&hstatus, dstatus, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   GS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->eval_flags = hstatus;
   return GS_OK;
 }
 
+// GS_FLAG_* raised by the last gs_spline_eval_* call of this context (the reference throws where these are set:
+// RuntimeException for an undefined argument, P/intervaltree/AbsITree.scala:475-479)
+extern "C" int gs_spline_eval_status(gs_ctx *ctx, uint32_t *flags) {
+  GS_REQUIRE(ctx && flags, "NULL argument");
+  *flags = ctx->eval_flags;
+  return GS_OK;
+}
 extern "C" int gs_spline_eval_apply(gs_ctx *ctx, int id, int n, const double *x, double *out) {
   return eval_common(ctx, id, n, x, nullptr, out, false);
 }

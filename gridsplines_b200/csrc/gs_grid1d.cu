@@ -1447,6 +1447,13 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
   if (g->hs_init) {
     cudaStreamDestroy(g->hs_in);
     cudaStreamDestroy(g->hs_out);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(g->hs_in_done[i]);
+      cudaEventDestroy(g->hs_in_free[i]);
+      cudaEventDestroy(g->hs_out_ready[i]);
+      cudaEventDestroy(g->hs_out_free[i]);
+    }
+    cudaEventDestroy(g->hs_start);
   }
   cudaFree(g->status);
   gs_ctx *owner = g->ctx;

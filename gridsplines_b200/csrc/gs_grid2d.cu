@@ -1044,6 +1044,7 @@ static int materialise_result(gs_grid2d *g) {
 extern "C" int gs_grid2d_fill(gs_grid2d *g, double value) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   GS_TRY(gs_ctx_use(g->ctx));
+  GS_TRY(materialise_result(g));   // `result` keeps the last solve (the reference never touches it here)
   long long count = (long long)g->cols * g->rows;
   GS_TRY(gs_launch_fill(g->ctx, g->grid, count, value));
   GS_TRY(gs_launch_fill(g->ctx, g->predict, count, value));
@@ -1059,6 +1060,7 @@ extern "C" int gs_grid2d_upload(gs_grid2d *g, int which, const double *host) {
   GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
   GS_TRY(gs_ctx_use(g->ctx));
   if (which == GS_RESULT) g->result_is_grid = false;
+  if (which == GS_GRID) GS_TRY(materialise_result(g));
   GS_CUDA(cudaMemcpyAsync(array2d(g, which), host, (size_t)g->cols * g->rows * sizeof(double), cudaMemcpyHostToDevice,
                           g->ctx->stream));
   GS_CUDA(cudaStreamSynchronize(g->ctx->stream));
@@ -1891,6 +1893,7 @@ extern "C" int gs_grid2d_copy_from_device(gs_grid2d *g, int which, const void *d
   GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
   GS_TRY(gs_ctx_use(g->ctx));
   if (which == GS_RESULT) g->result_is_grid = false;
+  if (which == GS_GRID) GS_TRY(materialise_result(g));
   GS_CUDA(cudaMemcpyAsync(array2d(g, which), dptr, (size_t)g->cols * g->rows * sizeof(double), cudaMemcpyDeviceToDevice,
                           g->ctx->stream));
   return GS_OK;
@@ -1912,6 +1915,7 @@ extern "C" int gs_grid2d_bind_device(gs_grid2d *g, int which, void *dptr) {
   GS_REQUIRE(g && dptr, "NULL argument");
   GS_REQUIRE(which >= GS_GRID && which <= GS_RESULT, "unknown array");
   GS_TRY(gs_ctx_use(g->ctx));
+  if (which == GS_GRID) GS_TRY(materialise_result(g));   // the old grid buffer may be the only copy of `result`
   GS_CUDA(cudaStreamSynchronize(g->ctx->stream));
   double **slot = which == GS_GRID ? &g->grid : which == GS_PREDICT ? &g->predict : &g->result;
   if (!g->bound[which]) cudaFree(*slot);

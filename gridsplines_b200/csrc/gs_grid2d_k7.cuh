@@ -289,22 +289,35 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant
       }
       ot ^= 1;
     } else if (act) {
-      const size_t g0 = (size_t)i0 * q.cols + line0 + lane;
+      const size_t cs = (size_t)q.cols, g0 = (size_t)i0 * cs + line0 + lane;
       if (FUSE) {
         const double *gold = reinterpret_cast<const double *>(st + K7_CH * 512) + lane;
         double *G = q.grid_io + g0, *P = q.predict_out + g0;
+        if (len == K7_CH) {
 #pragma unroll
-        for (int j = 0; j < K7_CH; ++j) {
-          if (j < len) {
-            P[(size_t)j * q.cols] = aval2d(gold[j * 32], xs[j]);
-            G[(size_t)j * q.cols] = xs[j];
+          for (int j = 0; j < K7_CH; ++j, G += cs, P += cs) {
+            *P = aval2d(gold[j * 32], xs[j]);
+            *G = xs[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < K7_CH; ++j, G += cs, P += cs) {
+            if (j < len) {
+              *P = aval2d(gold[j * 32], xs[j]);
+              *G = xs[j];
+            }
           }
         }
       } else {
         double *O = q.out + g0;
+        if (len == K7_CH) {
 #pragma unroll
-        for (int j = 0; j < K7_CH; ++j)
-          if (j < len) O[(size_t)j * q.cols] = xs[j];
+          for (int j = 0; j < K7_CH; ++j, O += cs) *O = xs[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < K7_CH; ++j, O += cs)
+            if (j < len) *O = xs[j];
+        }
       }
     }
     k7_advance(r.head);

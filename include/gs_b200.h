@@ -114,6 +114,10 @@ int gs_spline_create(gs_ctx *ctx, int kind, int npieces, const double *knots, co
 int gs_spline_eval_apply(gs_ctx *ctx, int id, int n, const double *x, double *out);
 int gs_spline_eval_average(gs_ctx *ctx, int id, int n, const double *lo, const double *hi,
                            double *out);
+/* GS_FLAG_* raised by the last gs_spline_eval_* call on this context: an argument where the reference throws
+ * (NaN -> RuntimeException, P/intervaltree/AbsITree.scala:475-479) sets GS_FLAG_SPLINE_UNDEFINED; the value returned
+ * for it is NaN */
+int gs_spline_eval_status(gs_ctx *ctx, uint32_t *flags);
 
 /* ---- metric coefficients (K1) ----------------------------------------- */
 /* TypeDir.preDef: arraygrid.makeOrthogonalMatrix A/arraygrid/package.scala:21-78 /

@@ -191,7 +191,7 @@ class Problem2D:
             if self.coefs == "dense":
                 g.set_coefs(gs.DenseCoef(*[ids(maps[k][1]) for k in (0, 1, 2, 3)]))
             else:
-                cls = gs.VarYCoef if self.coefs == "per_row" else gs.VarXCoef
+                cls = gs.VarYCoef if self.coefs == "per_row" else gs.VarXCoefByColumn
                 g.set_coefs(cls([pool[i] for i in maps[1][1]], [pool[i] for i in maps[2][1]],
                                 [pool[i] for i in maps[3][1]]))
         side_attr = {gs.UPP: "upp", gs.LOW: "low", gs.RIGHT: "right", gs.LEFT: "left"}

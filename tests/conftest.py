@@ -30,3 +30,15 @@ def gs():
 @pytest.fixture(scope="session")
 def ctx(gs):
     return gs.default_context()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured errors of every tolerance comparison (helpers.check_tol) -> gpurun_out/parity_tests.json."""
+    import json
+
+    from helpers import PARITY_LOG
+
+    out = os.path.join(ROOT, "gpurun_out")
+    if PARITY_LOG and os.path.isdir(out):
+        with open(os.path.join(out, "parity_tests.json"), "w") as f:
+            json.dump(PARITY_LOG, f, indent=1)

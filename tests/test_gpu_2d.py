@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import assert_bit_equal, max_rel_err
+from helpers import assert_bit_equal, check_tol, elem_rel_err, max_rel_err
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -115,7 +115,7 @@ def test_coefficient_maps_and_tables(O, gs, coefs, combo):
         lit.iteration(900.0)
     O.set_ascending_fold(True)
     for k, v in cases.snapshot(lit).items():
-        assert max_rel_err(got[k], v) <= 1e-12, k
+        check_tol(got[k], v, f"exact solver vs literal tree-order fold {coefs} {combo} {k}", 1e-12)
 
 
 def test_gridtest_physical_validation(O, gs):
@@ -201,6 +201,13 @@ def test_medium_grid_properties(O, gs):
 # chain, so the bar is the north star's tolerance: <= 1e-12 max relative error per field.
 # ---------------------------------------------------------------------------------------------
 TOL = 1e-12
+# Spline TABLES under a reordered solver: the reference's face property (antider(hi) - antider(lo)) / (hi - lo)
+# (A/AlwaysDefinedSpline.scala:43-46) cancels for neighbouring temperatures, so a last-bit difference of `predict` moves
+# the reference's OWN next step by up to ~1e-11 (measured by _oracle_sensitivity; profiles/r2_parity.json has the
+# numbers at full size).  The tolerance family therefore cannot hold 1e-12 on tables after several steps; the bar for
+# it is this FIXED constant (both measured errors are logged), and the within-1e-12 path for tables is the bit-exact
+# solver (K7, tests/test_gpu_k7.py).
+TOL_TABLES = 2e-11
 
 
 @pytest.fixture
@@ -212,10 +219,9 @@ def seg_len(ctx):
     ctx.set_option("seg_len", 32)
 
 
-def _compare_tol(got, want, what, tol=TOL):
+def _compare_tol(got, want, what, tol=TOL, tol_elem=None):
     for k, v in want.items():
-        err = max_rel_err(got[k], v)
-        assert err <= tol, f"{what} {k}: max relative error per field {err:.3e} (tolerance {tol:.1e})"
+        check_tol(got[k], v, f"{what} {k}", tol, tol_elem)
 
 
 def _oracle_sensitivity(O, p, steps):
@@ -242,9 +248,9 @@ def test_partitioned_all_boundary_kinds(O, gs, seg_len, combo, m):
     g, o = p.build_gs(gs), p.build_oracle(O)
     g.set_solver(gs.SOLVER_PARTITIONED)
     g.xIter(900.0); o.xIter(900.0)
-    assert max_rel_err(g.grid.result, o.result) <= TOL, "xIter"
+    check_tol(g.grid.result, o.result, f"partitioned xIter {combo} m={m}", TOL)
     g.yIter(900.0); o.yIter(900.0)
-    assert max_rel_err(g.grid.result, o.result) <= TOL, "yIter"
+    check_tol(g.grid.result, o.result, f"partitioned yIter {combo} m={m}", TOL)
     g.grid.update(); o.update()
     g.iteration(900.0, nsteps=3)
     for _ in range(3):
@@ -278,7 +284,7 @@ def test_partitioned_coefficient_maps_and_tables(O, gs, seg_len, coefs):
     for _ in range(3):
         o.iteration(900.0)
     O.set_ascending_fold(True)
-    _compare_tol(cases.snapshot(g), cases.snapshot(o), coefs, tol=max(TOL, 4.0 * _oracle_sensitivity(O, p, 3)))
+    _compare_tol(cases.snapshot(g), cases.snapshot(o), f"partitioned {coefs}", tol=TOL_TABLES)
 
 
 def test_partitioned_gridtest_and_medium(O, gs, seg_len):
@@ -338,7 +344,7 @@ def test_k6_faces_plus_elimination(O, gs, ctx, coefs, combo, cols, rows):
         for _ in range(3):
             o.iteration(900.0)
         O.set_ascending_fold(True)
-        tol = TOL if coefs == "const" else max(TOL, 4.0 * _oracle_sensitivity(O, p, 3))
+        tol = TOL if coefs == "const" else TOL_TABLES
         _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs} {combo} {cols}x{rows}", tol=tol)
         g.xIter(900.0); o.xIter(900.0)
         assert max_rel_err(g.grid.result, o.result) <= tol
@@ -364,7 +370,7 @@ def test_k6_fused_faces_variant(O, gs, ctx, coefs, combo, cols, rows):
         for _ in range(3):
             o.iteration(900.0)
         O.set_ascending_fold(True)
-        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 3))
+        tol = TOL_TABLES
         _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 fused faces {coefs}", tol=tol)
         assert g.status == 0
     finally:
@@ -386,7 +392,7 @@ def test_k6_tables_outside_the_fast_tier(O, gs, ctx, coefs):
     for _ in range(2):
         o.iteration(900.0)
     O.set_ascending_fold(True)
-    tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+    tol = TOL_TABLES
     _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 {coefs}", tol=tol)
     assert g.status == 0
 
@@ -417,7 +423,7 @@ def test_k6_face_tiers(O, gs, ctx, field):
         for _ in range(2):
             o.iteration(900.0)
         O.set_ascending_fold(True)
-        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+        tol = TOL_TABLES
         _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 tiers {field}", tol=tol)
     finally:
         ctx.set_option("k5", 1)
@@ -439,7 +445,7 @@ def test_k6_clustered_strips(O, gs, ctx, cols, rows):
         for _ in range(2):
             o.iteration(900.0)
         O.set_ascending_fold(True)
-        tol = max(TOL, 4.0 * _oracle_sensitivity(O, p, 2))
+        tol = TOL_TABLES
         _compare_tol(cases.snapshot(g), cases.snapshot(o), f"K6 clusters {cols}x{rows}", tol=tol)
         ctx.set_option("k6_cluster", 0)
         h = p.build_gs(gs)
