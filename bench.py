@@ -8,8 +8,15 @@ every line = nlines * n grid-point updates.  Inputs (4.3 GB of grid + predict pe
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 `value`   : device-resident throughput (CUDA events on the library's stream, max over ranks).
-`e2e`     : same metric through the C ABI with HOST buffers: per step H2D of grid+predict+BCs from pinned
-            memory, the step, D2H of grid+predict.
+`e2e`     : same metric through the C ABI with HOST buffers (gs_grid1d_step_host, the drop-in OneDGrid.step): per step
+            H2D of the public `grid` array + the per-line end temperatures from pinned memory, the step, D2H of `grid`
+            (`predict` is private to OneDGrid, A/OneDGrid.scala:21, and stays on the device).
+`configs` : (N = 1) the other BASELINE.json configs on the same GPU -- C1, C3, C4, C5 with SURVEY 8(d)'s inputs: ms per
+            step, updates/s, roofline fraction, solver, a parity figure measured in the run, and for C3 an end-to-end
+            number (upload grid, iteration, download grid).
+`c4_strong`, `c5_strong` : (N > 1, under torchrun) the sharded configs on all N GPUs -- C4 16384^2 row-sharded with the
+            reduced-system exchange (NCCL all-gather inside the step), C5 with its lines split -- next to the same problem
+            on one GPU measured in the same run.
 `roofline`: 32 algorithmic bytes per update / measured kernel time vs MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / --impl reference: the oracle's C restatement of the reference (the reference is Scala and no
             JVM exists on the image) on the host cores, on a bounded sample of the same workload.
@@ -31,6 +38,8 @@ NLINES, NNODES = 1 << 20, 256
 TIME_STEP = 900.0
 SEED = 20261019
 BYTES_PER_UPDATE_1D = 32.0
+C2_WORKLOAD = ("C2: batched 1-D orthogonal diffusion, 1M lines x 256 nodes per GPU, per-thread Thomas, "
+               "const properties, per-line Dirichlet ends")
 
 
 def workload_geometry(n):
@@ -144,13 +153,316 @@ def run_reference(args):
         "impl": "reference", "metric": "grid-point updates/s", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(per_step)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: batched 1-D orthogonal diffusion, 1M lines x 256 nodes, per-line Thomas, const properties",
+        "config": {"workload": C2_WORKLOAD,
+                   "sample": sample,
                    "note": "C restatement of the reference's Scala path (oracle/gs_oracle.c); JVM unavailable on the image"},
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (SURVEY 8(d) inputs)
+# ---------------------------------------------------------------------------------------------------------------
+RHO = [0.598, 0.826, 1.121, 1.496, 1.966, 2.547, 3.258, 4.122, 5.156, 6.397, 7.862]   # README density column
+BYTES_PER_UPDATE_2D = 64.0
+
+
+def _c4_coefs(gs, ctx):
+    """M1Hermite3 k(T), c(T) over T = -20..80 and alpha = k / c by the reference's own spline division."""
+    T = [-20.0 + 10.0 * i for i in range(11)]
+    k = gs.Spline.m1Hermite3([(t, 1.0 + 0.1 * q) for t, q in zip(T, RHO)])
+    c = gs.Spline.m1Hermite3([(t, 2.0e6 + 1.0e5 * q) for t, q in zip(T, RHO)])
+    return gs.ConstantCoef(k, c, k / c, ctx=ctx)
+
+
+def _c3_coefs(gs, ctx):
+    return gs.ConstantCoef(gs.Spline.const(1.5), gs.Spline.const(2.2e6), gs.Spline.const(1.5 / 2.2e6), ctx=ctx)
+
+
+def _grid2d(gs, ctx, torch, which, n, solver, field):
+    """C3: ortho x ortho, spacing 0.01, Dirichlet 20 / 4 (upp / low) + Neumann 50 / 0 (left / right).
+    C4: radial x (r_i = 0.05 * 1.0005^(i+1)), ortho y, Dirichlet left 30, others 7."""
+    if which == "C3":
+        x = gs.XDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
+        kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Flow), left=(gs.Many, gs.Flow))
+        bv = dict(upp=20.0, low=4.0, left=50.0, right=0.0)
+        coefs = _c3_coefs(gs, ctx)
+    else:
+        x = gs.XDim(0.05, 0.05 * 1.0005 ** np.arange(1, n + 1), 0.05 * 1.0005 ** (n + 1), gs.RADIAL)
+        kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Temp), left=(gs.Many, gs.Temp))
+        bv = dict(upp=7.0, low=7.0, right=7.0, left=30.0)
+        coefs = _c4_coefs(gs, ctx)
+    y = gs.YDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
+    g = gs.TwoDGrid(x, y, coefs=coefs, ctx=ctx, **kinds)
+    for side, v in bv.items():
+        getattr(g.bounds, side).update(v)
+    g.set_solver(solver)
+    g.copy_from_device(gs.GRID, field.data_ptr())
+    g.copy_from_device(gs.PREDICT, field.data_ptr())
+    return g
+
+
+def _field2d(torch, n, which):
+    gen = torch.Generator(device="cuda").manual_seed(SEED)
+    f = 7.0 + torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen)
+    if which == "C3":
+        f[100:164, 200:264] = 7.0     # keeps the t_lo == t_hi branch of `average` covered (SURVEY 8(d))
+    return f
+
+
+def _time_steps(torch, stream, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _errs(torch, a, b):
+    """(field-normalised, element-wise) max relative error of device tensors a against b."""
+    d = (a - b).abs()
+    den = b.abs()
+    field = float(d.max() / den.max())
+    den = torch.where(den == 0, den.max(), den)
+    return field, float((d / den).max())
+
+
+def _device_arrays(gs, torch, g, n):
+    out = {}
+    for name, which in (("grid", gs.GRID), ("predict", gs.PREDICT)):
+        t = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        g.copy_to_device(which, t.data_ptr())
+        out[name] = t
+    torch.cuda.synchronize()
+    return out
+
+
+def _roof(updates, bytes_per_update, ms, peak):
+    achieved = bytes_per_update * updates / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "algorithmic_bytes_per_update": bytes_per_update}
+
+
+def bench_c1(gs, ctx, torch, stream):
+    """C1: one radial 200-node line, 1000 implicit steps (the reference's own CPU-runnable case); bits vs the fixture."""
+    rng = np.array([0.05 + 0.01 * (i + 1) for i in range(200)])
+    mk = lambda: gs.OneDGrid(0.05, rng, rng[-1] + 0.01, gs.Spline.const(1e-6), 1.0, direction=gs.RADIAL, ctx=ctx)
+    g = mk()
+    g.step(900.0, 20.0, 4.0, nsteps=1000)
+    got = g.grid
+    want = np.load(os.path.join(ROOT, "tests", "golden", "c1_radial_200x1000.npz"))["grid"]
+    exact = bool(np.array_equal(got.view(np.uint64), np.asarray(want, dtype=np.float64).ravel().view(np.uint64)))
+    g = mk()
+    ms = _time_steps(torch, stream, lambda: g.step(900.0, 20.0, 4.0, nsteps=1000), 3, 1)
+    return {"workload": "C1: 1-D radial, 200 nodes, 1000 implicit steps, constant properties (one line: replicas only)",
+            "ms_per_step": ms / 1000.0, "updates_per_s": 200 * 1000 / (ms * 1e-3), "solver": "K2c (per-thread Thomas, exact)",
+            "parity": {"bit_identical_to_fixture": exact, "fixture": "tests/golden/c1_radial_200x1000.npz (oracle)"},
+            "note": "a single 200-node line is launch-latency bound by construction"}
+
+
+def bench_c3(gs, ctx, torch, stream, peak, steps=20, n=4096):
+    f = _field2d(torch, n, "C3")
+    fast = _grid2d(gs, ctx, torch, "C3", n, gs.SOLVER_AUTO, f)
+    ms = _time_steps(torch, stream, lambda: fast.iteration(TIME_STEP), steps, 3)
+    # parity: the configured 100 steps, AUTO (K5, tolerance family) against the exact solver (K7) from the same start
+    fast.copy_from_device(gs.GRID, f.data_ptr()); fast.copy_from_device(gs.PREDICT, f.data_ptr())
+    exact = _grid2d(gs, ctx, torch, "C3", n, gs.SOLVER_THOMAS, f)
+    fast.iteration(TIME_STEP, nsteps=100)
+    exact.iteration(TIME_STEP, nsteps=100)
+    a, b = _device_arrays(gs, torch, fast, n), _device_arrays(gs, torch, exact, n)
+    par = {k: dict(zip(("field", "elementwise"), _errs(torch, a[k], b[k]))) for k in a}
+    ms_exact = _time_steps(torch, stream, lambda: exact.iteration(TIME_STEP), 5, 1)
+    status = fast.status | exact.status
+    # end to end: upload the public grid array from pinned memory, one iteration, download it
+    h = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    h.copy_(f.cpu())
+
+    def e2e():
+        fast.upload_ptr(gs.GRID, h.data_ptr())
+        fast.iteration(TIME_STEP)
+        fast.download_ptr(gs.GRID, h.data_ptr())
+
+    e2e_ms = _time_steps(torch, stream, e2e, 5, 1)
+    exact.close(); fast.close()
+    cells = float(n) * n
+    return {"workload": f"C3: 2-D ortho x ortho {n}x{n}, constant properties, Dirichlet 20/4 + Neumann 50/0, one 64x64 flat patch",
+            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
+            "solver": "AUTO -> K5 (hoisted partitioned sweeps, tolerance family)",
+            "parity": {"after_steps": 100, "against": "GS_SOLVER_THOMAS (K7, bit-exact vs the oracle: tests/test_gpu_k7.py)", **par},
+            "exact_solver": {"ms_per_step": ms_exact, "updates_per_s": cells / (ms_exact * 1e-3),
+                             "roofline_frac": _roof(cells, BYTES_PER_UPDATE_2D, ms_exact, peak)["frac"], "solver": "K7"},
+            "e2e": {"ms_per_step": e2e_ms, "updates_per_s": cells / (e2e_ms * 1e-3), "h2d_bytes_per_step": int(cells * 8),
+                    "d2h_bytes_per_step": int(cells * 8)},
+            "status": int(status)}
+
+
+def bench_c4(gs, ctx, torch, stream, peak, steps=5, n=16384):
+    f = _field2d(torch, n, "C4")
+    g = _grid2d(gs, ctx, torch, "C4", n, gs.SOLVER_AUTO, f)
+    ms = _time_steps(torch, stream, lambda: g.iteration(TIME_STEP), steps, 2)
+    # the tolerance family (K6) on the same problem: its time, and its distance from the exact solver after the
+    # configured 20 steps from the same start
+    g.copy_from_device(gs.GRID, f.data_ptr()); g.copy_from_device(gs.PREDICT, f.data_ptr())
+    g.iteration(TIME_STEP, nsteps=20)
+    exact = _device_arrays(gs, torch, g, n)
+    status = g.status
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    g.copy_from_device(gs.GRID, f.data_ptr()); g.copy_from_device(gs.PREDICT, f.data_ptr())
+    g.iteration(TIME_STEP, nsteps=20)
+    part = _device_arrays(gs, torch, g, n)
+    par = {k: dict(zip(("field", "elementwise"), _errs(torch, part[k], exact[k]))) for k in exact}
+    ms_part = _time_steps(torch, stream, lambda: g.iteration(TIME_STEP), steps, 1)
+    status |= g.status
+    g.close()
+    cells = float(n) * n
+    return {"workload": f"C4: 2-D radial x ortho {n}x{n}, M1Hermite3 k(T), c(T), alpha = k / c, Dirichlet 30 / 7",
+            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
+            "solver": "AUTO -> K7 (faces pass + per-thread Thomas in the reference's order: bit-exact)",
+            "parity": {"statement": "bit-exact vs the oracle (tests/test_gpu_k7.py: 4096^2 C4 shape, every node, 2 steps)"},
+            "tolerance_family": {"solver": "GS_SOLVER_PARTITIONED -> K6", "ms_per_step": ms_part,
+                                 "updates_per_s": cells / (ms_part * 1e-3),
+                                 "roofline_frac": _roof(cells, BYTES_PER_UPDATE_2D, ms_part, peak)["frac"],
+                                 "error_vs_exact_after_20_steps": par},
+            "status": int(status)}
+
+
+def _c5_grid(gs, ctx, lines, n, solver, grid0, lt, rt):
+    g = gs.BatchedOneDGrid(0.0, 1e-3 * np.arange(1, n + 1), 1e-3 * (n + 1), gs.Spline.const(1e-6), 1.0, nlines=lines, ctx=ctx)
+    g.set_solver(solver)
+    g.upload(gs.GRID, grid0)
+    g.set_bc(lt, rt)
+    return g
+
+
+def bench_c5(gs, ctx, torch, stream, peak, steps=5, lines=4096, n=65536, parity=True):
+    r = np.random.default_rng(SEED + 5)
+    grid0 = r.uniform(0.0, 30.0, (lines, n))
+    lt, rt = r.uniform(10.0, 30.0, lines), r.uniform(0.0, 10.0, lines)
+    g = _c5_grid(gs, ctx, lines, n, gs.SOLVER_AUTO, grid0, lt, rt)
+    ms = _time_steps(torch, stream, lambda: g.step(TIME_STEP), steps, 2)
+    out = {"workload": f"C5: {lines} lines x {n} nodes, ortho, constant properties, per-line Dirichlet ends",
+           "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
+           "roofline": _roof(float(lines) * n, BYTES_PER_UPDATE_1D, ms, peak),
+           "solver": "AUTO -> K5 (partitioned Thomas: segments + reduced system, tolerance family)"}
+    if parity:
+        g.upload(gs.GRID, grid0); g.fill(gs.PREDICT, 4.0)
+        e = _c5_grid(gs, ctx, lines, n, gs.SOLVER_THOMAS, grid0, lt, rt)
+        g.step(TIME_STEP, nsteps=20)
+        e.step(TIME_STEP, nsteps=20)
+        par = {}
+        for name, which in (("grid", gs.GRID), ("predict", gs.PREDICT)):
+            a, b = g.download(which), e.download(which)
+            d = np.abs(a - b)
+            par[name] = {"field": float(d.max() / np.abs(b).max()), "elementwise": float((d / np.abs(b)).max())}
+        out["parity"] = {"after_steps": 20, "against": "GS_SOLVER_THOMAS (per-thread Thomas, bit-exact vs the oracle)", **par}
+        out["status"] = int(g.status | e.status)
+        e.close()
+    g.close()
+    return out
+
+
+def bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local, steps=5, n=16384):
+    """C4 on all ranks: rows sharded, x sweep local, y sweep = partitioned elimination continued across GPUs with ONE
+    all-gather of 6 x cols doubles per rank inside the step (gridsplines_b200/sharded2d.py); next to it the same
+    problem on ONE GPU (rank 0, same run) with the same solver family, and the distance between the two results."""
+    from gridsplines_b200.sharded2d import GsLocalGrid, SpikeShardedTwoDGrid
+
+    xv = 0.05 * 1.0005 ** np.arange(n + 2)
+    yv = 0.01 * np.arange(n + 2)
+    bounds = {0: (0, 1, np.full(n, 7.0)), 1: (0, 1, np.full(n, 7.0)), 2: (0, 1, np.full(n, 7.0)), 3: (0, 1, np.full(n, 30.0))}
+    mk = lambda xv_, yv_: GsLocalGrid(gs, ctx, xv_, yv_, gs.RADIAL, gs.ORTHO, lambda c: _c4_coefs(gs, c))
+    full = _field2d(torch, n, "C4")          # same seed on every rank
+    sg = SpikeShardedTwoDGrid(mk, xv, yv, bounds, world, rank)
+    mine = full[sg.r0:sg.r0 + sg.rl].contiguous()
+    sg.set_local_rows(mine, mine.clone())
+    sg.iteration(TIME_STEP, nsteps=2)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sg.iteration(TIME_STEP, nsteps=steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rows = sg.local_rows(0)
+    gathered = [torch.empty_like(rows) for _ in range(world)] if rank == 0 else None
+    dist.gather(rows, gathered, dst=0)
+    out = None
+    if rank == 0:
+        got = torch.cat(gathered)
+        del gathered
+        one = SpikeShardedTwoDGrid(mk, xv, yv, bounds, 1, 0)            # the same driver on one GPU
+        one.set_local_rows(full.clone(), full.clone())
+        one.iteration(TIME_STEP, nsteps=2)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        one.iteration(TIME_STEP, nsteps=steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / steps
+        f1, el1 = _errs(torch, got, one.local_rows(0))
+        del one
+        ex = _grid2d(gs, ctx, torch, "C4", n, gs.SOLVER_THOMAS, full)   # and the exact solver, same number of steps
+        ex.iteration(TIME_STEP, nsteps=2 + steps)
+        t_ex = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        ex.copy_to_device(gs.GRID, t_ex.data_ptr())
+        torch.cuda.synchronize()
+        f2, el2 = _errs(torch, got, t_ex)
+        ex.close()
+        cells = float(n) * n
+        out = {"workload": f"C4 {n}x{n} row-sharded over {world} GPUs, reduced-system (SPIKE) exchange", "n_gpus": world,
+               "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "n1_ms_per_step": ms1,
+               "efficiency_vs_n1": ms1 / (ms * world), "scaling": "strong",
+               "collective": "ncclAllGather", "collective_bytes_per_step_per_rank": int((6 + 2) * n * 8 * world),
+               "error_vs_n1_same_solver": {"field": f1, "elementwise": el1},
+               "error_vs_exact_solver_n1": {"field": f2, "elementwise": el2, "steps": 2 + steps},
+               "solver": "K6 split sweep (tolerance family)"}
+    dist.barrier()
+    return out
+
+
+def bench_c5_strong(gs, torch, dist, stream, ctx, world, rank, peak, steps=5, lines=4096, n=65536):
+    """C5 with its lines split over the ranks (no data-path collective), next to all lines on one GPU (rank 0)."""
+    from gridsplines_b200.sharding import block_shard
+
+    start, count = block_shard(lines, world, rank)
+    r = np.random.default_rng(SEED + 5 + rank)
+    grid0 = r.uniform(0.0, 30.0, (count, n))
+    lt, rt = r.uniform(10.0, 30.0, count), r.uniform(0.0, 10.0, count)
+    g = _c5_grid(gs, ctx, count, n, gs.SOLVER_AUTO, grid0, lt, rt)
+    g.step(TIME_STEP, nsteps=2)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    g.step(TIME_STEP, nsteps=steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    status = g.status
+    g.close()
+    out = None
+    if rank == 0:
+        one = bench_c5(gs, ctx, torch, stream, peak, steps=steps, lines=lines, n=n, parity=False)
+        out = {"workload": f"C5 {lines} lines x {n} nodes, lines split over {world} GPUs", "n_gpus": world,
+               "lines_per_gpu": count, "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
+               "n1_ms_per_step": one["ms_per_step"], "efficiency_vs_n1": one["ms_per_step"] / (ms * world),
+               "scaling": "strong", "collective": None, "status": int(status)}
+    dist.barrier()
+    return out
 
 
 def run_ours(args):
@@ -252,8 +564,32 @@ def run_ours(args):
     value = updates_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = updates_per_step * e2e_steps / (e2e_ms * 1e-3)
 
+    # ---- the other configs (N = 1) and the sharded configs (N > 1): C2's buffers are released first
+    g.close()
+    del h_grid, h_pred
+    peak, peak_src = measured_peak()
+    configs, strong = {}, {}
+    want = set(c.strip().upper() for c in args.configs.split(",")) if args.configs else set()
+    with torch.cuda.stream(stream):
+        if world == 1:
+            for name, fn in (("C1", lambda: bench_c1(gs, ctx, torch, stream)),
+                             ("C3", lambda: bench_c3(gs, ctx, torch, stream, peak)),
+                             ("C4", lambda: bench_c4(gs, ctx, torch, stream, peak)),
+                             ("C5", lambda: bench_c5(gs, ctx, torch, stream, peak))):
+                if "ALL" in want or name in want:
+                    try:
+                        configs[name] = fn()
+                    except Exception as exc:   # a failing extra config must not take the C2 line down with it
+                        configs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                    torch.cuda.empty_cache()
+        else:
+            for name, fn in (("c4_strong", lambda: bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local)),
+                             ("c5_strong", lambda: bench_c5_strong(gs, torch, dist, stream, ctx, world, rank, peak))):
+                if "ALL" in want or name.upper().split("_")[0] in want:
+                    strong[name] = fn()
+                    torch.cuda.empty_cache()
+
     if rank == 0:
-        peak, peak_src = measured_peak()
         achieved = BYTES_PER_UPDATE_1D * float(nlines) * n / (kernel_ms * 1e-3) / 1e9
         traffic = ncu_traffic()
         threads = os.cpu_count() or 1
@@ -263,8 +599,7 @@ def run_ours(args):
             "metric": "grid-point updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: batched 1-D orthogonal diffusion, 1M lines x 256 nodes per GPU, per-thread Thomas, "
-                                   "const properties, per-line Dirichlet ends",
+            "config": {"workload": C2_WORKLOAD,
                        "lines_per_gpu": nlines, "nodes": n, "time_step_s": TIME_STEP,
                        "l2_policy": "inputs (4.3 GB/GPU) exceed L2 (126 MB); no flush needed",
                        "parity": "bit-exact vs oracle (tests/test_gpu_1d.py)", "options": args.opt,
@@ -280,6 +615,10 @@ def run_ours(args):
                              "sample": f"{cpu_lines} of {nlines} lines x {n} nodes x {args.cpu_steps} steps "
                                        f"({cpu_dt:.1f} s), C restatement of the Scala reference, pthreads over lines"},
         }
+        if configs:
+            line["configs"] = configs
+        for k, v in strong.items():
+            line[k] = v
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -296,6 +635,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--opt", action="append", default=[], help="gs_ctx_set_option name=value")
+    ap.add_argument("--configs", default="all", help="extra configs to measure: all | none | comma list of C1,C3,C4,C5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -823,6 +823,13 @@ class TwoDGrid:
         """Second half: `gathered` = [nranks][6][cols] device doubles, every rank's `exported` in rank order."""
         L.check(L.lib().gs_grid2d_yiter_update_end(self._h, time, gathered, nranks, rank))
 
+    def upload_ptr(self, which: int, host_ptr: int):
+        """gs_grid2d_upload from a raw host pointer (e.g. pinned memory): rows * cols doubles, row-major."""
+        L.check(L.lib().gs_grid2d_upload(self._h, which, host_ptr))
+
+    def download_ptr(self, which: int, host_ptr: int):
+        L.check(L.lib().gs_grid2d_download(self._h, which, host_ptr))
+
     def copy_from_device(self, which: int, dptr: int):
         L.check(L.lib().gs_grid2d_copy_from_device(self._h, which, dptr))
 

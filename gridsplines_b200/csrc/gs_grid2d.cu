@@ -1813,19 +1813,28 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   return GS_OK;
 }
 
+// Solver choice per sweep.  GS_SOLVER_THOMAS: K7 (exact), first-draft exact kernels where K7 does not apply.
+// GS_SOLVER_PARTITIONED: K5 / K6 / first-generation partitioned kernels (tolerance family).  GS_SOLVER_AUTO: K5 for
+// literal-constant coefficients (<= 1e-12 measured at the configured step counts, profiles/r2_parity.json); everything
+// else -- spline tables, coefficient maps, short lines -- takes the exact K7, because a reordered elimination cannot
+// stay within 1e-12 of the reference on tables; option auto_exact = 0 restores the round-1 choice.
+static bool auto_exact(gs_grid2d *g, bool xdir) {
+  return g->solver == GS_SOLVER_AUTO && g->ctx->opt_auto_exact && use_k7(g, xdir);
+}
 static int sweep_x(gs_grid2d *g, double time) {
   if (use_k5(g, true)) return launch_k5(g, time, true);
+  if (auto_exact(g, true)) return launch_k7(g, time, true, false);
   if (use_k6(g, true)) return launch_k6(g, time, true);
   if (use_partitioned(g, g->cols)) return launch_part(g, time, true, false);
   return use_k7(g, true) ? launch_k7(g, time, true, false) : launch_xsweep(g, time);
 }
 static int sweep_y(gs_grid2d *g, double time, bool fuse) {
   if (fuse && use_k5(g, false)) return launch_k5(g, time, false);   // K5's / K6's y sweeps are always fused with Grid.update
+  if (auto_exact(g, false)) return launch_k7(g, time, false, fuse);
   if (fuse && use_k6(g, false)) return launch_k6(g, time, false);
   if (use_partitioned(g, g->rows)) return launch_part(g, time, false, fuse);
   return use_k7(g, false) ? launch_k7(g, time, false, fuse) : launch_ysweep(g, time, fuse);
 }
-
 extern "C" int gs_grid2d_xiter(gs_grid2d *g, double time) {
   GS_REQUIRE(g != nullptr, "NULL argument");
   GS_TRY(gs_ctx_use(g->ctx));

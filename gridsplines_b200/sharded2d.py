@@ -151,6 +151,8 @@ class SpikeShardedTwoDGrid:
             raise ValueError("a lower HeatFlow bound is not supported on a sharded grid")
         self.r0, self.rl = block_shard(self.rows, world, rank)
         self.g = make_local(xv, yv[self.r0:self.r0 + self.rl + 2])
+        if hasattr(self.g, "use_partitioned"):
+            self.g.use_partitioned()    # the split sweep is the partitioned solver; AUTO would pick the exact one for x
         for side, (kind, rep, values) in bounds.items():
             v = np.atleast_1d(np.asarray(values, float))
             if side in (LEFT, RIGHT) and v.size > 1:
@@ -222,6 +224,9 @@ class GsLocalGrid:
 
     def view(self, which) -> torch.Tensor:
         return self._t[which]
+
+    def use_partitioned(self):
+        self.g.set_solver(self.gs.SOLVER_PARTITIONED)
 
     def set_bound(self, side, kind, rep, values):
         v = np.atleast_1d(np.asarray(values, float))
