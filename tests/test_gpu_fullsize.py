@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import assert_bit_equal, max_rel_err
+from helpers import assert_bit_equal, check_tol, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -121,11 +121,15 @@ def test_c4_full_size_tables_vs_exact(gs):
     kinds = dict(upp=(gs.Many, gs.Temp), low=(gs.Many, gs.Temp), right=(gs.Many, gs.Temp), left=(gs.Many, gs.Temp))
     bvals = dict(upp=7.0, low=7.0, right=7.0, left=30.0)
     res = {}
-    for solver in (gs.SOLVER_AUTO, gs.SOLVER_THOMAS):
+    for solver in (gs.SOLVER_AUTO, gs.SOLVER_THOMAS, gs.SOLVER_PARTITIONED):
         g = _grid2d(gs, n, gs.ConstantCoef(k, c, alpha), kinds, bvals, field, solver, xdir=1)
-        g.iteration(900.0)      # one step from the rough field: the reference's own 1-ulp sensitivity is ~1e-13 here
+        g.iteration(900.0)
         res[solver] = g.grid.grid
         assert g.status == 0
         g.close()
-    assert max_rel_err(res[gs.SOLVER_AUTO], res[gs.SOLVER_THOMAS]) <= 1e-12
+    # AUTO takes the exact solver (K7) for tables: the same bits as GS_SOLVER_THOMAS
+    assert_bit_equal(res[gs.SOLVER_AUTO], res[gs.SOLVER_THOMAS], "C4 16384^2 AUTO vs THOMAS")
+    # the tolerance family (K6) after ONE step from the rough field; its drift over the configured 20 steps is measured
+    # by tools/parity_report.py (profiles/r2_parity.json) and stated in DESIGN.md
+    check_tol(res[gs.SOLVER_PARTITIONED], res[gs.SOLVER_THOMAS], "C4 16384^2 K6 vs exact, 1 step", 1e-12)
     assert res[gs.SOLVER_AUTO].min() >= 7.0 - 1e-9 and res[gs.SOLVER_AUTO].max() <= 30.0 + 1e-9
