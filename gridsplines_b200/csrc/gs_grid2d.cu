@@ -1589,12 +1589,13 @@ struct K6Split {
 
 // 1. faces + end rows of a direction (reads predict, rhs; every spline evaluation of the sweep happens here).  Shared by
 // K6 (tolerance solver) and K7 (exact solver).  `skip_faces`: the sweep evaluates the interior faces itself (k6_fuse).
-static int launch_faces(gs_grid2d *g, double time, bool xdir, const K6Split *split, K6FacesParams &fq, bool *ff_out) {
+static int launch_faces(gs_grid2d *g, double time, bool xdir, const K6Split *split, K6FacesParams &fq, bool *ff_out,
+                        bool ends_only = false) {
   gs_ctx *ctx = g->ctx;
   const int n = xdir ? g->cols : g->rows, nlines = xdir ? g->rows : g->cols;
   const size_t cells = (size_t)g->cols * g->rows;
-  if (!g->k6_F) GS_CUDA(cudaMalloc(&g->k6_F, cells * sizeof(double)));
-  const size_t ends_need = 6 * (size_t)std::max(g->cols, g->rows);
+  if (!g->k6_F && !ends_only) GS_CUDA(cudaMalloc(&g->k6_F, cells * sizeof(double)));
+  const size_t ends_need = 7 * (size_t)std::max(g->cols, g->rows);
   if (!g->k6_ends) GS_CUDA(cudaMalloc(&g->k6_ends, ends_need * sizeof(double)));
   const int mode = split ? split->mode : K6_FUSED;
   bool single;
@@ -1615,6 +1616,7 @@ static int launch_faces(gs_grid2d *g, double time, bool xdir, const K6Split *spl
   fq.halo_prev = split ? split->halo_prev : nullptr;
   fq.halo_next = split ? split->halo_next : nullptr;
   fq.fm1 = g->k6_split;
+  fq.face0 = ends_only ? g->k6_ends + 6 * (size_t)std::max(g->cols, g->rows) : nullptr;
   size_t pool_smem = p.smem_pool ? (size_t)p.pool_len * sizeof(double) : 0;
   // blocks of 256 columns x a stride of rows, ONE wave: as many CTAs as are resident at once, equal rows each
   // (several short waves leave the chip part-empty while the last one drains)
@@ -1624,9 +1626,9 @@ static int launch_faces(gs_grid2d *g, double time, bool xdir, const K6Split *spl
   const bool tab = !lit && p.smem_pool;
   const int eblocks = (nlines + 127) / 128;   // (one warp per CTA measured slower: every CTA stages the pool)
   // fused faces: the sweep evaluates the interior faces itself (phase A), only the end rows need their own kernel
-  const bool ff = ff_out && tab && ctx->opt_k6_fuse && k6_chunk(ctx) == 8;
+  const bool ff = ends_only || (ff_out && tab && ctx->opt_k6_fuse && k6_chunk(ctx) == 8);
   if (ff_out) *ff_out = ff;
-  if (ff) {
+  if (ff && !ends_only) {
     int m_, S_;
     k6_shape(ctx, n, &m_, &S_);
     GS_REQUIRE(k6_smem(ctx, xdir, S_, true, p.pool_len) <= ctx->smem_optin, "K6 shared memory");
@@ -1743,7 +1745,7 @@ typedef CUresult (*gs_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static_assert(sizeof(CUtensorMap) == sizeof(K7Map), "CUtensorMap is a 128-byte blob");
-static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox) {
+static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox, bool pred_box = false) {
   static gs_tmap_encode_fn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -1757,11 +1759,13 @@ static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(double)};
-  const cuuint32_t box[2] = {xbox ? 16u : 32u, xbox ? 32u : 16u};
+  // pred_box (fused faces): one more node along the line, 18 columns (a 16-byte multiple) without the swizzle for x
+  const cuuint32_t box[2] = {xbox ? (pred_box ? 18u : 16u) : 32u, xbox ? 32u : (pred_box ? 17u : 16u)};
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult rc = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base),
                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       xbox ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       (xbox && !pred_box) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     gs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%d x %d)", (int)rc, rows, cols);
@@ -1788,8 +1792,13 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     GS_CUDA(cudaMalloc(&g->k7_scratch, elems * sizeof(double2)));
     g->k7_scratch_elems = elems;
   }
+  // fused faces (k7f_sweep): the spline pool must fit its 4 KB of shared memory, or all coefficients are literal constants
+  bool lit = true;
+  for (int s4 = 0; s4 < 4 && lit; ++s4)
+    lit = g->map_mode[s4] == GS_MAP_SINGLE && literal_const(ctx, ctx->spline_off[g->map_host[s4][0]], nullptr);
+  const bool fused = ctx->opt_k7_fuse && (lit || ctx->pool.size() * sizeof(double) <= K7F_POOL);
   K6FacesParams fq;
-  GS_TRY(launch_faces(g, time, xdir, nullptr, fq, nullptr));
+  GS_TRY(launch_faces(g, time, xdir, nullptr, fq, nullptr, fused));
   K7Params q;
   q.n = n; q.nlines = nlines; q.cols = g->cols; q.rows = g->rows;
   q.coefs = (xdir ? g->x : g->y).coefs;
@@ -1800,12 +1809,25 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   q.scratch = g->k7_scratch;
   q.time = time;
   q.status = g->status;
+  q.face0 = fq.face0;
+  q.pool = fq.sw.pool;
+  q.pool_len = fq.sw.pool_len;
+  q.maps = fq.sw.maps;
   K7Maps tm;
-  GS_TRY(k7_encode(&tm.F, fq.F, g->cols, g->rows, xdir));
+  GS_TRY(k7_encode(&tm.F, fused ? (const void *)g->predict : (const void *)fq.F, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.rhs, fq.sw.rhs, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.gold, g->grid, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.out, g->result, g->cols, g->rows, xdir));
-  if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
+  GS_TRY(k7_encode(&tm.pred, g->predict, g->cols, g->rows, xdir, true));
+  if (fused) {
+    void (*kern)(K7Params, const K7Maps);
+    if (xdir) kern = lit ? k7f_sweep<true, false, true> : k7f_sweep<true, false, false>;
+    else if (fuse) kern = lit ? k7f_sweep<false, true, true> : k7f_sweep<false, true, false>;
+    else kern = lit ? k7f_sweep<false, false, true> : k7f_sweep<false, false, false>;
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K7F_SMEM));
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<strips, 64, K7F_SMEM, ctx->stream>>>(q, tm);
+  } else if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   else k7_sweep<false, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   ctx->launches++;

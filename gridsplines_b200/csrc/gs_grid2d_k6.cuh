@@ -25,6 +25,7 @@ struct K6FacesParams {
   int open_first, open_last;
   const double *halo_prev, *halo_next;   // [nlines] predict of the row above node 0 / below node n-1
   double *fm1;                            // [nlines] face between the upper halo row and node 0
+  double *face0;                          // K7F: the carry out of node 0 goes here [nlines] and F is not touched
 };
 
 // The two end rows of every line (Dirichlet or heat-flow, A/Dim.scala:28-64, 86-128) with the reference's general
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(128) k6_ends(K6FacesParams q) {
   } else {
     double face = 0.0;
     Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, 0, A.pred(0), A.pred(1), A.rhs(0), face, flags, ok);
-    q.F[A.idx(0)] = face;                  // carry into node 1: co, or cond / cap after a heat-flow end
+    if (q.face0) q.face0[line] = face;     // carry into node 1: co, or cond / cap after a heat-flow end
+    else q.F[A.idx(0)] = face;
     double *o = q.first3 + 3 * (size_t)line;
     o[0] = r.diag; o[1] = r.sup; o[2] = r.rhs;
   }
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(128) k6_ends(K6FacesParams q) {
     const double p0 = A.pred(i);
     double face = face_before<XDIR, SEL, false>(A, sel, k, i, A.pred(i - 1), p0, flags, ok);
     Row4 r = asm_node<XDIR, SEL, false>(A, sel, k, i, p0, 0.0, A.rhs(i), face, flags, ok);
-    q.F[A.idx(i)] = 0.0;
+    if (!q.face0) q.F[A.idx(i)] = 0.0;
     double *o = q.last3 + 3 * (size_t)line;
     o[0] = r.sub; o[1] = r.diag; o[2] = r.rhs;
   }

@@ -44,6 +44,7 @@ struct __align__(64) K7Map {
 };
 struct K7Maps {
   K7Map F, rhs, gold, out;   // boxes of k6_F, the right-hand side, the old grid (fused y) and the result (x)
+  K7Map pred;                // fused faces: predict, box 32 x 17 (y) / 18 x 32 (x)
 };
 
 struct K7Params {
@@ -56,6 +57,11 @@ struct K7Params {
   double2 *scratch;                // [strips][n][32] (delta, lambda)
   double time;
   unsigned *status;
+  // fused faces (k7f_sweep): the carry out of node 0 from k6_ends, the spline pool and the coefficient maps
+  const double *face0;
+  const double *pool;
+  int pool_len;
+  Maps2d maps;
 };
 
 // ring bookkeeping of one warp: stage s is used for the chunks s, s + NS, ...; bit s of `phase` is the parity the
@@ -189,61 +195,12 @@ GS_DEV void k7_issue_bwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, 
   k7_advance(r.tail);
 }
 
+// The backward walk (backwardRow :303-322 / backwardColumn :324-342 [+ Grid.update :474-481]) of one warp's 32 lines:
+// (delta, lambda) come back from the scratch array through the ring, results leave as described at the top.
 template <bool XDIR, bool FUSE>
-__global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
-  extern __shared__ unsigned char k7raw[];
-  // the swizzled boxes need a 1024-byte aligned base
-  unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
-  const int lane = threadIdx.x;
+GS_DEV double k7_backward(const K7Params &q, const K7Maps &tm, K7Ring &r, unsigned char *otile, int line0, bool act,
+                          int lane, const double2 *sc) {
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
-  const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
-  const bool act = lane < nl;
-  const int rl = act ? lane : nl - 1;      // lanes past the last line shadow it (their stores are suppressed)
-  K7Ring r;
-  r.bars = reinterpret_cast<uint64_t *>(k7s);
-  r.stages = k7s + 1024;
-  r.phase = 0;
-  r.head = r.tail = 0;
-  unsigned char *otile = k7s + 1024 + K7_NS * K7_STAGE;
-  if (lane == 0) {
-    for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&r.bars[s], 1);
-    gs_mbar_init_fence();
-    gs_tma_prefetch_desc(&tm.F);
-    gs_tma_prefetch_desc(&tm.rhs);
-    if (FUSE) gs_tma_prefetch_desc(&tm.gold);
-    if (XDIR) gs_tma_prefetch_desc(&tm.out);
-  }
-  gs_fence_proxy_async();
-  __syncwarp();
-  bool fast_allowed = true;
-  const GsRcp rt = gs_rcp_invariant(q.time, fast_allowed);
-  const double inv_time = 1.0 / q.time;
-  double2 *sc = q.scratch + (size_t)blockIdx.x * (size_t)n * 32;
-  unsigned flags = 0;
-
-  // ---- forward (Dim.* + passion.forward*) ----
-  {
-    bool ok = false;
-    unsigned fl = 0;
-    if (fast_allowed) {
-      ok = k7_forward<XDIR, true>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
-      ok = __all_sync(0xffffffffu, ok);
-    }
-    if (!ok) {
-      // an operand outside the shared-reciprocal divider's range (zero, denormal, Inf, NaN, absurd magnitude) somewhere
-      // in this warp's lines: the same walk with the native division
-      fl = 0;
-      __syncwarp();
-      k7_forward<XDIR, false>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
-    }
-    flags |= fl;
-  }
-  // the (delta, lambda) this warp wrote (generic proxy) are read back by bulk copies (async proxy)
-  __threadfence();
-  gs_fence_proxy_async();
-  __syncwarp();
-
-  // ---- backward (backwardRow :303-322 / backwardColumn :324-342 [+ Grid.update :474-481]) ----
   for (int k = 0; k < min(K7_NS, NC); ++k) k7_issue_bwd<FUSE>(q, tm, r, NC - 1 - k, line0, lane, sc);
   double u = 0.0;
   int ot = 0;
@@ -324,6 +281,338 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant
     __syncwarp();
     if (c - K7_NS >= 0) k7_issue_bwd<FUSE>(q, tm, r, c - K7_NS, line0, lane, sc);
   }
+  return u;
+}
+
+template <bool XDIR, bool FUSE>
+__global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
+  extern __shared__ unsigned char k7raw[];
+  // the swizzled boxes need a 1024-byte aligned base
+  unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
+  const int lane = threadIdx.x;
+  const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
+  const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
+  const bool act = lane < nl;
+  const int rl = act ? lane : nl - 1;      // lanes past the last line shadow it (their stores are suppressed)
+  K7Ring r;
+  r.bars = reinterpret_cast<uint64_t *>(k7s);
+  r.stages = k7s + 1024;
+  r.phase = 0;
+  r.head = r.tail = 0;
+  unsigned char *otile = k7s + 1024 + K7_NS * K7_STAGE;
+  if (lane == 0) {
+    for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&r.bars[s], 1);
+    gs_mbar_init_fence();
+    gs_tma_prefetch_desc(&tm.F);
+    gs_tma_prefetch_desc(&tm.rhs);
+    if (FUSE) gs_tma_prefetch_desc(&tm.gold);
+    if (XDIR) gs_tma_prefetch_desc(&tm.out);
+  }
+  gs_fence_proxy_async();
+  __syncwarp();
+  bool fast_allowed = true;
+  const GsRcp rt = gs_rcp_invariant(q.time, fast_allowed);
+  const double inv_time = 1.0 / q.time;
+  double2 *sc = q.scratch + (size_t)blockIdx.x * (size_t)n * 32;
+  unsigned flags = 0;
+
+  // ---- forward (Dim.* + passion.forward*) ----
+  {
+    bool ok = false;
+    unsigned fl = 0;
+    if (fast_allowed) {
+      ok = k7_forward<XDIR, true>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
+      ok = __all_sync(0xffffffffu, ok);
+    }
+    if (!ok) {
+      // an operand outside the shared-reciprocal divider's range (zero, denormal, Inf, NaN, absurd magnitude) somewhere
+      // in this warp's lines: the same walk with the native division
+      fl = 0;
+      __syncwarp();
+      k7_forward<XDIR, false>(q, tm, r, line0, lane, rl, rt, inv_time, sc, fl);
+    }
+    flags |= fl;
+  }
+  // the (delta, lambda) this warp wrote (generic proxy) are read back by bulk copies (async proxy)
+  __threadfence();
+  gs_fence_proxy_async();
+  __syncwarp();
+
+  const double u = k7_backward<XDIR, FUSE>(q, tm, r, otile, line0, act, lane, sc);
+  if (XDIR && lane == 0) gs_bulk_wait_read<0>();
+  if (act && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
+  gs_raise(q.status, flags);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k7f_sweep: K7 with the faces evaluated INSIDE the sweep by a second warp (warp-specialised producer), so that the
+// ~110 instructions of a face (interval average of the property table) run in the shadow of the chain warp's
+// dependent divisions instead of in a pass of their own, and F never travels through HBM:
+//   warp 1 (faces): TMA box of `predict` (16 + 1 nodes x 32 lines)  ->  F tile in shared memory (the tiers of
+//                   k6_faces: same doubles), and the TMA loads of the right-hand side / (cf0, cf1) for the chain warp;
+//   warp 0 (chain): waits for (F, rhs, cf) of a chunk on ONE mbarrier (transaction bytes of the loads + the faces
+//                   warp's arrival), runs the reference's recurrence, hands the stage back on an `empty` barrier.
+// The backward walk is K7's (k7_backward).  HBM traffic per node: x sweep 56 B (R predict, R grid, W + R (delta,
+// lambda), W result), y sweep 72 B.  Used when the spline pool fits 4 KB of shared memory (or the coefficients are
+// literal constants); otherwise K7 with its separate faces pass.
+// Shared memory (from a 1024-byte aligned base): barriers | ring region 39 KB | 2 output tiles | spline pool
+//   forward : 3 x (rhs tile 4 KB | F tile 4 KB) | 3 x cf 256 B | 3 x predict tile 4.5 KB
+//   backward: 3 x 12 KB stages (K7)
+// ---------------------------------------------------------------------------------------------------------------
+#define K7F_FT 8192                       // rhs tile + F tile
+#define K7F_CF (3 * K7F_FT)               // offset of the cf ring in the region
+#define K7F_P (K7F_CF + 1024)             // offset of the predict-tile ring
+#define K7F_PT 4608                       // one predict tile: y 17 x 32, x 32 x 18 doubles
+#define K7F_REGION 39936
+#define K7F_POOL 4096
+#define K7F_SMEM (1024 + 1024 + K7F_REGION + 2 * K7_TILE + K7F_POOL)
+static_assert(K7F_P + 3 * K7F_PT <= K7F_REGION && K7_NS * K7_STAGE <= K7F_REGION, "K7F shared-memory layout");
+
+struct K7FBars {
+  uint64_t bwd[K7_NS];   // backward ring (K7Ring)
+  uint64_t ft[3];        // (F, rhs, cf) of a chunk ready: tx bytes of the loads + 1 arrival (faces warp)
+  uint64_t empty[3];     // the chain warp is done with the stage
+  uint64_t pin[3];       // predict tile landed
+  int redo;              // the forward pass is repeated with the native division
+};
+
+// the chain warp's forward walk: as k7_forward, with F from the faces warp's tile and no loads of its own
+template <bool XDIR, bool FAST>
+GS_DEV bool k7f_forward(const K7Params &q, K7FBars *bars, unsigned char *region, uint32_t &ft_phase, int line0, int lane,
+                        int rl, GsRcp rt, double inv_time, double2 *sc, unsigned &flags) {
+  const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
+  const size_t line = (size_t)(line0 + rl);
+  const double f_diag = q.first3[3 * line], f_sup = q.first3[3 * line + 1], f_rhs = q.first3[3 * line + 2];
+  const double l_sub = q.last3[3 * line], l_diag = q.last3[3 * line + 1], l_rhs = q.last3[3 * line + 2];
+  bool ok = true;
+  double delta = 0.0, lambda = 0.0, fprev = 0.0;
+  auto node_mid = [&](double t, double F, double cf0, double cf1) {
+    const double a = cf0 * fprev;
+    const double cc = cf1 * F;
+    const double vect = gs_div<FAST>(-t, rt, ok);
+    gs_forward_unit<FAST>(a, -(a + cc) - inv_time, cc, vect, delta, lambda, flags, ok);
+    fprev = F;
+  };
+  int s = 0;
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    const int i0 = c * K7_CH, len = min(K7_CH, n - i0);
+    gs_mbar_wait_bounded(&bars->ft[s], (ft_phase >> s) & 1u, q.status);
+    ft_phase ^= 1u << s;
+    const unsigned char *st = region + s * K7F_FT;
+    const double *cF = reinterpret_cast<const double *>(st + K7_TILE) + rl;
+    const double2 *cf = reinterpret_cast<const double2 *>(region + K7F_CF + s * 256);
+    double2 *so = sc + (size_t)i0 * 32 + lane;
+    if (c != 0 && i0 + K7_CH < n) {
+      if (XDIR) {
+        const unsigned char *rT = st + rl * 128;
+        const int sw = rl & 7;
+#pragma unroll
+        for (int j = 0; j < K7_CH; j += 2) {
+          const double2 t2 = *reinterpret_cast<const double2 *>(rT + (((j >> 1) ^ sw) << 4));
+          node_mid(t2.x, cF[j * 32], cf[j].x, cf[j].y);
+          so[(size_t)j * 32] = make_double2(delta, lambda);
+          node_mid(t2.y, cF[(j + 1) * 32], cf[j + 1].x, cf[j + 1].y);
+          so[(size_t)(j + 1) * 32] = make_double2(delta, lambda);
+        }
+      } else {
+        const double *cT = reinterpret_cast<const double *>(st) + rl;
+#pragma unroll
+        for (int j = 0; j < K7_CH; ++j) {
+          node_mid(cT[j * 32], cF[j * 32], cf[j].x, cf[j].y);
+          so[(size_t)j * 32] = make_double2(delta, lambda);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < len; ++j) {
+        const int i = i0 + j;
+        const double F = cF[j * 32];
+        const double t = XDIR ? *reinterpret_cast<const double *>(st + k7_swz(rl, j))
+                              : reinterpret_cast<const double *>(st)[j * 32 + rl];
+        if (i == 0) {
+          gs_forward_first<FAST>(f_diag, f_sup, f_rhs, delta, lambda, ok);
+          fprev = F;
+        } else if (i == n - 1) {
+          gs_forward_last<FAST>(l_sub, l_diag, l_rhs, delta, lambda, ok);
+        } else {
+          node_mid(t, F, cf[j].x, cf[j].y);
+        }
+        so[(size_t)j * 32] = make_double2(delta, lambda);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) gs_mbar_arrive(&bars->empty[s]);
+    s = (s == 2) ? 0 : s + 1;
+  }
+  return ok;
+}
+
+// the faces warp's pass over all chunks of the strip
+template <bool XDIR, bool LIT>
+GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsigned char *region, const double *pool_sm,
+                      uint32_t &e_phase, uint32_t &p_phase, int line0, int lane, int rl, unsigned &flags) {
+  const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
+  const int line = line0 + rl;
+  auto issue_p = [&](int c) {
+    if (lane == 0) {
+      const int p = c % 3, i0 = c * K7_CH;
+      gs_mbar_expect_tx(&bars->pin[p], (uint32_t)(XDIR ? 32 * 18 * 8 : 17 * 32 * 8));
+      gs_tma_load_2d(region + K7F_P + p * K7F_PT, &tm.pred, XDIR ? i0 : line0, XDIR ? line0 : i0, &bars->pin[p]);
+    }
+  };
+  const bool single = LIT || q.maps.mode[GS_SEL_APPLY] == GS_MAP_SINGLE;
+  int off = q.maps.single_off[GS_SEL_APPLY];
+  K6Tab z = {};
+  GsLitConst zl;
+  zl.v = 0.0;
+  if (LIT) zl.v = q.pool[off + GS_HDR + 3];
+  else z = k6_tab(pool_sm + off);
+  auto face = [&](double p0, double p1, int i) -> double {
+    double v;
+    if (LIT) {
+      bool okf = true;
+      v = gs_take_average<true>(zl, p0, p1, flags, okf);
+      if (!okf) {
+        bool ok2 = true;
+        v = gs_take_average<false>(zl, p0, p1, flags, ok2);   // operands outside the fast divider's range
+      }
+      return v;
+    }
+    if (!single) {
+      off = map_off(q.maps, GS_SEL_APPLY, XDIR ? i : line, XDIR ? line : i, q.cols);
+      z = k6_tab(pool_sm + off);
+    }
+    if (!k6_face_fast(z, p0, p1, v)) {
+      if (!k6_face_mid(pool_sm + off, p0, p1, &v)) v = k6_face_general(q.pool, off, p0, p1, q.status);
+    }
+    return v;
+  };
+  for (int c = 0; c < min(3, NC); ++c) issue_p(c);
+  int s = 0;
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    const int i0 = c * K7_CH, len = min(K7_CH, n - i0);
+    // the stage is free again (the chain warp consumed chunk c - 3): start the chain warp's own loads into it
+    gs_mbar_wait_bounded(&bars->empty[s], (e_phase >> s) & 1u, q.status);
+    e_phase ^= 1u << s;
+    unsigned char *st = region + s * K7F_FT;
+    if (lane == 0) {
+      gs_mbar_expect_tx_only(&bars->ft[s], (uint32_t)(K7_TILE + len * 16));
+      gs_tma_load_2d(st, &tm.rhs, XDIR ? i0 : line0, XDIR ? line0 : i0, &bars->ft[s]);
+      gs_bulk_g2s(region + K7F_CF + s * 256, q.coefs + 2 * (size_t)i0, (uint32_t)len * 16u, &bars->ft[s]);
+    }
+    gs_mbar_wait_bounded(&bars->pin[s], (p_phase >> s) & 1u, q.status);
+    p_phase ^= 1u << s;
+    const double *P = reinterpret_cast<const double *>(region + K7F_P + s * K7F_PT);
+    double *F = reinterpret_cast<double *>(st + K7_TILE) + lane;
+    if (c != 0 && i0 + K7_CH < n) {
+#pragma unroll 2
+      for (int j = 0; j < K7_CH; ++j) {
+        const double p0 = XDIR ? P[rl * 18 + j] : P[j * 32 + rl], p1 = XDIR ? P[rl * 18 + j + 1] : P[(j + 1) * 32 + rl];
+        F[j * 32] = face(p0, p1, i0 + j);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < len; ++j) {
+        const int i = i0 + j;
+        double v = 0.0;
+        if (i == 0) {
+          v = q.face0[line];                    // carry out of node 0 (k6_ends): co, or cond / cap after a heat-flow end
+        } else if (i < n - 1) {
+          const double p0 = XDIR ? P[rl * 18 + j] : P[j * 32 + rl], p1 = XDIR ? P[rl * 18 + j + 1] : P[(j + 1) * 32 + rl];
+          v = face(p0, p1, i);
+        }
+        F[j * 32] = v;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) gs_mbar_arrive(&bars->ft[s]);          // release: the F tile is visible to the chain warp
+    if (c + 3 < NC) issue_p(c + 3);                        // the predict tile is free again
+    s = (s == 2) ? 0 : s + 1;
+  }
+}
+
+template <bool XDIR, bool FUSE, bool LIT>
+__global__ void __launch_bounds__(64, 4) k7f_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
+  extern __shared__ unsigned char k7raw[];
+  unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = q.n;
+  const int line0 = blockIdx.x * 32, nl = min(32, q.nlines - line0);
+  const bool act = lane < nl;
+  const int rl = act ? lane : nl - 1;
+  K7FBars *bars = reinterpret_cast<K7FBars *>(k7s);
+  unsigned char *region = k7s + 1024;
+  unsigned char *otile = region + K7F_REGION;
+  double *pool_sm = reinterpret_cast<double *>(otile + 2 * K7_TILE);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&bars->bwd[s], 1);
+    for (int s = 0; s < 3; ++s) {
+      gs_mbar_init(&bars->ft[s], 1);
+      gs_mbar_init(&bars->empty[s], 1);
+      gs_mbar_init(&bars->pin[s], 1);
+    }
+    bars->redo = 0;
+    gs_mbar_init_fence();
+    gs_tma_prefetch_desc(&tm.pred);
+    gs_tma_prefetch_desc(&tm.rhs);
+    if (FUSE) gs_tma_prefetch_desc(&tm.gold);
+    if (XDIR) gs_tma_prefetch_desc(&tm.out);
+  }
+  if (!LIT)
+    for (int i = threadIdx.x; i < q.pool_len; i += blockDim.x) pool_sm[i] = q.pool[i];
+  gs_fence_proxy_async();
+  __syncthreads();
+  if (warp == 1) {
+    // ---- faces warp ----
+    uint32_t e_phase = 0, p_phase = 0;
+    unsigned flags = 0;
+    k7f_faces<XDIR, LIT>(q, tm, bars, region, pool_sm, e_phase, p_phase, line0, lane, rl, flags);
+    __syncthreads();
+    if (bars->redo) {
+      k7f_faces<XDIR, LIT>(q, tm, bars, region, pool_sm, e_phase, p_phase, line0, lane, rl, flags);
+      __syncthreads();
+    }
+    gs_raise(q.status, flags);
+    return;
+  }
+  // ---- chain warp ----
+  if (lane == 0)
+    for (int s = 0; s < 3; ++s) gs_mbar_arrive(&bars->empty[s]);      // every stage starts empty
+  bool fast_allowed = true;
+  const GsRcp rt = gs_rcp_invariant(q.time, fast_allowed);
+  const double inv_time = 1.0 / q.time;
+  double2 *sc = q.scratch + (size_t)blockIdx.x * (size_t)n * 32;
+  unsigned flags = 0;
+  uint32_t ft_phase = 0;
+  {
+    bool ok = true;
+    unsigned fl = 0;
+    if (fast_allowed) {
+      ok = k7f_forward<XDIR, true>(q, bars, region, ft_phase, line0, lane, rl, rt, inv_time, sc, fl);
+      ok = __all_sync(0xffffffffu, ok);
+    } else {
+      k7f_forward<XDIR, false>(q, bars, region, ft_phase, line0, lane, rl, rt, inv_time, sc, fl);
+    }
+    if (lane == 0) bars->redo = ok ? 0 : 1;
+    __syncthreads();
+    if (!ok) {
+      fl = 0;
+      k7f_forward<XDIR, false>(q, bars, region, ft_phase, line0, lane, rl, rt, inv_time, sc, fl);
+      __syncthreads();
+    }
+    flags |= fl;
+  }
+  __threadfence();
+  gs_fence_proxy_async();
+  __syncwarp();
+  K7Ring r;
+  r.bars = bars->bwd;
+  r.stages = region;
+  r.phase = 0;
+  r.head = r.tail = 0;
+  const double u = k7_backward<XDIR, FUSE>(q, tm, r, otile, line0, act, lane, sc);
   if (XDIR && lane == 0) gs_bulk_wait_read<0>();
   if (act && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
   gs_raise(q.status, flags);

@@ -29,6 +29,13 @@ GS_TMA_DEV void gs_mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// transaction bytes announced without an arrival (the arrival comes later, from gs_mbar_arrive)
+GS_TMA_DEV void gs_mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+GS_TMA_DEV void gs_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs_smem_u32(bar)) : "memory");
+}
 // global -> shared, completion signalled on an mbarrier (bytes: multiple of 16, both addresses 16 B aligned)
 GS_TMA_DEV void gs_bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

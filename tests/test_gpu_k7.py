@@ -13,11 +13,15 @@ from helpers import assert_bit_equal
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def k7(ctx):
+@pytest.fixture(params=[1, 0], ids=["fused-faces", "separate-faces"])
+def k7(ctx, request):
+    """Both variants: k7f_sweep (faces by a producer warp inside the sweep) and k7_sweep after a k6_faces pass."""
     ctx.set_option("k7", 1)
+    ctx.set_option("k7_fuse", request.param)
+    ctx.k7_fuse = request.param
     yield ctx
     ctx.set_option("k7", 1)
+    ctx.set_option("k7_fuse", 1)
 
 
 def _snap_equal(g, o, what):
@@ -35,7 +39,7 @@ def test_k7_all_boundary_kinds(O, gs, k7, combo, dense):
     g.set_solver(gs.SOLVER_THOMAS)
     n0 = k7.launch_count
     g.xIter(900.0); o.xIter(900.0)
-    assert k7.launch_count - n0 == 3, "K7 = k6_ends + k6_faces + k7_sweep"
+    assert k7.launch_count - n0 == (2 if k7.k7_fuse else 3), "K7 = k6_ends [+ k6_faces] + sweep"
     assert_bit_equal(g.grid.result, o.result, combo + " xIter result")
     g.yIter(900.0); o.yIter(900.0)
     assert_bit_equal(g.grid.result, o.result, combo + " yIter result")
