@@ -1796,7 +1796,14 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   bool lit = true;
   for (int s4 = 0; s4 < 4 && lit; ++s4)
     lit = g->map_mode[s4] == GS_MAP_SINGLE && literal_const(ctx, ctx->spline_off[g->map_host[s4][0]], nullptr);
-  const bool fused = ctx->opt_k7_fuse && (lit || ctx->pool.size() * sizeof(double) <= K7F_POOL);
+  // what is staged in shared memory: the whole pool if it fits, else the one table of a SINGLE `apply` map
+  int stage_off = 0, stage_len = (int)ctx->pool.size();
+  if ((size_t)stage_len * sizeof(double) > K7F_POOL && g->map_mode[GS_SEL_APPLY] == GS_MAP_SINGLE) {
+    stage_off = ctx->spline_off[g->map_host[GS_SEL_APPLY][0]];
+    const int np = (int)ctx->pool[stage_off + 1];
+    stage_len = GS_HDR + (np + 1) + np * GS_PIECE;
+  }
+  const bool fused = ctx->opt_k7_fuse && (lit || (size_t)stage_len * sizeof(double) <= K7F_POOL);
   K6FacesParams fq;
   GS_TRY(launch_faces(g, time, xdir, nullptr, fq, nullptr, fused));
   K7Params q;
@@ -1812,6 +1819,7 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   q.face0 = fq.face0;
   q.pool = fq.sw.pool;
   q.pool_len = fq.sw.pool_len;
+  q.stage_off = stage_off; q.stage_len = stage_len;
   q.maps = fq.sw.maps;
   K7Maps tm;
   GS_TRY(k7_encode(&tm.F, fused ? (const void *)g->predict : (const void *)fq.F, g->cols, g->rows, xdir));
@@ -1824,8 +1832,15 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     if (xdir) kern = lit ? k7f_sweep<true, false, true> : k7f_sweep<true, false, false>;
     else if (fuse) kern = lit ? k7f_sweep<false, true, true> : k7f_sweep<false, true, false>;
     else kern = lit ? k7f_sweep<false, false, true> : k7f_sweep<false, false, false>;
-    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K7F_SMEM));
-    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    static void (*configured[8])(K7Params, const K7Maps) = {};
+    bool seen = false;
+    for (auto k : configured) seen = seen || k == kern;
+    if (!seen) {
+      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K7F_SMEM));
+      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      for (auto &k : configured)
+        if (!k) { k = kern; break; }
+    }
     kern<<<strips, 64, K7F_SMEM, ctx->stream>>>(q, tm);
   } else if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);

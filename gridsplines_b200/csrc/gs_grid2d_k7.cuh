@@ -61,6 +61,7 @@ struct K7Params {
   const double *face0;
   const double *pool;
   int pool_len;
+  int stage_off, stage_len;        // the part of the pool staged in shared memory: all of it, or the one table of a SINGLE map
   Maps2d maps;
 };
 
@@ -467,7 +468,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
   GsLitConst zl;
   zl.v = 0.0;
   if (LIT) zl.v = q.pool[off + GS_HDR + 3];
-  else z = k6_tab(pool_sm + off);
+  else z = k6_tab(pool_sm + (off - q.stage_off));
   auto face = [&](double p0, double p1, int i) -> double {
     double v;
     if (LIT) {
@@ -481,10 +482,10 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
     }
     if (!single) {
       off = map_off(q.maps, GS_SEL_APPLY, XDIR ? i : line, XDIR ? line : i, q.cols);
-      z = k6_tab(pool_sm + off);
+      z = k6_tab(pool_sm + (off - q.stage_off));
     }
     if (!k6_face_fast(z, p0, p1, v)) {
-      if (!k6_face_mid(pool_sm + off, p0, p1, &v)) v = k6_face_general(q.pool, off, p0, p1, q.status);
+      if (!k6_face_mid(pool_sm + (off - q.stage_off), p0, p1, &v)) v = k6_face_general(q.pool, off, p0, p1, q.status);
     }
     return v;
   };
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(64, 4) k7f_sweep(K7Params q, const __grid_cons
     if (XDIR) gs_tma_prefetch_desc(&tm.out);
   }
   if (!LIT)
-    for (int i = threadIdx.x; i < q.pool_len; i += blockDim.x) pool_sm[i] = q.pool[i];
+    for (int i = threadIdx.x; i < q.stage_len; i += blockDim.x) pool_sm[i] = q.pool[q.stage_off + i];
   gs_fence_proxy_async();
   __syncthreads();
   if (warp == 1) {
