@@ -1832,14 +1832,12 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     if (xdir) kern = lit ? k7f_sweep<true, false, true> : k7f_sweep<true, false, false>;
     else if (fuse) kern = lit ? k7f_sweep<false, true, true> : k7f_sweep<false, true, false>;
     else kern = lit ? k7f_sweep<false, false, true> : k7f_sweep<false, false, false>;
-    static void (*configured[8])(K7Params, const K7Maps) = {};
-    bool seen = false;
-    for (auto k : configured) seen = seen || k == kern;
-    if (!seen) {
+    // function attributes are per device: remembered per context
+    const void *key = reinterpret_cast<const void *>(kern);
+    if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K7F_SMEM));
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      for (auto &k : configured)
-        if (!k) { k = kern; break; }
+      ctx->configured.push_back(key);
     }
     kern<<<strips, 64, K7F_SMEM, ctx->stream>>>(q, tm);
   } else if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);

@@ -40,6 +40,7 @@ struct gs_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   uint64_t launches = 0;
+  std::vector<const void *> configured;   // kernels whose function attributes were set on this device
   unsigned eval_flags = 0;   // status word of the last gs_spline_eval_* call
   int refs = 0;        // live grids made from this context
   bool dead = false;   // gs_ctx_destroy was called while grids were still alive: freed with the last grid
