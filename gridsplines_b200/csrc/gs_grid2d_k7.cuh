@@ -507,23 +507,43 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
     p_phase ^= 1u << s;
     const double *P = reinterpret_cast<const double *>(region + K7F_P + s * K7F_PT);
     double *F = reinterpret_cast<double *>(st + K7_TILE) + lane;
-    if (c != 0 && i0 + K7_CH < n) {
-#pragma unroll 2
-      for (int j = 0; j < K7_CH; ++j) {
-        const double p0 = XDIR ? P[rl * 18 + j] : P[j * 32 + rl], p1 = XDIR ? P[rl * 18 + j + 1] : P[(j + 1) * 32 + rl];
-        F[j * 32] = face(p0, p1, i0 + j);
+    auto pred0 = [&](int j) { return XDIR ? P[rl * 18 + j] : P[j * 32 + rl]; };
+    if (c != 0 && i0 + K7_CH < n && single) {
+      // A single warp has nobody to hide its latencies behind: eight faces at a time go through the straight-line
+      // tier together (independent instruction streams the scheduler can interleave); the few that fall out of it
+      // -- equal temperatures, a straddled knot, clamps -- are redone one by one afterwards.
+#pragma unroll
+      for (int h = 0; h < K7_CH; h += 8) {
+        double v[8];
+        unsigned bad = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double p0 = pred0(h + j), p1 = pred0(h + j + 1);
+          bool good;
+          if (LIT) {
+            const double d = fabs(p0 - p1);      // max - min; (d * v) / d as gs_take_average(GsLitConst)
+            good = true;
+            v[j] = gs_div<true>(d * zl.v, gs_rcp<true>(d, good), good);
+          } else {
+            good = k6_face_fast(z, p0, p1, v[j]);
+          }
+          if (!good) bad |= 1u << j;
+        }
+        if (bad) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if ((bad >> j) & 1u) v[j] = face(pred0(h + j), pred0(h + j + 1), i0 + h + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) F[(h + j) * 32] = v[j];
       }
     } else {
 #pragma unroll 1
       for (int j = 0; j < len; ++j) {
         const int i = i0 + j;
         double v = 0.0;
-        if (i == 0) {
-          v = q.face0[line];                    // carry out of node 0 (k6_ends): co, or cond / cap after a heat-flow end
-        } else if (i < n - 1) {
-          const double p0 = XDIR ? P[rl * 18 + j] : P[j * 32 + rl], p1 = XDIR ? P[rl * 18 + j + 1] : P[(j + 1) * 32 + rl];
-          v = face(p0, p1, i);
-        }
+        if (i == 0) v = q.face0[line];          // carry out of node 0 (k6_ends): co, or cond / cap after a heat-flow end
+        else if (i < n - 1) v = face(pred0(j), pred0(j + 1), i);
         F[j * 32] = v;
       }
     }
