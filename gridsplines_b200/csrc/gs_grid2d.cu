@@ -1803,7 +1803,11 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     const int np = (int)ctx->pool[stage_off + 1];
     stage_len = GS_HDR + (np + 1) + np * GS_PIECE;
   }
-  const bool fused = ctx->opt_k7_fuse && (lit || (size_t)stage_len * sizeof(double) <= K7F_POOL);
+  // k7_fuse: 0 never; 1 (default) literal constants only -- MEASURED (B200): 4096^2 constants 0.87 ms/step fused against
+  // 1.24 with the faces pass, but Hermite tables 1.88 against 1.29 (16384^2: 9.4 against 8.65): ONE faces warp needs
+  // ~4500 clk for the 16 x 32 table faces of a chunk, the chain warp 2400; 2 = tables too (tested variant)
+  const bool fused = lit ? ctx->opt_k7_fuse >= 1
+                         : (ctx->opt_k7_fuse >= 2 && (size_t)stage_len * sizeof(double) <= K7F_POOL);
   K6FacesParams fq;
   GS_TRY(launch_faces(g, time, xdir, nullptr, fq, nullptr, fused));
   K7Params q;

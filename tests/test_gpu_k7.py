@@ -13,7 +13,7 @@ from helpers import assert_bit_equal
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["fused-faces", "separate-faces"])
+@pytest.fixture(params=[2, 0], ids=["fused-faces", "separate-faces"])
 def k7(ctx, request):
     """Both variants: k7f_sweep (faces by a producer warp inside the sweep) and k7_sweep after a k6_faces pass."""
     ctx.set_option("k7", 1)
