@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Iterable, Optional, Sequence
 
 import numpy as np
@@ -160,6 +161,92 @@ class Spline:
     @staticmethod
     def line(xl, yl, xu, yu) -> "Spline":
         return Spline.lines([(xl, yl), (xu, yu)])
+
+    @staticmethod
+    def lagrange2(points) -> "Spline":
+        """Quadratic Lagrange pieces (P/Lagrange2.scala:62-113): every window of three consecutive points gives one
+        parabola a x^2 + b x + c, coefficients by `polynomials` in its own operation order, evaluated about 0 by the
+        FMA Horner rule (:20-21) -- on the device a GS_CUBIC piece with x0 = 0, c3 = 0 (same doubles).
+        The reference lets consecutive windows overlap ((x_k, x_{k+2}) each); here window k owns [x_k, x_{k+1}) and
+        the last one runs to the last point."""
+        pts = Spline._sorted(points)
+        if len(pts) < 3:
+            raise ValueError("Must be 3 points")                     # IllegalArgumentException :67
+        knots, coefs = [], []
+        for (x0, y0), (x1, y1), (x2, y2) in zip(pts[:-2], pts[1:-1], pts[2:]):
+            d = [y0 / ((x0 - x1) * (x0 - x2)), y1 / ((x1 - x0) * (x1 - x2)), y2 / ((x2 - x0) * (x2 - x1))]
+            up = [[1.0, -(a + b), a * b] for a, b in ((x1, x2), (x0, x2), (x0, x1))]
+            fin = [0.0, 0.0, 0.0]
+            for k in range(3):
+                for t in range(3):
+                    fin[t] = fin[t] + up[k][t] * d[k]
+            a_, b_, c_ = fin                                         # (a, b, c) -> new Lagrange2(Array(c, b, a))
+            knots.append(x0)
+            coefs.append([c_, b_, a_, 0.0])
+        knots.append(pts[-1][0])
+        return Spline(CUBIC, knots, [0.0] * len(coefs), coefs)
+
+    @staticmethod
+    def lagrange3(points) -> "Spline":
+        """Natural cubic spline pieces (P/Lagrange3.scala:54-200, ListPassion.solve for the second-derivative terms):
+        piece k over [x_k, x_{k+1}] is cubicRuleOfHorner(x - low, d, c, b, a) (:33-34) -- a GS_CUBIC piece with
+        x0 = low.  The arithmetic follows the reference's list recursion literally."""
+        v = Spline._sorted(points)
+        n = len(v)
+        if n < 3:
+            raise ValueError("at least 3 points")
+        hk = lambda x2, x1: x2 - x1
+        f = lambda p1, p2: (p2[1] - p1[1]) / abs(p2[0] - p1[0]) if (p2[0] - p1[0]) != 0.0 else 0.0
+        vect = lambda t1, t2, t3: 3 * f(t2, t3) - 3 * f(t1, t2)
+        rows, vec = [], []
+        for i in range(n - 2):                                       # cCoefs :76-100
+            t1, t2, t3 = v[i], v[i + 1], v[i + 2]
+            h1, h2 = hk(t2[0], t1[0]), hk(t3[0], t2[0])
+            rows.append((h1, 2 * (h2 + h1), h2))
+            vec.append(vect(t1, t2, t3))
+        t1, t2 = v[n - 2], v[n - 1]
+        h1 = hk(t2[0], t1[0])
+        rows.append((h1, 2 * (0.0 + h1), 0.0))
+        vec.append(vect(t1, t2, t2))
+        # ListPassion.solve: forwardFirst / forwardUnit / forwardLast, backwardPassion; .head = all but the last value
+        _, c0, d0 = rows[0]
+        dl = [(-d0 / c0, vec[0] / c0)]
+        for (b, c, d), r in zip(rows[1:-1], vec[1:-1]):
+            assert abs(c) >= abs(d) + abs(b), "Passion is not correct or unstable"
+            big = c + b * dl[-1][0]
+            dl.append((-d / big, (r - b * dl[-1][1]) / big))
+        b, c, d = rows[-1]
+        big = c + b * dl[-1][0]
+        dl.append((0.0, (vec[-1] - b * dl[-1][1]) / big))
+        xs, prev = [], 0.0
+        for delta, lam in reversed(dl):
+            prev = delta * prev + lam
+            xs.append(prev)
+        sol = list(reversed(xs))
+        cc = sol[:-1]                                                # solve(...).head: the last unknown is split off
+        if len(cc) != n - 2:
+            raise ValueError("list of values size minus 2 must be more than c list size")
+        dd = []                                                      # dCoefs :103-125
+        for i in range(n - 1):
+            h = hk(v[i + 1][0], v[i][0])
+            if i == 0:
+                dd.append((cc[0] - 0.0) / 3 * h)
+            elif i == n - 2:
+                dd.append((0.0 - cc[i - 1]) / 3 * h)
+            else:
+                dd.append((cc[i - 1] - cc[i]) / 3 * h)
+        bb = []                                                      # bCoefs :127-139 (stops when c or d run out)
+        for i in range(min(n - 1, len(cc), len(dd))):
+            h = hk(v[i + 1][0], v[i][0])
+            bb.append(f(v[i], v[i + 1]) + cc[i] * _sq(h) - dd[i] * (h ** 3.0))
+        aa = [p[1] for p in v[1:]]                                   # aCoefs :141-143
+        knots, x0, coefs = [v[0][0]], [], []
+        for i in range(len(cc)):                                     # while (c.nonEmpty) :61-69
+            lo, hi = min(v[i][0], v[i + 1][0]), max(v[i][0], v[i + 1][0])
+            coefs.append([dd[i], cc[i], bb[i], aa[i]])
+            x0.append(lo)
+            knots.append(hi)
+        return Spline(CUBIC, knots, x0, coefs)
 
     @staticmethod
     def _sources(pts):
@@ -955,3 +1042,101 @@ def discTWithFlow(heatFlow, t0, r0, r1, k) -> float:
     rAtHalf = (r0 + r1) / 2.0
     coef = k * rAtHalf / (r1 - r0) * math.pi * 2.0
     return t0 - heatFlow / coef
+
+
+# ---- text output: TwoDGrid.write / toString (A/TwoDGrid.scala:62-133), XDim.toString (A/XDim.scala:17-23),
+# OneDGrid.writeGrid (A/OneDGrid.scala:37-63).  The JVM's two number formatters are restated from their documented
+# behaviour (no JVM exists in this image: tests/test_host_helpers.py pins known-answer strings).
+def java_number_format(x: float, max_fraction_digits: int) -> str:
+    """java.text.NumberFormat.getInstance(Locale.ROOT) with setMaximumFractionDigits(n): DecimalFormat "#,##0.###",
+    RoundingMode.HALF_EVEN applied to the EXACT binary value (JDK >= 8), grouping by three, no trailing zeros, "-0" for
+    a negative value that rounds to zero, "NaN" and the infinity sign for non-finite values."""
+    import decimal
+
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (math.inf, -math.inf):
+        return ("-" if x < 0 else "") + "∞"
+    neg = math.copysign(1.0, x) < 0
+    q = decimal.Decimal(abs(x)).quantize(decimal.Decimal(1).scaleb(-max_fraction_digits), rounding=decimal.ROUND_HALF_EVEN)
+    digits = f"{q:f}"
+    whole, _, frac = digits.partition(".")
+    frac = frac.rstrip("0")
+    groups = []
+    while len(whole) > 3:
+        groups.insert(0, whole[-3:])
+        whole = whole[:-3]
+    groups.insert(0, whole)
+    return ("-" if neg else "") + ",".join(groups) + ("." + frac if frac else "")
+
+
+def java_fixed(x: float, digits: int) -> str:
+    """Scala's f"$x%.3f" = java.util.Formatter %.nf: RoundingMode.HALF_UP applied to the decimal digits of
+    Double.toString (the shortest digits that round-trip, which is what repr() gives), always `digits` decimals."""
+    import decimal
+
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (math.inf, -math.inf):
+        return "-Infinity" if x < 0 else "Infinity"
+    q = decimal.Decimal(repr(x)).quantize(decimal.Decimal(1).scaleb(-digits), rounding=decimal.ROUND_HALF_UP)
+    s = f"{abs(q):f}"
+    return ("-" if math.copysign(1.0, x) < 0 else "") + s
+
+
+def _dim_to_string(d: "_Dim", sep: str = os.linesep) -> str:
+    """XDim.toString (A/XDim.scala:17-23)"""
+    return (f"X/Y\t\t|\t{java_fixed(d.low, 3)}\t|\t" + "\t".join(java_fixed(v, 3) for v in d.range)
+            + f"\t|\t{java_fixed(d.upp, 3)}\t|\t..." + sep)
+
+
+def twod_write(g: "TwoDGrid", writer, newline: str = os.linesep) -> None:
+    """TwoDGrid.write(writer) (:62-82): per row `format(rowCoord) format(g(row, 0)) ... ` + BufferedWriter.newLine()"""
+    a = g.grid.grid
+    for r in range(g.rows):
+        writer.write(" ".join([java_number_format(g.y.range[r], 3)] + [java_number_format(v, 3) for v in a[r]]))
+        writer.write(newline)
+
+
+def twod_to_string(g: "TwoDGrid", sep: str = os.linesep) -> str:
+    """TwoDGrid.toString (:86-133), quirks included: the lower-bound line comes first and ends with y.upp, the right
+    bound is printed with four decimals, the upper-bound line starts with y.upp."""
+    f3 = lambda v: java_fixed(v, 3)
+    xc = _dim_to_string(g.x, sep)
+    low, upp, left, right = g.bounds.low.get(), g.bounds.upp.get(), g.bounds.left.get(), g.bounds.right.get()
+    out = [xc]
+    out.append(f"{f3(g.y.low)}\t|\t...\t\t|\t" + "\t".join(f3(low[i]) for i in range(g.cols))
+               + f"\t|\t...\t\t|\t{f3(g.y.upp)}" + sep)
+    a = g.grid.grid
+    for r in range(g.rows):
+        yc = g.y.range[r]
+        out.append(f"{f3(yc)}\t|\t{f3(left[r])}\t|\t" + "\t".join(f3(v) for v in a[r])
+                   + f"\t|\t{java_fixed(right[r], 4)}\t|\t{f3(yc)}" + sep)
+    out.append(f"{f3(g.y.upp)}\t|\t...\t\t|\t" + "\t".join(f3(upp[i]) for i in range(g.cols))
+               + f"\t|\t...\t\t|\t{f3(g.y.upp)}" + sep)
+    out.append(xc)
+    return "".join(out)
+
+
+def oned_write_grid(g: "OneDGrid", at, path: str, newline: str = os.linesep) -> str:
+    """OneDGrid.writeGrid(at: LocalDateTime, path) (:37-63): `grid MONTH Dd Hh YEAR.dat`, a two-line header and one
+    `coord<TAB>temperature` line per node, every element followed by "\\r\\n" AND BufferedWriter.newLine() (sic).
+    `at` is a datetime; the file must already exist (StandardOpenOption.TRUNCATE_EXISTING without CREATE) in the
+    reference -- here it is created.  Returns the file name."""
+    os.makedirs(path, exist_ok=True)
+    name = os.path.join(path, f"grid {at.strftime('%B').upper()} {at.day}d {at.hour}h {at.year}.dat")
+    temps = g.grid
+    with open(name, "w", newline="") as f:
+        f.write("# One dimension grid output results\r\n# Coords \t Temperatures\r\n" + newline)
+        for x, t in zip(g.rangeX, temps):
+            f.write(f"{java_number_format(x, 2)}\t{java_number_format(t, 3)}\r\n" + newline)
+    return name
+
+
+TwoDGrid.write = twod_write
+TwoDGrid.toString = twod_to_string
+TwoDGrid.__str__ = lambda self: twod_to_string(self)
+_Dim.toString = _dim_to_string
+OneDGrid.writeGrid = oned_write_grid

@@ -569,3 +569,33 @@ def test_spline_quotient_matches_reference_resampling(O, gs, which, factory):
                          zip(gk._sum_arguments(gc, False), gk.apply(gk._sum_arguments(gc, False)),
                              gc.apply(gk._sum_arguments(gc, False)))]).apply(xs[:5]))
     assert gs.Spline.line(0.0, 1.0, 1.0, 2.0).combine(gs.Spline.line(5.0, 1.0, 6.0, 2.0), lambda a, b: a / b) is None
+
+
+def test_text_output_formats(gs, tmp_path):
+    """f-4: TwoDGrid.write / toString (A/TwoDGrid.scala:62-133) and OneDGrid.writeGrid (A/OneDGrid.scala:37-63)."""
+    import datetime
+    import io
+
+    x = gs.XDim(1.0, [2.0, 3.0, 4.0, 5.0], 6.0, gs.RADIAL)
+    y = gs.YDim(0.0, [10.0, 20.0], 30.0, gs.ORTHO)
+    g = gs.TwoDGrid(x, y, upp=(gs.Many, gs.Temp), low=(gs.One, gs.Temp), right=(gs.Many, gs.Temp), left=(gs.One, gs.Flow),
+                    coefs=gs.ConstantCoef(gs.Spline.const(1.5), gs.Spline.const(2.2e6), gs.Spline.const(1.5 / 2.2e6)))
+    g.grid.grid = np.array([[1234.5678, 7.0, 0.0005, -0.0004], [0.0625, 2.0, 54.44328715390563, 1e6]])
+    g.bounds.upp.update([1.0, 2.0, 3.0, 4.0]); g.bounds.low.update(9.5)
+    g.bounds.left.update(0.25); g.bounds.right.update([7.0, 8.12345])
+    buf = io.StringIO()
+    g.write(buf, newline="\n")
+    assert buf.getvalue() == "10 1,234.568 7 0.001 -0\n20 0.062 2 54.443 1,000,000\n"
+    s = g.toString(sep="\n").split("\n")
+    assert s[0] == "X/Y\t\t|\t1.000\t|\t2.000\t3.000\t4.000\t5.000\t|\t6.000\t|\t..."
+    assert s[1] == "0.000\t|\t...\t\t|\t9.500\t9.500\t9.500\t9.500\t|\t...\t\t|\t30.000"
+    assert s[2] == "10.000\t|\t0.250\t|\t1234.568\t7.000\t0.001\t-0.000\t|\t7.0000\t|\t10.000"
+    assert s[3] == "20.000\t|\t0.250\t|\t0.063\t2.000\t54.443\t1000000.000\t|\t8.1235\t|\t20.000"
+    assert s[4] == "30.000\t|\t...\t\t|\t1.000\t2.000\t3.000\t4.000\t|\t...\t\t|\t30.000"
+    assert s[5] == s[0]
+    o = gs.OneDGrid(0.0, [0.125, 0.25, 0.375], 0.5, gs.Spline.const(1e-6), 1.0)
+    o.grid = [4.0, 1234.5678, 0.5]
+    name = o.writeGrid(datetime.datetime(2026, 10, 20, 9, 30), str(tmp_path), newline="\n")
+    assert os.path.basename(name) == "grid OCTOBER 20d 9h 2026.dat"
+    assert open(name, newline="").read() == ("# One dimension grid output results\r\n# Coords \t Temperatures\r\n\n"
+                                             "0.12\t4\r\n\n0.25\t1,234.568\r\n\n0.38\t0.5\r\n\n")

@@ -76,3 +76,46 @@ def test_spline_undefined_is_flagged(gs, ctx):
         assert g3.status & gs.FLAG_SPLINE_UNDEFINED
     finally:
         ctx.set_option("const_hoist", 1)
+
+
+def _oracle_twin(O, s):
+    """The same table for the oracle, piece by piece (kind, lo, hi, x0, coefs)."""
+    np_ = len(s.x0)
+    return O.Spline.from_pieces([s.kind] * np_, s.knots[:-1], s.knots[1:], s.x0, s.coefs)
+
+
+@pytest.mark.parametrize("factory", ["lagrange2", "lagrange3"])
+def test_lagrange_tables(O, gs, factory):
+    """Lagrange tables (P/Lagrange2.scala, P/Lagrange3.scala) reach the device as cubic pieces (x0 = 0, c3 = 0 for the
+    parabolas; x0 = low for the cubics): point values, interval averages and a batched 1-D step with such a table as
+    the conductivity are the oracle's, bit for bit."""
+    pts = [(-20.0 + 10.0 * i, 1e-6 * (1.0 + 0.1 * README_RHO[i])) for i in range(11)]
+    s = getattr(gs.Spline, factory)(pts)
+    if factory == "lagrange2":       # every parabola interpolates its three points
+        for k in range(len(s.x0)):
+            c = s.coefs[k]
+            for x, y in pts[k:k + 3]:
+                assert abs((c[2] * x + c[1]) * x + c[0] - y) <= 1e-12 * abs(y) * 100
+    o = _oracle_twin(O, s)
+    ga, oa = gs.AlwaysDefinedSpline(s), O.AlwaysDefinedSpline(o)
+    r = np.random.default_rng(5)
+    hi_knot = float(s.knots[-1])
+    xs = np.concatenate([r.uniform(-30.0, hi_knot + 10.0, 400), s.knots, [-20.0, hi_knot]])
+    assert_bit_equal(ga(xs), np.array([oa(float(x)) for x in xs]), factory + " apply")
+    a, b = r.uniform(-25.0, hi_knot + 5.0, 300), r.uniform(-25.0, hi_knot + 5.0, 300)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    O.set_ascending_fold(True)
+    assert_bit_equal(ga.average(lo, hi), np.array([oa.average(float(p), float(q)) for p, q in zip(lo, hi)]),
+                     factory + " average")
+    # a batched 1-D step with the table as conductivity
+    n, nlines = 64, 40
+    rangeX = np.array([0.01 * (i + 1) for i in range(n)])
+    grid0 = r.uniform(-10.0, 60.0, (nlines, n))
+    lt, rt = r.uniform(10.0, 30.0, nlines), r.uniform(0.0, 10.0, nlines)
+    g = gs.BatchedOneDGrid(0.0, rangeX, 0.01 * (n + 1), s, 1.0, nlines=nlines)
+    g.upload(gs.GRID, grid0)
+    g.step(900.0, lt, rt, nsteps=3)
+    og, op = grid0.copy(), np.full((nlines, n), 4.0)
+    O.batch1d_step(O.ORTHO, 0.0, rangeX, 0.01 * (n + 1), o, 1.0, og, op, lt, rt, 900.0, nsteps=3, nthreads=2)
+    assert_bit_equal(g.download(gs.GRID), og, factory + " 1-D grid")
+    assert_bit_equal(g.download(gs.PREDICT), op, factory + " 1-D predict")
