@@ -5,6 +5,6 @@ from ._lib import (CONST, CUBIC, DENSE, FLAG_NONFINITE, FLAG_NOT_DOMINANT, FLAG_
                    MAP_SINGLE, ORTHO, PREDICT, RADIAL, RESULT, RIGHT, SEL_APPLY, SEL_CAP, SEL_TEMPCOND, SEL_THERM,
                    SOLVER_AUTO, SOLVER_PARTITIONED, SOLVER_THOMAS, SPARSE, TEMP, UPP, GsError)
 from .api import (AlwaysDefinedSpline, BatchedOneDGrid, RaggedLines, Coefficients, ConstantCoef, Context, DenseCoef, Flow, Many,
-                  One, OneDGrid, Ortho, PatchedXCoef, PatchedYCoef, PatchXCoef, PatchYCoef, Radial, Spline, Temp, TwoDGrid,
+                  One, OneDGrid, Ortho, ShardedTwoDGrid, PatchedXCoef, PatchedYCoef, PatchXCoef, PatchYCoef, Radial, Spline, Temp, TwoDGrid,
                   VarXCoef, VarXCoefByColumn, VarYCoef, XDim, YDim,
                   default_context, discHeatFlow, discTWithFlow, getRadialMidPoint, radialHeatFlow)

@@ -56,6 +56,21 @@ SIGNATURES = {
     "gs_grid1d_clear_status": (_vp,),
     "gs_grid1d_device_ptr": (_vp, C.c_int, _vpp, C.POINTER(C.c_int64)),
     "gs_grid1d_bytes_per_step": (_vp, _dp),
+    "gs_sharded2d_create": (C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _vpp),
+    "gs_sharded2d_destroy": (_vp,),
+    "gs_sharded2d_device_count": (_vp, _ip),
+    "gs_sharded2d_spline_create": (_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _ip),
+    "gs_sharded2d_set_map": (_vp, C.c_int, C.c_int, _ip),
+    "gs_sharded2d_set_bound": (_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int),
+    "gs_sharded2d_fill": (_vp, C.c_double),
+    "gs_sharded2d_upload": (_vp, C.c_int, _vp),
+    "gs_sharded2d_download": (_vp, C.c_int, _vp),
+    "gs_sharded2d_iteration": (_vp, C.c_double, C.c_int),
+    "gs_sharded2d_iteration_timed": (_vp, C.c_double, C.c_int, _dp),
+    "gs_sharded2d_synchronize": (_vp,),
+    "gs_sharded2d_status": (_vp, C.POINTER(C.c_uint32)),
+    "gs_sharded2d_launch_count": (_vp, C.POINTER(C.c_uint64)),
+    "gs_sharded2d_set_option": (_vp, C.c_char_p, C.c_int64),
     "gs_grid2d_create": (_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _vpp),
     "gs_grid2d_destroy": (_vp,),
     "gs_grid2d_set_map": (_vp, C.c_int, C.c_int, _ip),

@@ -1140,3 +1140,103 @@ TwoDGrid.toString = twod_to_string
 TwoDGrid.__str__ = lambda self: twod_to_string(self)
 _Dim.toString = _dim_to_string
 OneDGrid.writeGrid = oned_write_grid
+
+
+class ShardedTwoDGrid:
+    """ONE TwoDGrid on several GPUs of a box, driven by this process (gs_sharded2d_*, csrc/gs_sharded2d.cu): rows are
+    sharded over `devices`, the step's exchange happens inside the kernels over NVLink peer memory.  Same constructor
+    shape as TwoDGrid; `coefs_factory(register)` receives a function that registers a Spline on every device and
+    returns its id, and returns {selector: (mode, ids)} for the whole grid."""
+
+    def __init__(self, x: XDim, y: YDim, devices: Sequence[int], upp=(One, Temp), low=(One, Temp), right=(One, Temp),
+                 left=(One, Temp)):
+        self.x, self.y = x, y
+        self.cols, self.rows = x.colsNum, y.rowsNum
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        xv, yv = x.values, y.values
+        self._h = C.c_void_p()
+        L.check(L.lib().gs_sharded2d_create(len(dev), dev.ctypes.data_as(_ip), self.cols, self.rows, x.t, y.t, _p(xv),
+                                            _p(yv), C.byref(self._h)))
+        self._kinds = {UPP: upp, LOW: low, RIGHT: right, LEFT: left}
+        for side in (UPP, LOW, RIGHT, LEFT):
+            self.set_bound(side, 0.0)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib().gs_sharded2d_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register(self, spl: Spline, true_upper: bool = False) -> int:
+        """AlwaysDefinedSpline(spl) in every device's pool (clamps by the reference's literal rule, evaluated on the host
+        mirror of the piece formulas for Const tables, else through device 0 of the default context)."""
+        a = AlwaysDefinedSpline(spl, true_upper=true_upper)       # computes the clamps (default context)
+        out = C.c_int()
+        L.check(L.lib().gs_sharded2d_spline_create(self._h, spl.kind, spl.size, _p(spl.knots), _p(spl.x0),
+                                                   _p(np.ascontiguousarray(spl.coefs)), *a.clamps, C.byref(out)))
+        return out.value
+
+    def set_constant_coef(self, therm: Spline, cap: Spline, tempcond: Spline):
+        t, c, a = self.register(therm), self.register(cap), self.register(tempcond)
+        for sel, sid in ((SEL_APPLY, a), (SEL_THERM, t), (SEL_CAP, c), (SEL_TEMPCOND, a)):
+            self.set_map(sel, MAP_SINGLE, [sid])
+
+    def set_map(self, selector: int, mode: int, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        L.check(L.lib().gs_sharded2d_set_map(self._h, selector, mode, ids.ctypes.data_as(_ip)))
+
+    def set_bound(self, side: int, values):
+        rep, kind = self._kinds[side]
+        v = np.atleast_1d(_d(values))
+        L.check(L.lib().gs_sharded2d_set_bound(self._h, side, kind, rep, _p(v), len(v)))
+
+    def fill(self, v: float):
+        L.check(L.lib().gs_sharded2d_fill(self._h, v))
+
+    def upload(self, which: int, values):
+        v = _d(values)
+        assert v.size == self.rows * self.cols
+        L.check(L.lib().gs_sharded2d_upload(self._h, which, v.ctypes.data))
+
+    def download(self, which: int = GRID) -> np.ndarray:
+        out = np.empty((self.rows, self.cols))
+        L.check(L.lib().gs_sharded2d_download(self._h, which, out.ctypes.data))
+        return out
+
+    def upload_ptr(self, which: int, host_ptr: int):
+        L.check(L.lib().gs_sharded2d_upload(self._h, which, host_ptr))
+
+    def download_ptr(self, which: int, host_ptr: int):
+        L.check(L.lib().gs_sharded2d_download(self._h, which, host_ptr))
+
+    def iteration(self, time: float, nsteps: int = 1):
+        L.check(L.lib().gs_sharded2d_iteration(self._h, time, nsteps))
+
+    def iteration_timed(self, time: float, nsteps: int = 1) -> float:
+        """nsteps iterations; returns the device-measured time in ms (max over the devices)."""
+        ms = C.c_double()
+        L.check(L.lib().gs_sharded2d_iteration_timed(self._h, time, nsteps, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        L.check(L.lib().gs_sharded2d_synchronize(self._h))
+
+    def set_option(self, name: str, value: int):
+        L.check(L.lib().gs_sharded2d_set_option(self._h, name.encode(), value))
+
+    @property
+    def status(self) -> int:
+        f = C.c_uint32()
+        L.check(L.lib().gs_sharded2d_status(self._h, C.byref(f)))
+        return f.value
+
+    @property
+    def launch_count(self) -> int:
+        c = C.c_uint64()
+        L.check(L.lib().gs_sharded2d_launch_count(self._h, C.byref(c)))
+        return c.value

@@ -1585,6 +1585,8 @@ struct K6Split {
   double *exported;                      // device, [6][cols]
   const double *gathered;                // device, [nranks][6][cols]
   int nranks, rank;
+  double *const *export_peer = nullptr;  // single-process multi-GPU: one destination per device (see K6Params)
+  int nexport_peer = 0;
 };
 
 // 1. faces + end rows of a direction (reads predict, rhs; every spline evaluation of the sweep happens here).  Shared by
@@ -1695,6 +1697,8 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
   q.fm1 = g->k6_split;
   q.cdw = g->k6_split ? g->k6_split + nl_pad : nullptr;
   q.exported = split ? split->exported : nullptr;
+  q.nexport_peer = split ? split->nexport_peer : 0;
+  for (int t = 0; t < q.nexport_peer; ++t) q.export_peer[t] = split->export_peer[t];
   q.gathered = split ? split->gathered : nullptr;
   q.nranks = split ? split->nranks : 1;
   q.rank = split ? split->rank : 0;
@@ -1919,6 +1923,25 @@ extern "C" int gs_grid2d_yiter_update_begin(gs_grid2d *g, double time, const voi
              "a lower HeatFlow bound is not supported on a sharded grid (it reads the neighbouring column's last row)");
   GS_TRY(materialise_result(g));
   K6Split sp{K6_BEGIN, (const double *)halo_prev, (const double *)halo_next, (double *)exported, nullptr, 1, 0};
+  GS_TRY(launch_k6(g, time, false, &sp));
+  g->k6_split_open = true;
+  return GS_OK;
+}
+// begin with the export written straight into several (peer) destinations: used by gs_sharded2d
+int gs_grid2d_split_begin_peers(gs_grid2d *g, double time, const double *halo_prev, const double *halo_next,
+                                double *const *dsts, int ndst) {
+  GS_REQUIRE(g && dsts && ndst >= 1 && ndst <= GS_MAX_SHARDS, "bad peer destinations");
+  GS_TRY(gs_ctx_use(g->ctx));
+  GS_REQUIRE(g->solver != GS_SOLVER_THOMAS && g->ctx->opt_k6 && g->rows >= 16, "the split y sweep needs K6 and at least 16 local rows");
+  {
+    int m, S;
+    k6_shape(g->ctx, g->rows, &m, &S);
+    GS_REQUIRE(S >= 2 && S <= 16 && k6_smem(g->ctx, false, S) <= g->ctx->smem_optin, "local rows do not fit the K6 shape");
+  }
+  GS_TRY(materialise_result(g));
+  K6Split sp{K6_BEGIN, halo_prev, halo_next, dsts[0], nullptr, 1, 0};
+  sp.export_peer = dsts;
+  sp.nexport_peer = ndst;
   GS_TRY(launch_k6(g, time, false, &sp));
   g->k6_split_open = true;
   return GS_OK;

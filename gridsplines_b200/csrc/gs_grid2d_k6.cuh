@@ -14,6 +14,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#define GS_MAX_SHARDS 16
+
 // ---- faces -------------------------------------------------------------------------------------------------------
 struct K6FacesParams {
   Sweep2dParams sw;      // predict, rhs, coefs, bounds, maps, pool, time, geometry of the swept direction
@@ -252,6 +254,10 @@ struct K6Params {
   const double *fm1;       // [nlines] face above node 0 (open first end)
   double *cdw;             // [S][3][nlines padded]: the local reduced system after elimination, E_k = c E_{k+1} + d + w L0
   double *exported;        // [6][nlines]: this rank as ONE segment: C, D, W of its last node and P, Q, R of its first
+  // single-process multi-GPU (gs_sharded2d): the export goes straight into every device's gathered[] slot of this rank
+  // -- peer-to-peer stores over NVLink from inside the elimination kernel, no collective afterwards
+  double *export_peer[GS_MAX_SHARDS];
+  int nexport_peer;
   const double *gathered;  // [nranks][6][nlines]
   int nranks, rank;
   int csize;               // CTAs per strip (thread-block cluster): the line's segments are spread over csize x S warps
@@ -591,12 +597,16 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       }
       if (MODE == K6_BEGIN) {
         if (act) {
-          double *ex = q.exported + line;
           const size_t nlp = (size_t)q.nlines;
-          ex[0 * nlp] = c; ex[1 * nlp] = d; ex[2 * nlp] = w;             // E_last = c X + d + w L0
-          ex[3 * nlp] = P0 * Pc;                                        // x_first = P E_last + Q + R L0
-          ex[4 * nlp] = fma(P0, Qc, Q0);
-          ex[5 * nlp] = fma(P0, Rc, R0);
+          const double e3 = P0 * Pc, e4 = fma(P0, Qc, Q0), e5 = fma(P0, Rc, R0);
+          const int ndst = q.nexport_peer > 0 ? q.nexport_peer : 1;
+          for (int t = 0; t < ndst; ++t) {
+            double *ex = (q.nexport_peer > 0 ? q.export_peer[t] : q.exported) + line;
+            ex[0 * nlp] = c; ex[1 * nlp] = d; ex[2 * nlp] = w;           // E_last = c X + d + w L0
+            ex[3 * nlp] = e3;                                           // x_first = P E_last + Q + R L0
+            ex[4 * nlp] = e4;
+            ex[5 * nlp] = e5;
+          }
         }
         for (int kk = 0; kk < ST; ++kk) {
           const double *sk = seg_at(kk);

@@ -85,6 +85,7 @@ typedef struct gs_ctx gs_ctx;
 typedef struct gs_grid1d gs_grid1d;
 typedef struct gs_grid2d gs_grid2d;
 typedef struct gs_ragged gs_ragged;
+typedef struct gs_sharded2d gs_sharded2d;
 
 int gs_version(void);
 const char *gs_last_error(void);
@@ -221,6 +222,34 @@ int gs_ragged_upload(gs_ragged *g, int which, const double *host);      /* GS_GR
 int gs_ragged_download(gs_ragged *g, int which, double *host);
 int gs_ragged_iteration(gs_ragged *g, double time, const double *upper, const double *lower);   /* nlines each */
 int gs_ragged_status(gs_ragged *g, uint32_t *flags);
+
+/* ---- ONE TwoDGrid on several GPUs of a box, owned by one host process (the multi-device form of the boundary, SURVEY
+ * 8(b)/(e)): rows sharded over the devices, x sweep local, y sweep = the partitioned elimination continued across the
+ * devices.  The exchange of a step (six doubles per column and device + one halo row of `predict` each way) is done by
+ * the kernels themselves over NVLink peer memory; the host only orders the devices' streams with events.  Tolerance
+ * solver family (GS_SOLVER_PARTITIONED semantics).  devices == NULL: devices 0 .. ndev-1.  rows % ndev == 0.
+ * Replaces TwoDGrid(x, y)(...)(coefs) + iteration (A/TwoDGrid.scala:254-258, 553-574) when one grid spans GPUs. ---- */
+#define GS_MAX_SHARDS_ABI 16
+int gs_sharded2d_create(int ndev, const int *devices, int cols, int rows, int xdir, int ydir, const double *xvalues,
+                        const double *yvalues, gs_sharded2d **out);
+int gs_sharded2d_destroy(gs_sharded2d *s);
+int gs_sharded2d_device_count(gs_sharded2d *s, int *ndev);
+/* registers the table in every device's pool; one id for all */
+int gs_sharded2d_spline_create(gs_sharded2d *s, int kind, int npieces, const double *knots, const double *x0,
+                               const double *coefs, double lowerX, double upperX, double lowerY, double upperY,
+                               int *id_out);
+int gs_sharded2d_set_map(gs_sharded2d *s, int selector, int mode, const int *ids);       /* ids of the WHOLE grid */
+int gs_sharded2d_set_bound(gs_sharded2d *s, int side, int kind, int rep, const double *values, int n);
+int gs_sharded2d_fill(gs_sharded2d *s, double value);
+int gs_sharded2d_upload(gs_sharded2d *s, int which, const double *host);                  /* rows x cols, row-major */
+int gs_sharded2d_download(gs_sharded2d *s, int which, double *host);
+int gs_sharded2d_iteration(gs_sharded2d *s, double time, int nsteps);
+/* the same, timed on the devices (events on every device's stream): *ms_max = the longest device interval */
+int gs_sharded2d_iteration_timed(gs_sharded2d *s, double time, int nsteps, double *ms_max);
+int gs_sharded2d_synchronize(gs_sharded2d *s);
+int gs_sharded2d_status(gs_sharded2d *s, uint32_t *flags);
+int gs_sharded2d_launch_count(gs_sharded2d *s, uint64_t *count);
+int gs_sharded2d_set_option(gs_sharded2d *s, const char *name, int64_t value);
 
 #ifdef __cplusplus
 }
