@@ -214,17 +214,21 @@ def _field2d(torch, n, which):
     return f
 
 
-def _time_steps(torch, stream, fn, steps, warmup):
+def _time_steps(torch, stream, fn, steps, warmup, reps=3):
+    """ms per call: `warmup` untimed calls, then the median of `reps` timed groups of `steps` calls (CUDA events)."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        fn()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1) / steps)
+    return float(np.median(out))
 
 
 def _errs(torch, a, b):
@@ -384,17 +388,21 @@ def bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local, steps=5, n
     sg = SpikeShardedTwoDGrid(mk, xv, yv, bounds, world, rank)
     mine = full[sg.r0:sg.r0 + sg.rl].contiguous()
     sg.set_local_rows(mine, mine.clone())
-    sg.iteration(TIME_STEP, nsteps=2)
+    sg.iteration(TIME_STEP, nsteps=3)
     torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    sg.iteration(TIME_STEP, nsteps=steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    runs = []
+    for _ in range(3):          # three timed groups, the median is reported (2 + 3 + 3 * steps steps in all)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sg.iteration(TIME_STEP, nsteps=steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        runs.append(float(t.item()))
+    ms = float(np.median(runs))
+    total_steps = 3 + 3 * steps
     rows = sg.local_rows(0)
     gathered = [torch.empty_like(rows) for _ in range(world)] if rank == 0 else None
     dist.gather(rows, gathered, dst=0)
@@ -404,17 +412,17 @@ def bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local, steps=5, n
         del gathered
         one = SpikeShardedTwoDGrid(mk, xv, yv, bounds, 1, 0)            # the same driver on one GPU
         one.set_local_rows(full.clone(), full.clone())
-        one.iteration(TIME_STEP, nsteps=2)
+        one.iteration(TIME_STEP, nsteps=3)
         torch.cuda.synchronize()
         e0.record(stream)
-        one.iteration(TIME_STEP, nsteps=steps)
+        one.iteration(TIME_STEP, nsteps=3 * steps)
         e1.record(stream)
         torch.cuda.synchronize()
-        ms1 = e0.elapsed_time(e1) / steps
+        ms1 = e0.elapsed_time(e1) / (3 * steps)
         f1, el1 = _errs(torch, got, one.local_rows(0))
         del one
         ex = _grid2d(gs, ctx, torch, "C4", n, gs.SOLVER_THOMAS, full)   # and the exact solver, same number of steps
-        ex.iteration(TIME_STEP, nsteps=2 + steps)
+        ex.iteration(TIME_STEP, nsteps=total_steps)
         t_ex = torch.empty((n, n), dtype=torch.float64, device="cuda")
         ex.copy_to_device(gs.GRID, t_ex.data_ptr())
         torch.cuda.synchronize()
@@ -422,14 +430,49 @@ def bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local, steps=5, n
         ex.close()
         cells = float(n) * n
         out = {"workload": f"C4 {n}x{n} row-sharded over {world} GPUs, reduced-system (SPIKE) exchange", "n_gpus": world,
-               "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "n1_ms_per_step": ms1,
+               "ms_per_step": ms, "ms_per_step_runs": runs, "updates_per_s": cells / (ms * 1e-3), "n1_ms_per_step": ms1,
                "efficiency_vs_n1": ms1 / (ms * world), "scaling": "strong",
                "collective": "ncclAllGather", "collective_bytes_per_step_per_rank": int((6 + 2) * n * 8 * world),
                "error_vs_n1_same_solver": {"field": f1, "elementwise": el1},
-               "error_vs_exact_solver_n1": {"field": f2, "elementwise": el2, "steps": 2 + steps},
+               "error_vs_exact_solver_n1": {"field": f2, "elementwise": el2, "steps": total_steps},
                "solver": "K6 split sweep (tolerance family)"}
     dist.barrier()
     return out
+
+
+def bench_c4_strong_abi(gs, torch, world, rank, steps=5, n=16384):
+    """The same C4 problem through gs_sharded2d_* (the multi-device C ABI a single JVM process would call): rank 0 alone
+    drives all `world` GPUs -- the exchange is done by the elimination kernels over NVLink peer memory, no NCCL -- while
+    the other ranks wait at the barrier that follows."""
+    if rank != 0:
+        return None
+    x = gs.XDim(0.05, 0.05 * 1.0005 ** np.arange(1, n + 1), 0.05 * 1.0005 ** (n + 1), gs.RADIAL)
+    y = gs.YDim(0.0, 0.01 * np.arange(1, n + 1), 0.01 * (n + 1), gs.ORTHO)
+    many = (gs.Many, gs.Temp)
+    T = [-20.0 + 10.0 * i for i in range(11)]
+    k = gs.Spline.m1Hermite3([(t, 1.0 + 0.1 * q) for t, q in zip(T, RHO)])
+    c = gs.Spline.m1Hermite3([(t, 2.0e6 + 1.0e5 * q) for t, q in zip(T, RHO)])
+    field = _field2d(torch, n, "C4").cpu().pin_memory()
+    res = {}
+    for ndev in (world, 1):
+        s = gs.ShardedTwoDGrid(x, y, list(range(ndev)), upp=many, low=many, right=many, left=many)
+        s.set_constant_coef(k, c, k / c)
+        for side, v in ((gs.UPP, 7.0), (gs.LOW, 7.0), (gs.RIGHT, 7.0), (gs.LEFT, 30.0)):
+            s.set_bound(side, v)
+        s.upload_ptr(gs.GRID, field.data_ptr())
+        s.upload_ptr(gs.PREDICT, field.data_ptr())
+        s.iteration(TIME_STEP, nsteps=3)
+        l0 = s.launch_count
+        runs = [s.iteration_timed(TIME_STEP, nsteps=steps) / steps for _ in range(3)]
+        res[ndev] = (float(np.median(runs)), runs, (s.launch_count - l0) / (3 * steps), s.status)
+        s.close()
+    ms, runs, launches, status = res[world]
+    cells = float(n) * n
+    return {"workload": f"C4 {n}x{n} row-sharded over {world} GPUs through gs_sharded2d_* (one process, peer-memory exchange)",
+            "n_gpus": world, "ms_per_step": ms, "ms_per_step_runs": runs, "updates_per_s": cells / (ms * 1e-3),
+            "n1_ms_per_step": res[1][0], "efficiency_vs_n1": res[1][0] / (ms * world), "scaling": "strong",
+            "collective": None, "exchange": "peer-to-peer stores from k6_sweep<K6_BEGIN>, halo rows read in place, stream events",
+            "kernel_launches_per_step": launches, "status": int(status | res[1][3]), "solver": "K6 split sweep (tolerance family)"}
 
 
 def bench_c5_strong(gs, torch, dist, stream, ctx, world, rank, peak, steps=5, lines=4096, n=65536):
@@ -441,24 +484,27 @@ def bench_c5_strong(gs, torch, dist, stream, ctx, world, rank, peak, steps=5, li
     grid0 = r.uniform(0.0, 30.0, (count, n))
     lt, rt = r.uniform(10.0, 30.0, count), r.uniform(0.0, 10.0, count)
     g = _c5_grid(gs, ctx, count, n, gs.SOLVER_AUTO, grid0, lt, rt)
-    g.step(TIME_STEP, nsteps=2)
+    g.step(TIME_STEP, nsteps=3)
     torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    g.step(TIME_STEP, nsteps=steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    runs = []
+    for _ in range(3):
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.step(TIME_STEP, nsteps=steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        runs.append(float(t.item()))
+    ms = float(np.median(runs))
     status = g.status
     g.close()
     out = None
     if rank == 0:
         one = bench_c5(gs, ctx, torch, stream, peak, steps=steps, lines=lines, n=n, parity=False)
         out = {"workload": f"C5 {lines} lines x {n} nodes, lines split over {world} GPUs", "n_gpus": world,
-               "lines_per_gpu": count, "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
+               "lines_per_gpu": count, "ms_per_step": ms, "ms_per_step_runs": runs, "updates_per_s": float(lines) * n / (ms * 1e-3),
                "n1_ms_per_step": one["ms_per_step"], "efficiency_vs_n1": one["ms_per_step"] / (ms * world),
                "scaling": "strong", "collective": None, "status": int(status)}
     dist.barrier()
@@ -583,7 +629,17 @@ def run_ours(args):
                         configs[name] = {"error": f"{type(exc).__name__}: {exc}"}
                     torch.cuda.empty_cache()
         else:
+            def abi():
+                out = None
+                try:
+                    out = bench_c4_strong_abi(gs, torch, world, rank)
+                except Exception as exc:
+                    out = {"error": f"{type(exc).__name__}: {exc}"}
+                dist.barrier()
+                return out
+
             for name, fn in (("c4_strong", lambda: bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local)),
+                             ("c4_strong_abi", abi),
                              ("c5_strong", lambda: bench_c5_strong(gs, torch, dist, stream, ctx, world, rank, peak))):
                 if "ALL" in want or name.upper().split("_")[0] in want:
                     strong[name] = fn()
