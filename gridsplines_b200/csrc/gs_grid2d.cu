@@ -1836,10 +1836,12 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   GS_TRY(k7_encode(&tm.out, g->result, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.pred, g->predict, g->cols, g->rows, xdir, true));
   if (fused) {
+    // literal constants: one faces warp keeps up with the chain warp; tables: two (each takes half of a chunk's nodes)
     void (*kern)(K7Params, const K7Maps);
-    if (xdir) kern = lit ? k7f_sweep<true, false, true> : k7f_sweep<true, false, false>;
-    else if (fuse) kern = lit ? k7f_sweep<false, true, true> : k7f_sweep<false, true, false>;
-    else kern = lit ? k7f_sweep<false, false, true> : k7f_sweep<false, false, false>;
+    if (xdir) kern = lit ? k7f_sweep<true, false, true, 1> : k7f_sweep<true, false, false, 2>;
+    else if (fuse) kern = lit ? k7f_sweep<false, true, true, 1> : k7f_sweep<false, true, false, 2>;
+    else kern = lit ? k7f_sweep<false, false, true, 1> : k7f_sweep<false, false, false, 2>;
+    const int threads = lit ? 64 : 96;
     // function attributes are per device: remembered per context
     const void *key = reinterpret_cast<const void *>(kern);
     if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
@@ -1847,7 +1849,7 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       ctx->configured.push_back(key);
     }
-    kern<<<strips, 64, K7F_SMEM, ctx->stream>>>(q, tm);
+    kern<<<strips, threads, K7F_SMEM, ctx->stream>>>(q, tm);
   } else if (xdir) k7_sweep<true, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   else if (fuse) k7_sweep<false, true><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);
   else k7_sweep<false, false><<<strips, 32, K7_SMEM, ctx->stream>>>(q, tm);

@@ -374,6 +374,7 @@ struct K7FBars {
   uint64_t ft[3];        // (F, rhs, cf) of a chunk ready: tx bytes of the loads + 1 arrival (faces warp)
   uint64_t empty[3];     // the chain warp is done with the stage
   uint64_t pin[3];       // predict tile landed
+  uint64_t pdone[3];     // every faces warp is done with the predict tile (NFW > 1)
   int redo;              // the forward pass is repeated with the native division
 };
 
@@ -449,12 +450,16 @@ GS_DEV bool k7f_forward(const K7Params &q, K7FBars *bars, unsigned char *region,
   return ok;
 }
 
-// the faces warp's pass over all chunks of the strip
-template <bool XDIR, bool LIT>
+// A faces warp's pass over all chunks of the strip.  NFW faces warps share every chunk: warp fw evaluates the faces of
+// nodes [fw * 16 / NFW, (fw + 1) * 16 / NFW) of the chunk; warp 0 issues all loads.
+template <bool XDIR, bool LIT, int NFW>
 GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsigned char *region, const double *pool_sm,
-                      uint32_t &e_phase, uint32_t &p_phase, int line0, int lane, int rl, unsigned &flags) {
+                      uint32_t &e_phase, uint32_t &p_phase, uint32_t &d_phase, int fw, int line0, int lane, int rl,
+                      unsigned &flags) {
+  constexpr int PER = K7_CH / NFW;
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
   const int line = line0 + rl;
+  const int j0 = fw * PER;
   auto issue_p = [&](int c) {
     if (lane == 0) {
       const int p = c % 3, i0 = c * K7_CH;
@@ -489,7 +494,8 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
     }
     return v;
   };
-  for (int c = 0; c < min(3, NC); ++c) issue_p(c);
+  if (fw == 0)
+    for (int c = 0; c < min(3, NC); ++c) issue_p(c);
   int s = 0;
 #pragma unroll 1
   for (int c = 0; c < NC; ++c) {
@@ -498,7 +504,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
     gs_mbar_wait_bounded(&bars->empty[s], (e_phase >> s) & 1u, q.status);
     e_phase ^= 1u << s;
     unsigned char *st = region + s * K7F_FT;
-    if (lane == 0) {
+    if (fw == 0 && lane == 0) {
       gs_mbar_expect_tx_only(&bars->ft[s], (uint32_t)(K7_TILE + len * 16));
       gs_tma_load_2d(st, &tm.rhs, XDIR ? i0 : line0, XDIR ? line0 : i0, &bars->ft[s]);
       gs_bulk_g2s(region + K7F_CF + s * 256, q.coefs + 2 * (size_t)i0, (uint32_t)len * 16u, &bars->ft[s]);
@@ -513,7 +519,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
       // tier together (independent instruction streams the scheduler can interleave); the few that fall out of it
       // -- equal temperatures, a straddled knot, clamps -- are redone one by one afterwards.
 #pragma unroll
-      for (int h = 0; h < K7_CH; h += 8) {
+      for (int h = j0; h < j0 + PER; h += 8) {
         double v[8];
         unsigned bad = 0;
 #pragma unroll
@@ -539,7 +545,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
       }
     } else {
 #pragma unroll 1
-      for (int j = 0; j < len; ++j) {
+      for (int j = j0; j < min(len, j0 + PER); ++j) {
         const int i = i0 + j;
         double v = 0.0;
         if (i == 0) v = q.face0[line];          // carry out of node 0 (k6_ends): co, or cond / cap after a heat-flow end
@@ -548,14 +554,26 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
       }
     }
     __syncwarp();
-    if (lane == 0) gs_mbar_arrive(&bars->ft[s]);          // release: the F tile is visible to the chain warp
-    if (c + 3 < NC) issue_p(c + 3);                        // the predict tile is free again
+    if (lane == 0) {
+      gs_mbar_arrive(&bars->ft[s]);                        // release: this warp's part of the F tile is visible
+      if (NFW > 1) gs_mbar_arrive(&bars->pdone[s]);        // ... and it is done with the predict tile
+    }
+    if (fw == 0 && c + 3 < NC) {
+      if (NFW > 1) {   // every faces warp has read the predict tile
+        gs_mbar_wait_bounded(&bars->pdone[s], (d_phase >> s) & 1u, q.status);
+        d_phase ^= 1u << s;
+      }
+      issue_p(c + 3);
+    } else if (fw == 0 && NFW > 1) {
+      gs_mbar_wait_bounded(&bars->pdone[s], (d_phase >> s) & 1u, q.status);   // keeps the phase bits in step
+      d_phase ^= 1u << s;
+    }
     s = (s == 2) ? 0 : s + 1;
   }
 }
 
-template <bool XDIR, bool FUSE, bool LIT>
-__global__ void __launch_bounds__(64, 4) k7f_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
+template <bool XDIR, bool FUSE, bool LIT, int NFW>
+__global__ void __launch_bounds__(32 + 32 * NFW, 4) k7f_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
   extern __shared__ unsigned char k7raw[];
   unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -570,9 +588,10 @@ __global__ void __launch_bounds__(64, 4) k7f_sweep(K7Params q, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&bars->bwd[s], 1);
     for (int s = 0; s < 3; ++s) {
-      gs_mbar_init(&bars->ft[s], 1);
+      gs_mbar_init(&bars->ft[s], NFW);
       gs_mbar_init(&bars->empty[s], 1);
       gs_mbar_init(&bars->pin[s], 1);
+      gs_mbar_init(&bars->pdone[s], NFW);
     }
     bars->redo = 0;
     gs_mbar_init_fence();
@@ -585,14 +604,14 @@ __global__ void __launch_bounds__(64, 4) k7f_sweep(K7Params q, const __grid_cons
     for (int i = threadIdx.x; i < q.stage_len; i += blockDim.x) pool_sm[i] = q.pool[q.stage_off + i];
   gs_fence_proxy_async();
   __syncthreads();
-  if (warp == 1) {
-    // ---- faces warp ----
-    uint32_t e_phase = 0, p_phase = 0;
+  if (warp >= 1) {
+    // ---- faces warps ----
+    uint32_t e_phase = 0, p_phase = 0, d_phase = 0;
     unsigned flags = 0;
-    k7f_faces<XDIR, LIT>(q, tm, bars, region, pool_sm, e_phase, p_phase, line0, lane, rl, flags);
+    k7f_faces<XDIR, LIT, NFW>(q, tm, bars, region, pool_sm, e_phase, p_phase, d_phase, warp - 1, line0, lane, rl, flags);
     __syncthreads();
     if (bars->redo) {
-      k7f_faces<XDIR, LIT>(q, tm, bars, region, pool_sm, e_phase, p_phase, line0, lane, rl, flags);
+      k7f_faces<XDIR, LIT, NFW>(q, tm, bars, region, pool_sm, e_phase, p_phase, d_phase, warp - 1, line0, lane, rl, flags);
       __syncthreads();
     }
     gs_raise(q.status, flags);
