@@ -1807,9 +1807,10 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
     const int np = (int)ctx->pool[stage_off + 1];
     stage_len = GS_HDR + (np + 1) + np * GS_PIECE;
   }
-  // k7_fuse: 0 never; 1 (default) literal constants only -- MEASURED (B200): 4096^2 constants 0.87 ms/step fused against
-  // 1.24 with the faces pass, but Hermite tables 1.88 against 1.29 (16384^2: 9.4 against 8.65): ONE faces warp needs
-  // ~4500 clk for the 16 x 32 table faces of a chunk, the chain warp 2400; 2 = tables too (tested variant)
+  // k7_fuse: 0 never; 1 literal constants only; 2 (default) tables too.  MEASURED (B200, ms/step, fused against the
+  // separate faces pass): 4096^2 constants 0.87 / 1.24; 4096^2 Hermite tables 1.25 / 1.29 with two faces warps (one
+  // faces warp: 1.88 -- it needs ~4500 clk for the 16 x 32 table faces of a chunk, the chain warp 2400); 16384^2 Hermite
+  // tables 7.14 / 8.66.
   const bool fused = lit ? ctx->opt_k7_fuse >= 1
                          : (ctx->opt_k7_fuse >= 2 && (size_t)stage_len * sizeof(double) <= K7F_POOL);
   K6FacesParams fq;

@@ -72,7 +72,7 @@ struct gs_ctx {
   int opt_k6_fuse = 0;          // K6: the sweep evaluates the faces along its lines itself (no separate faces pass); measured slower, off
   int opt_k6_cluster = 1;       // K6: give a strip to a cluster of 2 / 4 CTAs when strips alone would not fill the chip
   int64_t opt_auto_exact = 1;   // AUTO: tables / maps take the exact K7 instead of the tolerance family (K6)
-  int64_t opt_k7_fuse = 1;      // K7: faces evaluated inside the sweep by a producer warp (k7f_sweep): 0 never, 1 literal constants, 2 tables too
+  int64_t opt_k7_fuse = 2;      // K7: faces evaluated inside the sweep by a producer warp (k7f_sweep): 0 never, 1 literal constants, 2 tables too
   int64_t opt_k7 = 1;           // K7: exact sweeps from precomputed faces (0: first-draft k_xsweep / k_ysweep)
   int64_t opt_host_chunk_mb = 64;
   int64_t opt_ck_block = 16;

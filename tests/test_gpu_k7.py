@@ -21,7 +21,7 @@ def k7(ctx, request):
     ctx.k7_fuse = request.param
     yield ctx
     ctx.set_option("k7", 1)
-    ctx.set_option("k7_fuse", 1)
+    ctx.set_option("k7_fuse", 2)
 
 
 def _snap_equal(g, o, what):
