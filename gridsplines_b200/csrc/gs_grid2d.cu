@@ -813,6 +813,7 @@ __global__ void __launch_bounds__(128, 5) k_part_C(PartParams q) {
 
 #include "gs_grid2d_k6.cuh"
 #include "gs_grid2d_k7.cuh"
+#include "gs_grid2d_k5t.cuh"
 
 // ---------------------------------------------------------------------------------
 // small kernels: Grid.update, edges, reductions
@@ -1271,6 +1272,43 @@ static int launch_part(gs_grid2d *g, double time, bool xdir, bool fuse) {
   return GS_OK;
 }
 
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// tensor map of a row-major rows x cols array of doubles with K7's box: x sweep 16 columns x 32 rows, 128-byte swizzle
+// (the transposing tile); y sweep 32 columns x 16 rows.  cuTensorMapEncodeTiled is a driver entry point: fetched through
+// the runtime, libcuda is not linked.
+typedef CUresult (*gs_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static_assert(sizeof(CUtensorMap) == sizeof(K7Map), "CUtensorMap is a 128-byte blob");
+// generic form: a row-major dim1 x dim0 array of doubles (dim0 innermost), box0 x box1 boxes
+static int gs_encode_map2d(K7Map *out, const void *base, uint64_t dim0, uint64_t dim1, unsigned box0, unsigned box1,
+                           bool swizzle128) {
+  static gs_tmap_encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      gs_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return GS_ERR_CUDA;
+    }
+    encode = reinterpret_cast<gs_tmap_encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  const cuuint64_t strides[1] = {(cuuint64_t)dim0 * sizeof(double)};
+  const cuuint32_t box[2] = {box0, box1};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base),
+                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    gs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%llu x %llu, box %u x %u)", (int)rc,
+                 (unsigned long long)dim1, (unsigned long long)dim0, box1, box0);
+    return GS_ERR_CUDA;
+  }
+  return GS_OK;
+}
 // ---- K5: hoisted sweeps for literal-constant coefficients --------------------------------------------------
 static bool literal_const(gs_ctx *ctx, int off, double *value) {
   const double *h = ctx->pool.data() + off;
@@ -1280,8 +1318,8 @@ static bool literal_const(gs_ctx *ctx, int off, double *value) {
   return lit;
 }
 
-static void k5_shape(int n, int *m, int *S) {
-  int s = std::max(2, std::min(16, n / 256));
+static void k5_shape(int n, int *m, int *S, int smax = 16) {
+  int s = std::max(2, std::min(smax, n / 256));
   int mm = ((n + s - 1) / s + K5_CH - 1) / K5_CH * K5_CH;
   *m = mm;
   *S = (n + mm - 1) / mm;
@@ -1333,6 +1371,47 @@ static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int
   return 1;
 }
 
+// K5T (gs_grid2d_k5t.cuh): the tuning options a shape was chosen under, and the shape itself.
+// kind: 0 = x sweep, 1 = y sweep (2-D), 2 = 1-D batch.  Returns false where K5T does not apply (k5_sweep then runs).
+static long long k5_opt_sig(gs_ctx *ctx) {
+  return (long long)ctx->opt_k5t | ((long long)(ctx->opt_k5t_sx & 255) << 1) | ((long long)(ctx->opt_k5t_sy & 255) << 9) |
+         ((long long)(ctx->opt_k5t_s1 & 255) << 17) | ((long long)(ctx->opt_k5t_nt & 255) << 25) |
+         ((long long)ctx->opt_k5_cluster << 33);
+}
+static bool k5t_plan(gs_ctx *ctx, int kind, int n, int *m, int *S, int *NT) {
+  if (!ctx->opt_k5t) return false;
+  const bool xdir = kind == 0;
+  int smax = kind == 0 ? ctx->opt_k5t_sx : (kind == 1 ? ctx->opt_k5t_sy : ctx->opt_k5t_s1);
+  if (smax <= 0) smax = xdir ? 16 : 8;
+  smax = std::min(16, std::max(2, smax));
+  int mm, ss;
+  k5_shape(n, &mm, &ss, smax);
+  if (ss < 2) return false;
+  const int need = kind == 1 ? 2 : 1;   // the y sweep's stages are pairs of tiles
+  const int cap = ctx->opt_k5t_nt > 0 ? std::min(8, ctx->opt_k5t_nt) : 8;
+  int nt = 0;
+  for (int t = cap; t >= need; --t)
+    if (k5t_smem(xdir, ss, t) <= ctx->smem_optin) { nt = t; break; }
+  if (kind == 1) nt &= ~1;
+  if (nt < need) return false;
+  *m = mm; *S = ss; *NT = nt;
+  return true;
+}
+template <bool XDIR, bool ONED>
+static int k5t_launch(gs_ctx *ctx, int blocks, int S, int NT, const K5Params &q, const K5TMaps &tm) {
+  void (*kern)(K5Params, int, const K5TMaps) = S <= 8 ? k5t_sweep<XDIR, ONED, 256> : k5t_sweep<XDIR, ONED, 512>;
+  const size_t smem = k5t_smem(XDIR, S, NT);
+  const void *key = reinterpret_cast<const void *>(kern);
+  if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ctx->configured.push_back(key);
+  }
+  kern<<<blocks, 32 * S, smem, ctx->stream>>>(q, NT, tm);
+  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+
 static bool use_k5(gs_grid2d *g, bool xdir) {
   gs_ctx *ctx = g->ctx;
   if (g->solver == GS_SOLVER_THOMAS || !ctx->opt_k5) return false;
@@ -1354,9 +1433,12 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
   const int n = d.n;
   const int sf = xdir ? GS_LEFT : GS_UPP, sl = xdir ? GS_RIGHT : GS_LOW;
   if (kd.valid && kd.time == time && kd.kind_first == g->b[sf].kind && kd.kind_last == g->b[sl].kind &&
-      kd.pool_gen == ctx->spline_off.size())
+      kd.pool_gen == ctx->spline_off.size() && kd.opt_sig == k5_opt_sig(ctx))
     return GS_OK;
   kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false, 2> : k5_sweep<false, false, 2>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
+  // K5T: tensor-map strides are multiples of 16 bytes (an even number of columns); whole strips only
+  kd.tma = kd.cs == 1 && !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, &kd.m, &kd.S, &kd.NT);
+  kd.opt_sig = k5_opt_sig(ctx);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
     GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
@@ -1454,6 +1536,26 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     q.strip = std::max(24, (q.d.nlines + ctx->sm_count - 1) / ctx->sm_count);
     blocks = (q.d.nlines + q.strip - 1) / q.strip;
   }
+  if (kd.tma && aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result)) {
+    K5TMaps tm;
+    const uint64_t c = (uint64_t)g->cols, r = (uint64_t)g->rows;
+    if (xdir) {
+      GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, c, r, 16u, (unsigned)q.strip, true));
+      GS_TRY(gs_encode_map2d(&tm.out, g->result, c, r, 16u, (unsigned)q.strip, true));
+      tm.gold = tm.rhs;
+      tm.pout = tm.out;
+      GS_TRY((k5t_launch<true, false>(ctx, blocks, kd.S, kd.NT, q, tm)));
+    } else {
+      GS_TRY(gs_encode_map2d(&tm.rhs, g->result, c, r, 32u, 16u, false));
+      GS_TRY(gs_encode_map2d(&tm.out, g->grid, c, r, 32u, 16u, false));
+      tm.gold = tm.out;
+      GS_TRY(gs_encode_map2d(&tm.pout, g->predict, c, r, 32u, 16u, false));
+      GS_TRY((k5t_launch<false, false>(ctx, blocks, kd.S, kd.NT, q, tm)));
+    }
+    ctx->launches++;
+    return GS_OK;
+  }
+  GS_REQUIRE(smem <= ctx->smem_optin, "K5 shape does not fit shared memory");
   GS_TRY(k5_launch(xdir ? k5_sweep<true, false, 2> : (nb == 3 ? k5_sweep<false, false, 3> : k5_sweep<false, false, 2>), blocks, threads,
                    smem, ctx->stream, q));
   ctx->launches++;
@@ -1479,8 +1581,12 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   gs_ctx *ctx = g->ctx;
   gs_k5dir &kd = g->k5;
   const int n = g->n;
-  if (!(kd.valid && kd.time == time)) {
+  if (!(kd.valid && kd.time == time && kd.opt_sig == k5_opt_sig(ctx))) {
     kd.cs = k5_cluster(ctx, k5_sweep<false, true, 2>, false, n, (int)g->nlines, &kd.m, &kd.S);
+    // K5T: a 16-node box must not straddle two 32-line blocks; box coordinates are ints
+    kd.tma = kd.cs == 1 && n % K5_CH == 0 && (g->pitch / 32) * (int64_t)n < (int64_t)1 << 31 && aligned16(g->grid) &&
+             aligned16(g->predict) && k5t_plan(ctx, 2, n, &kd.m, &kd.S, &kd.NT);
+    kd.opt_sig = k5_opt_sig(ctx);
     if (!kd.tab) {
       GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
       GS_CUDA(cudaMalloc(&kd.omega_end, ((size_t)n / K5_CH + 2) * sizeof(double)));
@@ -1525,6 +1631,19 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   const int nb = k5_nb(ctx, false, kd.m, kd.S, kd.cs);
   size_t smem = k5_smem(false, kd.m, kd.S, kd.cs, nb);
   int blocks = (int)(g->pitch / 32), threads = 32 * kd.S;
+  if (kd.tma) {
+    K5TMaps tm;
+    const uint64_t rows = (uint64_t)(g->pitch / 32) * (uint64_t)n;
+    GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, 32u, rows, 32u, 16u, false));
+    tm.out = tm.rhs;
+    tm.gold = tm.rhs;
+    GS_TRY(gs_encode_map2d(&tm.pout, g->predict, 32u, rows, 32u, 16u, false));
+    for (int s = 0; s < nsteps; ++s) {
+      GS_TRY((k5t_launch<false, true>(ctx, blocks, kd.S, kd.NT, q, tm)));
+      ctx->launches++;
+    }
+    return GS_OK;
+  }
   for (int s = 0; s < nsteps; ++s) {
     GS_TRY(k5_launch(nb == 3 ? k5_sweep<false, true, 3> : k5_sweep<false, true, 2>, blocks, threads, smem, ctx->stream, q));
     ctx->launches++;
@@ -1733,7 +1852,6 @@ static int launch_k6(gs_grid2d *g, double time, bool xdir, const K6Split *split 
 }
 
 // ---- K7: exact sweeps (faces pass + one thread per line in the reference's order) -----------------------------
-static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool use_k7(gs_grid2d *g, bool xdir) {
   gs_ctx *ctx = g->ctx;
   if (!ctx->opt_k7 || g->solver == GS_SOLVER_PARTITIONED) return false;
@@ -1742,40 +1860,10 @@ static bool use_k7(gs_grid2d *g, bool xdir) {
   if (n < 4 || (g->cols & 1)) return false;
   return aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
 }
-// tensor map of a row-major rows x cols array of doubles with K7's box: x sweep 16 columns x 32 rows, 128-byte swizzle
-// (the transposing tile); y sweep 32 columns x 16 rows.  cuTensorMapEncodeTiled is a driver entry point: fetched through
-// the runtime, libcuda is not linked.
-typedef CUresult (*gs_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static_assert(sizeof(CUtensorMap) == sizeof(K7Map), "CUtensorMap is a 128-byte blob");
 static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox, bool pred_box = false) {
-  static gs_tmap_encode_fn encode = nullptr;
-  if (!encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    GS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || !fn) {
-      gs_set_error("cuTensorMapEncodeTiled is not available from this driver");
-      return GS_ERR_CUDA;
-    }
-    encode = reinterpret_cast<gs_tmap_encode_fn>(fn);
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(double)};
   // pred_box (fused faces): one more node along the line, 18 columns (a 16-byte multiple) without the swizzle for x
-  const cuuint32_t box[2] = {xbox ? (pred_box ? 18u : 16u) : 32u, xbox ? 32u : (pred_box ? 17u : 16u)};
-  const cuuint32_t estr[2] = {1u, 1u};
-  CUresult rc = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base),
-                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       (xbox && !pred_box) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) {
-    gs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%d x %d)", (int)rc, rows, cols);
-    return GS_ERR_CUDA;
-  }
-  return GS_OK;
+  return gs_encode_map2d(out, base, (uint64_t)cols, (uint64_t)rows, xbox ? (pred_box ? 18u : 16u) : 32u,
+                         xbox ? 32u : (pred_box ? 17u : 16u), xbox && !pred_box);
 }
 
 static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {

@@ -66,6 +66,9 @@ struct gs_ctx {
   int64_t opt_k5_xstrip = 0;   // 0 = automatic
   int opt_k5_nb = 2;           // K5: tile buffers per warp (3: triple buffer where it fits; measured slower)
   int opt_k5_cluster = 1;      // K5: clusters of 2 / 4 / 8 CTAs per strip when strips alone would not fill the chip
+  int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles)
+  int opt_k5t_sx = 0, opt_k5t_sy = 0, opt_k5t_s1 = 0;   // K5T: warps (segments) per CTA of the x / y / 1-D sweeps (0 = automatic)
+  int opt_k5t_nt = 0;          // K5T: tiles per warp ring (0 = as many as fit, at most 8)
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k6_chunk = 8;
@@ -89,6 +92,9 @@ struct gs_k5dir {
   bool valid = false;
   double time = 0.0;
   int kind_first = -1, kind_last = -1, m = 0, S = 0, cs = 1;   // S: segments (warps) per CTA, cs: CTAs per strip
+  bool tma = false;     // K5T (tensor-map TMA rings) instead of k5_sweep
+  int NT = 0;           // K5T: tiles per warp ring
+  long long opt_sig = -1;   // the tuning options the shape was chosen under
   size_t pool_gen = 0;
   double4 *tab = nullptr, *seg = nullptr;
   double *omega_end = nullptr, *ends = nullptr;
