@@ -16,6 +16,7 @@
 // Both keep the reference's operation order exactly (GS_SOLVER_THOMAS, bit-exact).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1282,7 +1283,7 @@ typedef CUresult (*gs_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint
 static_assert(sizeof(CUtensorMap) == sizeof(K7Map), "CUtensorMap is a 128-byte blob");
 // generic form: a row-major dim1 x dim0 array of doubles (dim0 innermost), box0 x box1 boxes
 static int gs_encode_map2d(K7Map *out, const void *base, uint64_t dim0, uint64_t dim1, unsigned box0, unsigned box1,
-                           bool swizzle128) {
+                           bool swizzle128, int promo256 = 0) {
   static gs_tmap_encode_fn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -1301,7 +1302,8 @@ static int gs_encode_map2d(K7Map *out, const void *base, uint64_t dim0, uint64_t
   CUresult rc = encode(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base),
                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       promo256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     gs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%llu x %llu, box %u x %u)", (int)rc,
                  (unsigned long long)dim1, (unsigned long long)dim0, box1, box0);
@@ -1376,39 +1378,97 @@ static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int
 static long long k5_opt_sig(gs_ctx *ctx) {
   return (long long)ctx->opt_k5t | ((long long)(ctx->opt_k5t_sx & 255) << 1) | ((long long)(ctx->opt_k5t_sy & 255) << 9) |
          ((long long)(ctx->opt_k5t_s1 & 255) << 17) | ((long long)(ctx->opt_k5t_nt & 255) << 25) |
-         ((long long)ctx->opt_k5_cluster << 33);
+         ((long long)ctx->opt_k5_cluster << 33) | ((long long)ctx->opt_k5t_wide << 34);
 }
-static bool k5t_plan(gs_ctx *ctx, int kind, int n, int *m, int *S, int *NT) {
-  if (!ctx->opt_k5t) return false;
-  const bool xdir = kind == 0;
-  int smax = kind == 0 ? ctx->opt_k5t_sx : (kind == 1 ? ctx->opt_k5t_sy : ctx->opt_k5t_s1);
-  if (smax <= 0) smax = xdir ? 16 : 8;
-  smax = std::min(16, std::max(2, smax));
-  int mm, ss;
-  k5_shape(n, &mm, &ss, smax);
-  if (ss < 2) return false;
-  const int need = kind == 1 ? 2 : 1;   // the y sweep's stages are pairs of tiles
-  const int cap = ctx->opt_k5t_nt > 0 ? std::min(8, ctx->opt_k5t_nt) : 8;
-  int nt = 0;
-  for (int t = cap; t >= need; --t)
-    if (k5t_smem(xdir, ss, t) <= ctx->smem_optin) { nt = t; break; }
-  if (kind == 1) nt &= ~1;
-  if (nt < need) return false;
-  *m = mm; *S = ss; *NT = nt;
-  return true;
+// wide x stages: 0 never, 1 for lines of 8192 nodes and more (measured: 16384^2 x sweep 1.120 against 1.153 ms; 4096^2
+// 71.9 against 70.6 us), 2 always
+static bool k5t_wide(gs_ctx *ctx, int kind, int n) {
+  return kind == 0 && (ctx->opt_k5t_wide >= 2 || (ctx->opt_k5t_wide == 1 && n >= 8192));
 }
-template <bool XDIR, bool ONED>
-static int k5t_launch(gs_ctx *ctx, int blocks, int S, int NT, const K5Params &q, const K5TMaps &tm) {
-  void (*kern)(K5Params, int, const K5TMaps) = S <= 8 ? k5t_sweep<XDIR, ONED, 256> : k5t_sweep<XDIR, ONED, 512>;
-  const size_t smem = k5t_smem(XDIR, S, NT);
+typedef void (*k5t_kern_t)(K5Params, int, int, const K5TMaps);
+static k5t_kern_t k5t_kernel(int kind, int S, bool wide) {
+  if (kind == 0 && wide) return S <= 8 ? k5t_sweep<true, false, 256, true> : k5t_sweep<true, false, 512, true>;
+  if (kind == 0) return S <= 8 ? k5t_sweep<true, false, 256, false> : k5t_sweep<true, false, 512, false>;
+  if (kind == 1) return S <= 8 ? k5t_sweep<false, false, 256, false> : k5t_sweep<false, false, 512, false>;
+  return S <= 8 ? k5t_sweep<false, true, 256, false> : k5t_sweep<false, true, 512, false>;
+}
+static int k5t_configure(gs_ctx *ctx, k5t_kern_t kern) {
+  // function attributes are per device: remembered per context
   const void *key = reinterpret_cast<const void *>(kern);
   if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ctx->configured.push_back(key);
   }
-  kern<<<blocks, 32 * S, smem, ctx->stream>>>(q, NT, tm);
-  GS_CUDA(cudaGetLastError());
+  return GS_OK;
+}
+// The K5T shape of a sweep over `nlines` lines of n nodes: segments per CTA S (= warps), segment length m, tiles per
+// warp ring NT, CTAs per strip cs (a thread-block cluster when the strips alone would leave half the SMs idle; every
+// cluster must be resident at once).  Returns false where K5T does not apply (k5_sweep then runs).
+static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, int *NT, int *cs_out) {
+  if (!ctx->opt_k5t) return false;
+  const bool xdir = kind == 0, wide = k5t_wide(ctx, kind, n);
+  int smax = kind == 0 ? ctx->opt_k5t_sx : (kind == 1 ? ctx->opt_k5t_sy : ctx->opt_k5t_s1);
+  if (smax <= 0) smax = (xdir && !wide) ? 16 : 8;
+  smax = std::min(16, std::max(2, smax));
+  const int need = kind == 1 ? 2 : 1;   // the y sweep's stages are pairs of tiles
+  const int cap = ctx->opt_k5t_nt > 0 ? std::min(8, ctx->opt_k5t_nt) : 8;
+  const int strips = (nlines + 31) / 32;
+  // clusters: any size up to 8 (not only powers of two: GPCs of 16 - 20 SMs hold two clusters of 7 where only one of 8
+  // fits next to another), the largest whose clusters are all resident at once
+  int cs = 1;
+  if (ctx->opt_k5_cluster && strips * 2 <= ctx->sm_count) cs = std::min(8, ctx->sm_count / strips);
+  for (; cs >= 1; --cs) {
+    int mm, ss;
+    k5_shape(n, &mm, &ss, smax);
+    if (ss < 2) return false;
+    if (cs > 1) {
+      const int st = ss * cs;
+      mm = ((n + st - 1) / st + K5_CH - 1) / K5_CH * K5_CH;
+      if (!(mm >= 2 * K5_CH && (n + mm - 1) / mm == st)) continue;
+    }
+    int nt = 0;
+    for (int t = cap; t >= need; --t)
+      if (k5t_smem(xdir, wide, ss, t, cs) <= ctx->smem_optin) { nt = t; break; }
+    if (kind == 1) nt &= ~1;
+    if (nt < need) continue;
+    if (cs > 1) {
+      k5t_kern_t kern = k5t_kernel(kind, ss, wide);
+      if (k5t_configure(ctx, kern) != GS_OK) { cudaGetLastError(); continue; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(strips * cs);
+      cfg.blockDim = dim3(32 * ss);
+      cfg.dynamicSmemBytes = k5t_smem(xdir, wide, ss, nt, cs);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int resident = 0;
+      if (cudaOccupancyMaxActiveClusters(&resident, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (resident < strips) continue;
+    }
+    *m = mm; *S = ss; *NT = nt; *cs_out = cs;
+    if (getenv("GS_DEBUG"))
+      fprintf(stderr, "[gs] K5T plan kind=%d n=%d lines=%d: S=%d m=%d NT=%d cluster=%d wide=%d\n", kind, n, nlines, ss, mm, nt, cs, (int)wide);
+    return true;
+  }
+  return false;
+}
+static int k5t_launch(gs_ctx *ctx, int kind, bool wide, int blocks, int S, int NT, int cs, const K5Params &q, const K5TMaps &tm) {
+  k5t_kern_t kern = k5t_kernel(kind, S, wide);
+  GS_TRY(k5t_configure(ctx, kern));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks * cs);
+  cfg.blockDim = dim3(32 * S);
+  cfg.dynamicSmemBytes = k5t_smem(kind == 0, wide, S, NT, cs);
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q, NT, (int)ctx->opt_k5t_hints, tm));
   return GS_OK;
 }
 
@@ -1436,8 +1496,8 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
       kd.pool_gen == ctx->spline_off.size() && kd.opt_sig == k5_opt_sig(ctx))
     return GS_OK;
   kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false, 2> : k5_sweep<false, false, 2>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
-  // K5T: tensor-map strides are multiples of 16 bytes (an even number of columns); whole strips only
-  kd.tma = kd.cs == 1 && !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, &kd.m, &kd.S, &kd.NT);
+  // K5T: tensor-map strides are multiples of 16 bytes (an even number of columns)
+  kd.tma = !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, xdir ? g->rows : g->cols, &kd.m, &kd.S, &kd.NT, &kd.cs);
   kd.opt_sig = k5_opt_sig(ctx);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
@@ -1539,18 +1599,36 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   if (kd.tma && aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result)) {
     K5TMaps tm;
     const uint64_t c = (uint64_t)g->cols, r = (uint64_t)g->rows;
+    // lines per CTA: one CTA per SM and a memory-bound kernel, so what counts is waves x strip width (4096 lines: 147
+    // strips of 28 instead of 128 of 32).  The y sweep's box rows are `strip` doubles: an even number (16-byte units).
+    if (kd.cs == 1) {
+      const int64_t forced = xdir ? ctx->opt_k5_xstrip : ctx->opt_k5t_ystrip;
+      int best = 32;
+      long long best_cost = -1;
+      // (y: measured -- 28-column strips = 224-byte row pieces that straddle 256-byte units cost more than the idle SMs:
+      // 4096^2 0.198 against 0.183 ms per step, 16384^2 3.65 against 2.91)
+      for (int w = 32; w >= (xdir ? 24 : 32); w -= (xdir ? 1 : 2)) {
+        const long long ctas = (q.d.nlines + w - 1) / w, waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+        if (best_cost < 0 || waves * w < best_cost) { best = w; best_cost = waves * w; }
+      }
+      q.strip = (forced > 0 && forced <= 32 && (xdir || !(forced & 1))) ? (int)forced : best;
+      blocks = (q.d.nlines + q.strip - 1) / q.strip;
+    }
     if (xdir) {
-      GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, c, r, 16u, (unsigned)q.strip, true));
-      GS_TRY(gs_encode_map2d(&tm.out, g->result, c, r, 16u, (unsigned)q.strip, true));
+      const bool wide = k5t_wide(ctx, 0, q.d.n);
+      if (wide) GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, c, r, (unsigned)K5T_WCOLS, (unsigned)q.strip, false, ctx->opt_k5t_promo));
+      else GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, c, r, 16u, (unsigned)q.strip, true, ctx->opt_k5t_promo));
+      GS_TRY(gs_encode_map2d(&tm.out, g->result, c, r, 16u, (unsigned)q.strip, true, ctx->opt_k5t_promo));
       tm.gold = tm.rhs;
       tm.pout = tm.out;
-      GS_TRY((k5t_launch<true, false>(ctx, blocks, kd.S, kd.NT, q, tm)));
+      GS_TRY(k5t_launch(ctx, 0, wide, blocks, kd.S, kd.NT, kd.cs, q, tm));
     } else {
-      GS_TRY(gs_encode_map2d(&tm.rhs, g->result, c, r, 32u, 16u, false));
-      GS_TRY(gs_encode_map2d(&tm.out, g->grid, c, r, 32u, 16u, false));
+      q.cta_stride = q.strip;
+      GS_TRY(gs_encode_map2d(&tm.rhs, g->result, c, r, (unsigned)q.strip, 16u, false));
+      GS_TRY(gs_encode_map2d(&tm.out, g->grid, c, r, (unsigned)q.strip, 16u, false));
       tm.gold = tm.out;
-      GS_TRY(gs_encode_map2d(&tm.pout, g->predict, c, r, 32u, 16u, false));
-      GS_TRY((k5t_launch<false, false>(ctx, blocks, kd.S, kd.NT, q, tm)));
+      GS_TRY(gs_encode_map2d(&tm.pout, g->predict, c, r, (unsigned)q.strip, 16u, false));
+      GS_TRY(k5t_launch(ctx, 1, false, blocks, kd.S, kd.NT, kd.cs, q, tm));
     }
     ctx->launches++;
     return GS_OK;
@@ -1584,8 +1662,8 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   if (!(kd.valid && kd.time == time && kd.opt_sig == k5_opt_sig(ctx))) {
     kd.cs = k5_cluster(ctx, k5_sweep<false, true, 2>, false, n, (int)g->nlines, &kd.m, &kd.S);
     // K5T: a 16-node box must not straddle two 32-line blocks; box coordinates are ints
-    kd.tma = kd.cs == 1 && n % K5_CH == 0 && (g->pitch / 32) * (int64_t)n < (int64_t)1 << 31 && aligned16(g->grid) &&
-             aligned16(g->predict) && k5t_plan(ctx, 2, n, &kd.m, &kd.S, &kd.NT);
+    kd.tma = n % K5_CH == 0 && (g->pitch / 32) * (int64_t)n < (int64_t)1 << 31 && aligned16(g->grid) &&
+             aligned16(g->predict) && k5t_plan(ctx, 2, n, (int)g->nlines, &kd.m, &kd.S, &kd.NT, &kd.cs);
     kd.opt_sig = k5_opt_sig(ctx);
     if (!kd.tab) {
       GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
@@ -1639,7 +1717,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
     tm.gold = tm.rhs;
     GS_TRY(gs_encode_map2d(&tm.pout, g->predict, 32u, rows, 32u, 16u, false));
     for (int s = 0; s < nsteps; ++s) {
-      GS_TRY((k5t_launch<false, true>(ctx, blocks, kd.S, kd.NT, q, tm)));
+      GS_TRY(k5t_launch(ctx, 2, false, blocks, kd.S, kd.NT, kd.cs, q, tm));
       ctx->launches++;
     }
     return GS_OK;

@@ -68,6 +68,10 @@ struct gs_ctx {
   int opt_k5_cluster = 1;      // K5: clusters of 2 / 4 / 8 CTAs per strip when strips alone would not fill the chip
   int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles)
   int opt_k5t_sx = 0, opt_k5t_sy = 0, opt_k5t_s1 = 0;   // K5T: warps (segments) per CTA of the x / y / 1-D sweeps (0 = automatic)
+  int opt_k5t_promo = 1;       // K5T x sweep: L2 promotion of the tensor maps (0: 128 B, 1: 256 B; measured: x sweep 4096^2 75 -> 72 us, 16384^2 1.21 -> 1.15 ms)
+  int opt_k5t_ystrip = 0;      // K5T y sweep: columns per CTA (even, <= 32; 0 = automatic)
+  int opt_k5t_wide = 1;        // K5T x sweep: 32-column stages loaded as one un-swizzled 34-column box (272-byte rows)
+  int opt_k5t_hints = 0;       // K5T: L2 eviction hints, bit 0 loads (phase A evict_last, phase C evict_first), bit 1 stores (evict_first)
   int opt_k5t_nt = 0;          // K5T: tiles per warp ring (0 = as many as fit, at most 8)
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)

@@ -101,6 +101,18 @@ GS_TMA_DEV void gs_tma_store_2d(const void *tmap, int c0, int c1, const void *ss
                "r"(c1), "r"(gs_smem_u32(ssrc))
                : "memory");
 }
+GS_TMA_DEV void gs_tma_load_2d_hint(void *sdst, const void *tmap, int c0, int c1, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          gs_smem_u32(sdst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(gs_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+GS_TMA_DEV void gs_tma_store_2d_hint(const void *tmap, int c0, int c1, const void *ssrc, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tmap),
+               "r"(c0), "r"(c1), "r"(gs_smem_u32(ssrc)), "l"(policy)
+               : "memory");
+}
 GS_TMA_DEV void gs_tma_prefetch_desc(const void *tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
