@@ -1440,6 +1440,8 @@ extern "C" int gs_grid1d_destroy(gs_grid1d *g) {
   cudaFree(g->k5.omega_end);
   cudaFree(g->k5.seg);
   cudaFree(g->k5.ends);
+  cudaFree(g->k5.soft_buf);
+  cudaFree(g->k5.soft_sync);
   for (int i = 0; i < 2; ++i) {
     cudaFree(g->hs_stage_in[i]);
     cudaFree(g->hs_stage_out[i]);

@@ -952,6 +952,8 @@ extern "C" int gs_grid2d_destroy(gs_grid2d *g) {
     cudaFree(kd->omega_end);
     cudaFree(kd->seg);
     cudaFree(kd->ends);
+    cudaFree(kd->soft_buf);
+    cudaFree(kd->soft_sync);
   }
   cudaFree(g->status);
   gs_ctx *owner = g->ctx;
@@ -1378,7 +1380,7 @@ static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int
 static long long k5_opt_sig(gs_ctx *ctx) {
   return (long long)ctx->opt_k5t | ((long long)(ctx->opt_k5t_sx & 255) << 1) | ((long long)(ctx->opt_k5t_sy & 255) << 9) |
          ((long long)(ctx->opt_k5t_s1 & 255) << 17) | ((long long)(ctx->opt_k5t_nt & 255) << 25) |
-         ((long long)ctx->opt_k5_cluster << 33) | ((long long)ctx->opt_k5t_wide << 34);
+         ((long long)ctx->opt_k5_cluster << 33) | ((long long)ctx->opt_k5t_wide << 34) | ((long long)ctx->opt_k5t_soft << 36);
 }
 // wide x stages: 0 never, 1 for lines of 8192 nodes and more (measured: 16384^2 x sweep 1.120 against 1.153 ms; 4096^2
 // 71.9 against 70.6 us), 2 always
@@ -1405,7 +1407,7 @@ static int k5t_configure(gs_ctx *ctx, k5t_kern_t kern) {
 // The K5T shape of a sweep over `nlines` lines of n nodes: segments per CTA S (= warps), segment length m, tiles per
 // warp ring NT, CTAs per strip cs (a thread-block cluster when the strips alone would leave half the SMs idle; every
 // cluster must be resident at once).  Returns false where K5T does not apply (k5_sweep then runs).
-static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, int *NT, int *cs_out) {
+static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, int *NT, int *cs_out, bool *soft_out) {
   if (!ctx->opt_k5t) return false;
   const bool xdir = kind == 0, wide = k5t_wide(ctx, kind, n);
   int smax = kind == 0 ? ctx->opt_k5t_sx : (kind == 1 ? ctx->opt_k5t_sy : ctx->opt_k5t_s1);
@@ -1414,26 +1416,34 @@ static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, i
   const int need = kind == 1 ? 2 : 1;   // the y sweep's stages are pairs of tiles
   const int cap = ctx->opt_k5t_nt > 0 ? std::min(8, ctx->opt_k5t_nt) : 8;
   const int strips = (nlines + 31) / 32;
-  // clusters: any size up to 8 (not only powers of two: GPCs of 16 - 20 SMs hold two clusters of 7 where only one of 8
-  // fits next to another), the largest whose clusters are all resident at once
-  int cs = 1;
-  if (ctx->opt_k5_cluster && strips * 2 <= ctx->sm_count) cs = std::min(8, ctx->sm_count / strips);
-  for (; cs >= 1; --cs) {
-    int mm, ss;
-    k5_shape(n, &mm, &ss, smax);
-    if (ss < 2) return false;
-    if (cs > 1) {
-      const int st = ss * cs;
-      mm = ((n + st - 1) / st + K5_CH - 1) / K5_CH * K5_CH;
-      if (!(mm >= 2 * K5_CH && (n + mm - 1) / mm == st)) continue;
-    }
+  int mm1, ss;
+  k5_shape(n, &mm1, &ss, smax);
+  if (ss < 2) return false;
+  // segment length when a strip's line is split over cs CTAs of ss segments each (0: does not divide)
+  auto seg_len = [&](int cs) {
+    if (cs == 1) return mm1;
+    const int st = ss * cs;
+    const int mm = ((n + st - 1) / st + K5_CH - 1) / K5_CH * K5_CH;
+    // (segments shorter than 4 chunks are all pipeline ramp: 4096 columns x 512 rows, x sweep: m = 32 measured 84 us, m = 64 29 us)
+    return (mm >= 4 * K5_CH && (n + mm - 1) / mm == st && st <= 128) ? mm : 0;
+  };
+  auto tiles_for = [&](int cs_smem) {
     int nt = 0;
     for (int t = cap; t >= need; --t)
-      if (k5t_smem(xdir, wide, ss, t, cs) <= ctx->smem_optin) { nt = t; break; }
+      if (k5t_smem(xdir, wide, ss, t, cs_smem) <= ctx->smem_optin) { nt = t; break; }
     if (kind == 1) nt &= ~1;
-    if (nt < need) continue;
+    return nt;
+  };
+  k5t_kern_t kern = k5t_kernel(kind, ss, wide);
+  // hardware clusters: any size up to 8 (not only powers of two: GPCs of 16 - 20 SMs hold two clusters of 6 where only
+  // one of 8 fits), the largest whose clusters are all resident at once
+  int cs = 1;
+  if (ctx->opt_k5_cluster && strips * 2 <= ctx->sm_count) cs = std::min(8, ctx->sm_count / strips);
+  int hw_cs = 0, hw_nt = 0, hw_m = 0;
+  for (; cs >= 1; --cs) {
+    const int mm = seg_len(cs), nt = tiles_for(cs);
+    if (!mm || nt < need) continue;
     if (cs > 1) {
-      k5t_kern_t kern = k5t_kernel(kind, ss, wide);
       if (k5t_configure(ctx, kern) != GS_OK) { cudaGetLastError(); continue; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(strips * cs);
@@ -1448,24 +1458,64 @@ static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, i
       if (cudaOccupancyMaxActiveClusters(&resident, kern, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
       if (resident < strips) continue;
     }
-    *m = mm; *S = ss; *NT = nt; *cs_out = cs;
-    if (getenv("GS_DEBUG"))
-      fprintf(stderr, "[gs] K5T plan kind=%d n=%d lines=%d: S=%d m=%d NT=%d cluster=%d wide=%d\n", kind, n, nlines, ss, mm, nt, cs, (int)wide);
-    return true;
+    hw_cs = cs; hw_nt = nt; hw_m = mm;
+    break;
   }
-  return false;
+  // soft groups (global-memory gather, no GPC constraint): taken when they put at least 10 % more CTAs to work; every
+  // CTA must be resident (they wait for each other)
+  int sf_cs = 0, sf_nt = 0, sf_m = 0;
+  if (ctx->opt_k5_cluster && ctx->opt_k5t_soft && strips * 2 <= ctx->sm_count) {
+    const int nt = tiles_for(1);
+    int per_sm = 0;
+    if (nt >= need && k5t_configure(ctx, kern) == GS_OK &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * ss, k5t_smem(xdir, wide, ss, nt, 1)) == cudaSuccess) {
+      for (int c2 = std::min(16, per_sm * ctx->sm_count / strips); c2 >= 2; --c2) {
+        const int mm = seg_len(c2);
+        // the first CTA stages [2][c2 * ss][32] doubles in its (idle) stage tiles between the phases
+        if (!mm || (size_t)2 * c2 * ss * 256 > (size_t)ss * nt * (wide ? K5T_WTILE : K5T_TILE)) continue;
+        sf_cs = c2; sf_nt = nt; sf_m = mm;
+        break;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  const bool soft = sf_cs > 0 && (hw_cs == 0 || sf_cs * 10 >= hw_cs * 11);
+  if (!soft && hw_cs == 0) return false;
+  *m = soft ? sf_m : hw_m; *S = ss; *NT = soft ? sf_nt : hw_nt; *cs_out = soft ? sf_cs : hw_cs; *soft_out = soft;
+  if (getenv("GS_DEBUG"))
+    fprintf(stderr, "[gs] K5T plan kind=%d n=%d lines=%d: S=%d m=%d NT=%d CTAs per strip=%d (%s) wide=%d\n", kind, n, nlines, ss,
+            *m, *NT, *cs_out, soft ? "soft group" : "cluster", (int)wide);
+  return true;
+}
+// buffers of a soft group: [3][strips][cs * S][32] doubles + [strips][2] words (zeroed once: the counters are monotonic)
+static int k5t_soft_buffers(gs_ctx *ctx, gs_k5dir &kd, int strips) {
+  const size_t need = (size_t)3 * strips * kd.cs * kd.S * 32;
+  if (kd.soft_len < need || kd.soft_strips < (size_t)strips) {
+    GS_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(kd.soft_buf);
+    cudaFree(kd.soft_sync);
+    kd.soft_buf = nullptr; kd.soft_sync = nullptr; kd.soft_len = 0; kd.soft_strips = 0;
+    GS_CUDA(cudaMalloc(&kd.soft_buf, need * sizeof(double)));
+    GS_CUDA(cudaMalloc(&kd.soft_sync, (size_t)2 * strips * sizeof(unsigned)));
+    GS_CUDA(cudaMemsetAsync(kd.soft_sync, 0, (size_t)2 * strips * sizeof(unsigned), ctx->stream));
+    kd.soft_len = need; kd.soft_strips = strips;
+    kd.epoch = 0;
+  }
+  return GS_OK;
 }
 static int k5t_launch(gs_ctx *ctx, int kind, bool wide, int blocks, int S, int NT, int cs, const K5Params &q, const K5TMaps &tm) {
+  const int hw = q.soft ? 1 : cs;   // soft groups: plain CTAs
   k5t_kern_t kern = k5t_kernel(kind, S, wide);
   GS_TRY(k5t_configure(ctx, kern));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks * cs);
   cfg.blockDim = dim3(32 * S);
-  cfg.dynamicSmemBytes = k5t_smem(kind == 0, wide, S, NT, cs);
+  cfg.dynamicSmemBytes = k5t_smem(kind == 0, wide, S, NT, hw);
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = hw; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q, NT, (int)ctx->opt_k5t_hints, tm));
@@ -1497,7 +1547,8 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
     return GS_OK;
   kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false, 2> : k5_sweep<false, false, 2>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
   // K5T: tensor-map strides are multiples of 16 bytes (an even number of columns)
-  kd.tma = !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, xdir ? g->rows : g->cols, &kd.m, &kd.S, &kd.NT, &kd.cs);
+  kd.soft = false;
+  kd.tma = !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, xdir ? g->rows : g->cols, &kd.m, &kd.S, &kd.NT, &kd.cs, &kd.soft);
   kd.opt_sig = k5_opt_sig(ctx);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
@@ -1552,6 +1603,7 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   GS_TRY(k5_prepare(g, xdir, time));
   gs_k5dir &kd = xdir ? g->k5x : g->k5y;
   K5Params q;
+  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr;
   q.d.n = xdir ? g->cols : g->rows;
   q.d.nlines = xdir ? g->rows : g->cols;
   q.d.m = kd.m; q.d.S = kd.S;
@@ -1614,6 +1666,10 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
       q.strip = (forced > 0 && forced <= 32 && (xdir || !(forced & 1))) ? (int)forced : best;
       blocks = (q.d.nlines + q.strip - 1) / q.strip;
     }
+    if (kd.soft) {
+      GS_TRY(k5t_soft_buffers(ctx, kd, blocks));
+      q.soft = 1; q.epoch = ++kd.epoch; q.g_buf = kd.soft_buf; q.g_sync = kd.soft_sync;
+    }
     if (xdir) {
       const bool wide = k5t_wide(ctx, 0, q.d.n);
       if (wide) GS_TRY(gs_encode_map2d(&tm.rhs, g->grid, c, r, (unsigned)K5T_WCOLS, (unsigned)q.strip, false, ctx->opt_k5t_promo));
@@ -1662,8 +1718,9 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
   if (!(kd.valid && kd.time == time && kd.opt_sig == k5_opt_sig(ctx))) {
     kd.cs = k5_cluster(ctx, k5_sweep<false, true, 2>, false, n, (int)g->nlines, &kd.m, &kd.S);
     // K5T: a 16-node box must not straddle two 32-line blocks; box coordinates are ints
+    kd.soft = false;
     kd.tma = n % K5_CH == 0 && (g->pitch / 32) * (int64_t)n < (int64_t)1 << 31 && aligned16(g->grid) &&
-             aligned16(g->predict) && k5t_plan(ctx, 2, n, (int)g->nlines, &kd.m, &kd.S, &kd.NT, &kd.cs);
+             aligned16(g->predict) && k5t_plan(ctx, 2, n, (int)g->nlines, &kd.m, &kd.S, &kd.NT, &kd.cs, &kd.soft);
     kd.opt_sig = k5_opt_sig(ctx);
     if (!kd.tab) {
       GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
@@ -1687,6 +1744,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
     kd.time = time;
   }
   K5Params q;
+  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr;
   q.d.n = n;
   q.d.nlines = (int)g->nlines;
   q.d.m = kd.m; q.d.S = kd.S;
@@ -1716,7 +1774,12 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
     tm.out = tm.rhs;
     tm.gold = tm.rhs;
     GS_TRY(gs_encode_map2d(&tm.pout, g->predict, 32u, rows, 32u, 16u, false));
+    if (kd.soft) {
+      GS_TRY(k5t_soft_buffers(ctx, kd, blocks));
+      q.soft = 1; q.g_buf = kd.soft_buf; q.g_sync = kd.soft_sync;
+    }
     for (int s = 0; s < nsteps; ++s) {
+      if (kd.soft) q.epoch = ++kd.epoch;
       GS_TRY(k5t_launch(ctx, 2, false, blocks, kd.S, kd.NT, kd.cs, q, tm));
       ctx->launches++;
     }

@@ -49,6 +49,11 @@ struct K5Params {
   int bc_stride;         // bound_first/last index = line * bc_stride (1-D batches: 0 = one value for all lines)
   int csize;             // CTAs per strip (thread-block cluster): the line's csize * S segments are spread over them
   unsigned *status;
+  // K5T strip groups through global memory (soft != 0; csize CTAs per strip, no hardware cluster)
+  int soft;
+  unsigned epoch;        // number of this launch on these buffers (1, 2, ...)
+  double *g_buf;         // [3][strips][csize * S][32]: lambda_e, Q, x at the segment ends
+  unsigned *g_sync;      // [strips][2]
 };
 
 // ---- setup: line-independent elimination ------------------------------------------------------------------

@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
   const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;   // warp k = segment crank * S + k
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  const int csz = q.csize, crank = csz > 1 ? (int)cluster.block_rank() : 0, ST = S * csz;
+  const bool soft = q.soft != 0;   // the strip's CTAs meet through global memory instead of a hardware cluster
+  const int csz = q.csize, crank = csz > 1 ? (soft ? (int)(blockIdx.x % csz) : (int)cluster.block_rank()) : 0, ST = S * csz;
   const int strip_id = blockIdx.x / csz;
-  auto sync_strip = [&]() { if (csz > 1) cluster.sync(); else __syncthreads(); };
+  auto sync_strip = [&]() { if (csz > 1 && !soft) cluster.sync(); else __syncthreads(); };
   const int line0 = strip_id * q.strip, nl = min(q.strip, d.nlines - line0);
   const int NTS = NT + 1;   // table slots
   // shared memory: output tiles [S][NOUT] | stage tiles [S][NT] | table slots [S][NT + 1] | lamE [S][32] | Q [S][32] | barriers [S][NT]
@@ -215,8 +216,18 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
     }
   }
   // segment results go where the reduced system is solved: this CTA's arrays, or -- clustered strips -- the first
-  // CTA's [ST][32] gather arrays through distributed shared memory
-  if (csz > 1) {
+  // CTA's [ST][32] gather arrays through distributed shared memory, or -- soft groups -- global memory
+  double *gLam = nullptr, *gQ = nullptr, *gE = nullptr;
+  if (csz > 1 && soft) {
+    const size_t per = (size_t)(gridDim.x / csz) * ST * 32;
+    gLam = q.g_buf + (size_t)strip_id * ST * 32;
+    gQ = gLam + per;
+    gE = gQ + per;
+    const int kg = crank * S + k;
+    __stcg(&gLam[kg * 32 + lane], lam);
+    __stcg(&gQ[kg * 32 + lane], Qacc);
+    __threadfence();
+  } else if (csz > 1) {
     const int kg = crank * S + k;
     cluster.map_shared_rank(allLam, 0)[kg * 32 + lane] = lam;
     cluster.map_shared_rank(allQ, 0)[kg * 32 + lane] = Qacc;
@@ -225,6 +236,52 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
     Qs[k * 32 + lane] = Qacc;
   }
   sync_strip();
+  if (csz > 1 && soft) {
+    // arrive; the strip's first CTA waits for all csz arrivals of this launch (the counter is never reset: launch
+    // number `epoch` ends at epoch * csz), solves, publishes; everybody waits for its `done` word
+    unsigned *arrive = q.g_sync + 2 * strip_id, *done = arrive + 1;
+    if (threadIdx.x == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(arrive) : "memory");
+    }
+    if (crank == 0) {
+      // the whole first CTA copies the strip's [ST][32] segment results into shared memory (its stage tiles are idle
+      // between the phases) in ONE round trip to L2, warp 0 solves there, and all warps publish the result
+      if (threadIdx.x == 0) gs_spin_until(arrive, q.epoch * (unsigned)csz, q.status);
+      __syncthreads();
+      double *sl = reinterpret_cast<double *>(base + (size_t)S * NOUT * K5T_TILE), *sq = sl + ST * 32;
+      for (int i = threadIdx.x; i < ST * 32; i += blockDim.x) {
+        sl[i] = __ldcg(&gLam[i]);
+        sq[i] = __ldcg(&gQ[i]);
+      }
+      __syncthreads();
+      if (k == 0) {
+        double dp = 0.0;
+        for (int kk = 0; kk < ST; ++kk) {
+          const double4 sg = d.seg[kk];
+          const double rhs = sl[kk * 32 + lane] + ((kk + 1 < ST) ? sg.x * sq[(kk + 1) * 32 + lane] : 0.0);
+          dp = (rhs - sg.y * dp) * sg.z;
+          sl[kk * 32 + lane] = dp;
+        }
+        double x = 0.0;
+        for (int kk = ST - 1; kk >= 0; --kk) {
+          x = sl[kk * 32 + lane] - d.seg[kk].w * x;
+          sl[kk * 32 + lane] = x;
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < ST * 32; i += blockDim.x) __stcg(&gE[i], sl[i]);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done), "r"(q.epoch) : "memory");
+    }
+    if (lane == 0) gs_spin_until(done, q.epoch, q.status);
+    __syncwarp();
+    const int kg = crank * S + k;
+    Es[k * 32 + lane] = __ldcg(&gE[kg * 32 + lane]);
+    if (k == 0) Qs[lane] = kg > 0 ? __ldcg(&gE[(kg - 1) * 32 + lane]) : 0.0;
+    gs_fence_proxy_async();   // the first CTA's scratch (generic proxy) is overwritten by phase C's TMA loads
+    __syncthreads();
+  } else {
   // ---- reduced system (first CTA's warp 0; lane = line).  Afterwards Es[k] = x at the end of segment k and
   //      Qs[0 * 32 + lane] of every CTA = x just above its first segment ----
   if (k == 0 && crank == 0) {
@@ -249,6 +306,7 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
     Qs[lane] = 0.0;
   }
   sync_strip();
+  }
   // ---- phase C: chunks last to first: recompute the lambdas from the checkpoint, back-substitute, store ----
   if (nch == 0) return;
   const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : Qs[lane];   // x just before the segment

@@ -69,6 +69,7 @@ struct gs_ctx {
   int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles)
   int opt_k5t_sx = 0, opt_k5t_sy = 0, opt_k5t_s1 = 0;   // K5T: warps (segments) per CTA of the x / y / 1-D sweeps (0 = automatic)
   int opt_k5t_promo = 1;       // K5T x sweep: L2 promotion of the tensor maps (0: 128 B, 1: 256 B; measured: x sweep 4096^2 75 -> 72 us, 16384^2 1.21 -> 1.15 ms)
+  int opt_k5t_soft = 1;        // K5T: strip groups through global memory when they put more CTAs to work than clusters
   int opt_k5t_ystrip = 0;      // K5T y sweep: columns per CTA (even, <= 32; 0 = automatic)
   int opt_k5t_wide = 1;        // K5T x sweep: 32-column stages loaded as one un-swizzled 34-column box (272-byte rows)
   int opt_k5t_hints = 0;       // K5T: L2 eviction hints, bit 0 loads (phase A evict_last, phase C evict_first), bit 1 stores (evict_first)
@@ -99,6 +100,13 @@ struct gs_k5dir {
   bool tma = false;     // K5T (tensor-map TMA rings) instead of k5_sweep
   int NT = 0;           // K5T: tiles per warp ring
   long long opt_sig = -1;   // the tuning options the shape was chosen under
+  // K5T strip groups without a hardware cluster (more CTAs per strip than fit one GPC): segment results and the solved
+  // interface values travel through global memory, the CTAs of a strip meet on a counter (all CTAs are resident)
+  bool soft = false;
+  double *soft_buf = nullptr;      // [3][strips][cs * S][32]
+  unsigned *soft_sync = nullptr;   // [strips][2] arrivals (monotonic), done (epoch)
+  size_t soft_len = 0, soft_strips = 0;
+  unsigned epoch = 0;
   size_t pool_gen = 0;
   double4 *tab = nullptr, *seg = nullptr;
   double *omega_end = nullptr, *ends = nullptr;

@@ -137,3 +137,19 @@ GS_TMA_DEV void gs_mbar_wait_bounded(uint64_t *bar, uint32_t parity, unsigned *s
     }
   }
 }
+
+// spin on a global word (acquire, gpu scope) until it equals `want`; as gs_mbar_wait_bounded it cannot hang the device
+GS_TMA_DEV void gs_spin_until(const unsigned *word, unsigned want, unsigned *status) {
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+    if (v == want) return;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > (1ll << 32)) {
+      atomicOr(status, 0x80000000u);
+      __trap();
+    }
+  }
+}

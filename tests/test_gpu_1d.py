@@ -216,3 +216,25 @@ def test_long_lines_partitioned(O, gs, nlines, n, solver, per_node):
     exact = cases.run_batch(gs, solver=gs.SOLVER_THOMAS, **kw)
     for k in ("grid", "predict"):
         assert_bit_equal(exact[k], want[k], "THOMAS stays bit-exact " + k)
+
+
+@pytest.mark.parametrize("nlines,n", [(96, 16384), (1000, 4096), (33, 2048)])
+def test_long_lines_k5t_variants(O, gs, ctx, nlines, n):
+    """K5T on 1-D batches (TMA boxes of 32 lines x 16 nodes, clusters / soft groups when the strips are few) against
+    k5_sweep and the oracle."""
+    from helpers import max_rel_err
+
+    kw = dict(nlines=nlines, n=n, steps=2, spline="const", random_grid=True)
+    want = cases.run_batch(O, oracle=True, **kw)
+    defaults = {"k5t": 1, "k5t_soft": 1, "k5_cluster": 1, "k5t_s1": 0}
+    try:
+        for opts in ({}, {"k5t": 0}, {"k5t_soft": 0}, {"k5_cluster": 0}, {"k5t_s1": 4}):
+            for k, v in {**defaults, **opts}.items():
+                ctx.set_option(k, v)
+            got = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
+            for k in ("grid", "predict"):
+                err = max_rel_err(got[k], want[k])
+                assert err <= 1e-12, f"{opts} {k}: {err:.3e}"
+    finally:
+        for k, v in defaults.items():
+            ctx.set_option(k, v)

@@ -478,6 +478,57 @@ def test_k5_clustered_strips(O, gs, ctx, cols, rows, combo):
         ctx.set_option("k5_cluster", 1)
 
 
+@pytest.mark.parametrize("cols,rows,combo", [(512, 384, "TTFF"), (1000, 140, "FTTF"), (130, 1025, "TFFT"), (4096, 300, "TTTT"),
+                                             (2048, 64, "TTFF"), (64, 2048, "TFTT"), (8192, 40, "FFTT")])
+def test_k5t_tma_rings_match_k5(O, gs, ctx, cols, rows, combo):
+    """K5T (tensor-map TMA rings: swizzled / wide boxes, box stores, clusters of any size, soft groups through global
+    memory) runs K5's arithmetic: same answer as k5_sweep (k5t = 0) far inside the tolerance, and as the reference."""
+    p = cases.bc_problem(combo, xdir=1, ydir=0, cols=cols, rows=rows, coefs="const")
+    o = p.build_oracle(O)
+    for _ in range(2):
+        o.iteration(900.0)
+    want = cases.snapshot(o)
+    runs = {}
+    variants = [("k5", {"k5t": 0}), ("k5t", {}), ("wide x", {"k5t_wide": 2}), ("narrow x", {"k5t_wide": 0, "k5t_sx": 8}),
+                ("no soft groups", {"k5t_soft": 0}), ("hints", {"k5t_hints": 3, "k5t_promo": 0}), ("short rings", {"k5t_nt": 2})]
+    defaults = {"k5t": 1, "k5t_wide": 1, "k5t_sx": 0, "k5t_soft": 1, "k5t_hints": 0, "k5t_promo": 1, "k5t_nt": 0}
+    try:
+        for name, opts in variants:
+            for k, v in {**defaults, **opts}.items():
+                ctx.set_option(k, v)
+            g = p.build_gs(gs)
+            g.set_solver(gs.SOLVER_PARTITIONED)
+            g.iteration(900.0, nsteps=2)
+            runs[name] = cases.snapshot(g)
+            assert g.status == 0
+            _compare_tol(runs[name], want, f"{name} {cols}x{rows} vs oracle")
+    finally:
+        for k, v in defaults.items():
+            ctx.set_option(k, v)
+    for name in runs:
+        for k in ("grid", "predict"):
+            assert max_rel_err(runs[name][k], runs["k5"][k]) <= 2e-13, (name, k)
+
+
+def test_k5t_x_sweep_bits_equal_k5_with_the_same_segments(gs, ctx):
+    """With the same segmentation (16 segments of 256 columns) K5T's x sweep and k5_sweep perform the same operations
+    in the same order: `result` is bit-identical."""
+    p = cases.bc_problem("TFFT", xdir=0, ydir=0, cols=4096, rows=70, coefs="const")
+    out = {}
+    try:
+        for name, opts in (("k5", {"k5t": 0, "k5_cluster": 0}), ("k5t", {"k5t": 1, "k5_cluster": 0, "k5t_wide": 0, "k5t_sx": 16})):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            g = p.build_gs(gs)
+            g.set_solver(gs.SOLVER_PARTITIONED)
+            g.xIter(900.0)
+            out[name] = np.array(g.grid.result)
+    finally:
+        for k, v in {"k5t": 1, "k5_cluster": 1, "k5t_wide": 1, "k5t_sx": 0}.items():
+            ctx.set_option(k, v)
+    assert_bit_equal(out["k5t"], out["k5"], "K5T x sweep vs k5_sweep")
+
+
 def test_k5_triple_buffer_variant(O, gs, ctx):
     """Option k5_nb = 3: three tile buffers per warp on the y sweep (measured slower, kept as a tested variant)."""
     ctx.set_option("k5_nb", 3)
