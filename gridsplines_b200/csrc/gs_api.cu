@@ -134,6 +134,9 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "k6_fuse")) ctx->opt_k6_fuse = value != 0;
   else if (!strcmp(name, "k7")) ctx->opt_k7 = value;
   else if (!strcmp(name, "k7_fuse")) ctx->opt_k7_fuse = value;
+  else if (!strcmp(name, "k7_nsb")) ctx->opt_k7_nsb = value;
+  else if (!strcmp(name, "k7f_nfw")) ctx->opt_k7f_nfw = value;
+  else if (!strcmp(name, "k7_promo")) ctx->opt_k7_promo = value;
   else if (!strcmp(name, "auto_exact")) ctx->opt_auto_exact = value;
   else if (!strcmp(name, "host_chunk_mb")) ctx->opt_host_chunk_mb = value;
   else if (!strcmp(name, "ck_block")) ctx->opt_ck_block = value;

@@ -2001,10 +2001,11 @@ static bool use_k7(gs_grid2d *g, bool xdir) {
   if (n < 4 || (g->cols & 1)) return false;
   return aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
 }
+static int k7_promo = 0;   // x sweep boxes: 256-byte L2 promotion (set from option k7_promo before a launch encodes its maps)
 static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox, bool pred_box = false) {
   // pred_box (fused faces): one more node along the line, 18 columns (a 16-byte multiple) without the swizzle for x
   return gs_encode_map2d(out, base, (uint64_t)cols, (uint64_t)rows, xbox ? (pred_box ? 18u : 16u) : 32u,
-                         xbox ? 32u : (pred_box ? 17u : 16u), xbox && !pred_box);
+                         xbox ? 32u : (pred_box ? 17u : 16u), xbox && !pred_box, xbox ? k7_promo : 0);
 }
 
 static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
@@ -2058,8 +2059,10 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   q.pool = fq.sw.pool;
   q.pool_len = fq.sw.pool_len;
   q.stage_off = stage_off; q.stage_len = stage_len;
+  q.nsb = (int)ctx->opt_k7_nsb;
   q.maps = fq.sw.maps;
   K7Maps tm;
+  k7_promo = (int)ctx->opt_k7_promo;
   GS_TRY(k7_encode(&tm.F, fused ? (const void *)g->predict : (const void *)fq.F, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.rhs, fq.sw.rhs, g->cols, g->rows, xdir));
   GS_TRY(k7_encode(&tm.gold, g->grid, g->cols, g->rows, xdir));
@@ -2068,10 +2071,17 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   if (fused) {
     // literal constants: one faces warp keeps up with the chain warp; tables: two (each takes half of a chunk's nodes)
     void (*kern)(K7Params, const K7Maps);
-    if (xdir) kern = lit ? k7f_sweep<true, false, true, 1> : k7f_sweep<true, false, false, 2>;
-    else if (fuse) kern = lit ? k7f_sweep<false, true, true, 1> : k7f_sweep<false, true, false, 2>;
-    else kern = lit ? k7f_sweep<false, false, true, 1> : k7f_sweep<false, false, false, 2>;
-    const int threads = lit ? 64 : 96;
+    // faces warps per CTA: literal constants 1; tables 2, or 3 while every SM holds at most two strips (the faces warps
+    // then bound the pipeline: 4096^2 1.255 -> 1.172 ms per step; with 3.5 strips per SM the SM itself is busy and three
+    // measured 7.35 against 7.24 ms at 16384^2; four need a 102-register cap and spill: 8.48 ms)
+    int nfw = 2;
+    if (ctx->opt_k7f_nfw >= 2 && ctx->opt_k7f_nfw <= 4) nfw = (int)ctx->opt_k7f_nfw;
+    else if (strips <= 2 * ctx->sm_count) nfw = 3;
+    if (lit) nfw = 1;
+    if (xdir) kern = lit ? k7f_sweep<true, false, true, 1> : (nfw == 4 ? k7f_sweep<true, false, false, 4> : nfw == 3 ? k7f_sweep<true, false, false, 3> : k7f_sweep<true, false, false, 2>);
+    else if (fuse) kern = lit ? k7f_sweep<false, true, true, 1> : (nfw == 4 ? k7f_sweep<false, true, false, 4> : nfw == 3 ? k7f_sweep<false, true, false, 3> : k7f_sweep<false, true, false, 2>);
+    else kern = lit ? k7f_sweep<false, false, true, 1> : (nfw == 4 ? k7f_sweep<false, false, false, 4> : nfw == 3 ? k7f_sweep<false, false, false, 3> : k7f_sweep<false, false, false, 2>);
+    const int threads = 32 + 32 * nfw;
     // function attributes are per device: remembered per context
     const void *key = reinterpret_cast<const void *>(kern);
     if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {

@@ -35,7 +35,8 @@
 #define K7_NS 3                          // ring depth
 #define K7_TILE 4096                     // one box: 16 x 32 doubles
 #define K7_STAGE 12288                   // bytes per stage = max(forward 2 tiles + cf, backward 8 KB + tile)
-#define K7_SMEM (1024 + 1024 + K7_NS * K7_STAGE + 2 * K7_TILE)   // alignment slack + barriers + stages + output tiles
+#define K7_NSB 8                         // most stages of the backward ring (as many as fit: see k7_bwd_ring)
+#define K7_SMEM (1024 + 1024 + K7_NS * K7_STAGE + 2 * K7_TILE)   // alignment slack + barriers + stages + output tiles (< 48 KB: no opt-in)
 
 // CUtensorMap is an opaque 128-byte, 64-byte aligned blob (cuda.h); kept as bytes here so that device code does not
 // need the driver header
@@ -62,6 +63,7 @@ struct K7Params {
   const double *pool;
   int pool_len;
   int stage_off, stage_len;        // the part of the pool staged in shared memory: all of it, or the one table of a SINGLE map
+  int nsb;                         // most stages of the backward ring (option k7_nsb)
   Maps2d maps;
 };
 
@@ -73,13 +75,15 @@ struct K7Ring {
   uint32_t phase;
   int head;      // stage of the next chunk to be consumed
   int tail;      // stage of the next chunk to be issued
+  int ns;        // depth
+  int stride;    // bytes per stage
 };
-GS_DEV unsigned char *k7_stage(const K7Ring &r, int s) { return r.stages + (size_t)s * K7_STAGE; }
+GS_DEV unsigned char *k7_stage(const K7Ring &r, int s) { return r.stages + (size_t)s * r.stride; }
 GS_DEV void k7_wait(K7Ring &r, unsigned *status) {
   gs_mbar_wait_bounded(&r.bars[r.head], (r.phase >> r.head) & 1u, status);
   r.phase ^= 1u << r.head;
 }
-GS_DEV void k7_advance(int &s) { s = (s == K7_NS - 1) ? 0 : s + 1; }
+GS_DEV void k7_advance(const K7Ring &r, int &s) { s = (s == r.ns - 1) ? 0 : s + 1; }
 
 // element (row r, column j) of a 32 x 16 box that landed with CU_TENSOR_MAP_SWIZZLE_128B (tile base 1024 B aligned):
 // the 16-byte unit index j / 2 is XORed with r % 8
@@ -99,7 +103,7 @@ GS_DEV void k7_issue_fwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, 
     gs_tma_load_2d(st + K7_TILE, &tm.rhs, c0, c1, bar);
     gs_bulk_g2s(st + 2 * K7_TILE, q.coefs + 2 * (size_t)i0, (uint32_t)len * 16u, bar);
   }
-  k7_advance(r.tail);
+  k7_advance(r, r.tail);
 }
 
 // The forward walk of one line (lane) over all chunks; toPassion -> scratch.  Returns the sticky range predicate of
@@ -113,7 +117,7 @@ GS_DEV bool k7_forward(const K7Params &q, const K7Maps &tm, K7Ring &r, int line0
   const double l_sub = q.last3[3 * line], l_diag = q.last3[3 * line + 1], l_rhs = q.last3[3 * line + 2];
   bool ok = true;
   double delta = 0.0, lambda = 0.0, fprev = 0.0;
-  for (int c = 0; c < min(K7_NS, NC); ++c) k7_issue_fwd<XDIR>(q, tm, r, c, line0, lane);
+  for (int c = 0; c < min(r.ns, NC); ++c) k7_issue_fwd<XDIR>(q, tm, r, c, line0, lane);
   // Dim.general :67-83 + forwardUnit :257-265 of an interior node
   auto node_mid = [&](double t, double F, double cf0, double cf1) {
     const double a = cf0 * fprev;
@@ -175,13 +179,28 @@ GS_DEV bool k7_forward(const K7Params &q, const K7Maps &tm, K7Ring &r, int line0
         so[(size_t)j * 32] = make_double2(delta, lambda);
       }
     }
-    k7_advance(r.head);
+    k7_advance(r, r.head);
     __syncwarp();
-    if (c + K7_NS < NC) k7_issue_fwd<XDIR>(q, tm, r, c + K7_NS, line0, lane);
+    if (c + r.ns < NC) k7_issue_fwd<XDIR>(q, tm, r, c + r.ns, line0, lane);
   }
   return ok;
 }
 
+// The backward ring: stages of 8 KB (+ 4 KB with the old grid tile), as many as fit `capacity` bytes.  The backward walk
+// has two dependent FP64 operations per node and runs at HBM speed: timed alone at 16384^2 (forward skipped, stale
+// scratch) it takes 1.10 ms (x, 24 B/node: 5.9 TB/s) and 1.84 ms (y, 40 B/node: 5.8 TB/s); 2, 3, 4 or 6 stages measure
+// the same (option k7_nsb).  The FORWARD walk is what costs: 2.30 / 2.25 ms per sweep alone, ~4400 clk per 16-node chunk
+// and CTA against ~2400 for the bare chain -- the SM issues ~1.9 instructions per clock for 150 warp instructions per
+// node-row (faces 102, chain 45), FP64 pipe ~40 % busy (profiles/r2_k7f_phases.md).
+template <bool FUSE>
+GS_DEV void k7_bwd_ring(K7Ring &r, unsigned char *stages, uint64_t *bars, int capacity, int most) {
+  r.stages = stages;
+  r.bars = bars;
+  r.phase = 0;
+  r.head = r.tail = 0;
+  r.stride = K7_CH * 512 + (FUSE ? K7_TILE : 0);
+  r.ns = max(1, min(min(K7_NSB, most), capacity / r.stride));
+}
 // backward stage layout: (delta, lambda) [16][32] double2 (8 KB) | old grid tile [16][32] (fused y sweep)
 template <bool FUSE>
 GS_DEV void k7_issue_bwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, int line0, int lane, const double2 *sc) {
@@ -193,7 +212,7 @@ GS_DEV void k7_issue_bwd(const K7Params &q, const K7Maps &tm, K7Ring &r, int c, 
     gs_bulk_g2s(st, sc + (size_t)i0 * 32, (uint32_t)len * 512u, bar);
     if (FUSE) gs_tma_load_2d(st + K7_CH * 512, &tm.gold, line0, i0, bar);
   }
-  k7_advance(r.tail);
+  k7_advance(r, r.tail);
 }
 
 // The backward walk (backwardRow :303-322 / backwardColumn :324-342 [+ Grid.update :474-481]) of one warp's 32 lines:
@@ -202,7 +221,7 @@ template <bool XDIR, bool FUSE>
 GS_DEV double k7_backward(const K7Params &q, const K7Maps &tm, K7Ring &r, unsigned char *otile, int line0, bool act,
                           int lane, const double2 *sc) {
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
-  for (int k = 0; k < min(K7_NS, NC); ++k) k7_issue_bwd<FUSE>(q, tm, r, NC - 1 - k, line0, lane, sc);
+  for (int k = 0; k < min(r.ns, NC); ++k) k7_issue_bwd<FUSE>(q, tm, r, NC - 1 - k, line0, lane, sc);
   double u = 0.0;
   int ot = 0;
 #pragma unroll 1
@@ -278,9 +297,9 @@ GS_DEV double k7_backward(const K7Params &q, const K7Maps &tm, K7Ring &r, unsign
         }
       }
     }
-    k7_advance(r.head);
+    k7_advance(r, r.head);
     __syncwarp();
-    if (c - K7_NS >= 0) k7_issue_bwd<FUSE>(q, tm, r, c - K7_NS, line0, lane, sc);
+    if (c - r.ns >= 0) k7_issue_bwd<FUSE>(q, tm, r, c - r.ns, line0, lane, sc);
   }
   return u;
 }
@@ -300,9 +319,12 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant
   r.stages = k7s + 1024;
   r.phase = 0;
   r.head = r.tail = 0;
+  r.ns = K7_NS;
+  r.stride = K7_STAGE;
+  uint64_t *bwd_bars = r.bars + K7_NS;
   unsigned char *otile = k7s + 1024 + K7_NS * K7_STAGE;
   if (lane == 0) {
-    for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&r.bars[s], 1);
+    for (int s = 0; s < K7_NS + K7_NSB; ++s) gs_mbar_init(&r.bars[s], 1);
     gs_mbar_init_fence();
     gs_tma_prefetch_desc(&tm.F);
     gs_tma_prefetch_desc(&tm.rhs);
@@ -339,6 +361,8 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant
   gs_fence_proxy_async();
   __syncwarp();
 
+  // the x sweep's output tiles follow the stages; the y sweeps store from registers and may use that room too
+  k7_bwd_ring<FUSE>(r, k7s + 1024, bwd_bars, K7_NS * K7_STAGE + (XDIR ? 0 : 2 * K7_TILE), q.nsb);
   const double u = k7_backward<XDIR, FUSE>(q, tm, r, otile, line0, act, lane, sc);
   if (XDIR && lane == 0) gs_bulk_wait_read<0>();
   if (act && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
@@ -370,7 +394,7 @@ __global__ void __launch_bounds__(32) k7_sweep(K7Params q, const __grid_constant
 static_assert(K7F_P + 3 * K7F_PT <= K7F_REGION && K7_NS * K7_STAGE <= K7F_REGION, "K7F shared-memory layout");
 
 struct K7FBars {
-  uint64_t bwd[K7_NS];   // backward ring (K7Ring)
+  uint64_t bwd[K7_NSB];  // backward ring (K7Ring)
   uint64_t ft[3];        // (F, rhs, cf) of a chunk ready: tx bytes of the loads + 1 arrival (faces warp)
   uint64_t empty[3];     // the chain warp is done with the stage
   uint64_t pin[3];       // predict tile landed
@@ -456,10 +480,12 @@ template <bool XDIR, bool LIT, int NFW>
 GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsigned char *region, const double *pool_sm,
                       uint32_t &e_phase, uint32_t &p_phase, uint32_t &d_phase, int fw, int line0, int lane, int rl,
                       unsigned &flags) {
-  constexpr int PER = K7_CH / NFW;
+  // warp fw takes the nodes [j0, j1) of every chunk (NFW = 3: five, five and six)
+  constexpr bool EVEN = K7_CH % NFW == 0;
+  constexpr int PER = (K7_CH + NFW - 1) / NFW;
   const int n = q.n, NC = (n + K7_CH - 1) / K7_CH;
   const int line = line0 + rl;
-  const int j0 = fw * PER;
+  const int j0 = fw * K7_CH / NFW, j1 = (fw + 1) * K7_CH / NFW;
   auto issue_p = [&](int c) {
     if (lane == 0) {
       const int p = c % 3, i0 = c * K7_CH;
@@ -518,12 +544,14 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
       // A single warp has nobody to hide its latencies behind: eight faces at a time go through the straight-line
       // tier together (independent instruction streams the scheduler can interleave); the few that fall out of it
       // -- equal temperatures, a straddled knot, clamps -- are redone one by one afterwards.
+      constexpr int B = PER < 8 ? PER : 8;   // faces per batch (a batch may run past j1: its last face is then dropped)
 #pragma unroll
-      for (int h = j0; h < j0 + PER; h += 8) {
-        double v[8];
+      for (int h0 = 0; h0 < PER; h0 += B) {
+        const int h = j0 + h0;
+        double v[B];
         unsigned bad = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < B; ++j) {
           const double p0 = pred0(h + j), p1 = pred0(h + j + 1);
           bool good;
           if (LIT) {
@@ -533,19 +561,20 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
           } else {
             good = k6_face_fast(z, p0, p1, v[j]);
           }
-          if (!good) bad |= 1u << j;
+          if (!good && (EVEN || h + j < j1)) bad |= 1u << j;
         }
         if (bad) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < B; ++j)
             if ((bad >> j) & 1u) v[j] = face(pred0(h + j), pred0(h + j + 1), i0 + h + j);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) F[(h + j) * 32] = v[j];
+        for (int j = 0; j < B; ++j)
+          if (EVEN || h + j < j1) F[(h + j) * 32] = v[j];
       }
     } else {
 #pragma unroll 1
-      for (int j = j0; j < min(len, j0 + PER); ++j) {
+      for (int j = j0; j < min(len, j1); ++j) {
         const int i = i0 + j;
         double v = 0.0;
         if (i == 0) v = q.face0[line];          // carry out of node 0 (k6_ends): co, or cond / cap after a heat-flow end
@@ -586,7 +615,7 @@ __global__ void __launch_bounds__(32 + 32 * NFW, 4) k7f_sweep(K7Params q, const 
   unsigned char *otile = region + K7F_REGION;
   double *pool_sm = reinterpret_cast<double *>(otile + 2 * K7_TILE);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < K7_NS; ++s) gs_mbar_init(&bars->bwd[s], 1);
+    for (int s = 0; s < K7_NSB; ++s) gs_mbar_init(&bars->bwd[s], 1);
     for (int s = 0; s < 3; ++s) {
       gs_mbar_init(&bars->ft[s], NFW);
       gs_mbar_init(&bars->empty[s], 1);
@@ -647,11 +676,9 @@ __global__ void __launch_bounds__(32 + 32 * NFW, 4) k7f_sweep(K7Params q, const 
   __threadfence();
   gs_fence_proxy_async();
   __syncwarp();
+  // backward ring: the forward region; the y sweeps also take the output tiles and the (now idle) spline pool
   K7Ring r;
-  r.bars = bars->bwd;
-  r.stages = region;
-  r.phase = 0;
-  r.head = r.tail = 0;
+  k7_bwd_ring<FUSE>(r, region, bars->bwd, K7F_REGION + (XDIR ? 0 : 2 * K7_TILE + K7F_POOL), q.nsb);
   const double u = k7_backward<XDIR, FUSE>(q, tm, r, otile, line0, act, lane, sc);
   if (XDIR && lane == 0) gs_bulk_wait_read<0>();
   if (act && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
