@@ -300,7 +300,7 @@ def bench_c3(gs, ctx, torch, stream, peak, steps=20, n=4096):
     cells = float(n) * n
     return {"workload": f"C3: 2-D ortho x ortho {n}x{n}, constant properties, Dirichlet 20/4 + Neumann 50/0, one 64x64 flat patch",
             "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
-            "solver": "AUTO -> K5 (hoisted partitioned sweeps, tolerance family)",
+            "solver": "AUTO -> K5T (hoisted partitioned sweeps on tensor-map TMA rings, tolerance family)",
             "parity": {"after_steps": 100, "against": "GS_SOLVER_THOMAS (K7, bit-exact vs the oracle: tests/test_gpu_k7.py)", **par},
             "exact_solver": {"ms_per_step": ms_exact, "updates_per_s": cells / (ms_exact * 1e-3),
                              "roofline_frac": _roof(cells, BYTES_PER_UPDATE_2D, ms_exact, peak)["frac"], "solver": "K7"},
@@ -330,7 +330,7 @@ def bench_c4(gs, ctx, torch, stream, peak, steps=5, n=16384):
     cells = float(n) * n
     return {"workload": f"C4: 2-D radial x ortho {n}x{n}, M1Hermite3 k(T), c(T), alpha = k / c, Dirichlet 30 / 7",
             "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
-            "solver": "AUTO -> K7 (faces pass + per-thread Thomas in the reference's order: bit-exact)",
+            "solver": "AUTO -> K7F (faces warps + per-thread Thomas in the reference's order: bit-exact)",
             "parity": {"statement": "bit-exact vs the oracle (tests/test_gpu_k7.py: 4096^2 C4 shape, every node, 2 steps)"},
             "tolerance_family": {"solver": "GS_SOLVER_PARTITIONED -> K6", "ms_per_step": ms_part,
                                  "updates_per_s": cells / (ms_part * 1e-3),
@@ -356,7 +356,7 @@ def bench_c5(gs, ctx, torch, stream, peak, steps=5, lines=4096, n=65536, parity=
     out = {"workload": f"C5: {lines} lines x {n} nodes, ortho, constant properties, per-line Dirichlet ends",
            "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
            "roofline": _roof(float(lines) * n, BYTES_PER_UPDATE_1D, ms, peak),
-           "solver": "AUTO -> K5 (partitioned Thomas: segments + reduced system, tolerance family)"}
+           "solver": "AUTO -> K5T (partitioned Thomas: segments + reduced system on TMA rings, tolerance family)"}
     if parity:
         g.upload(gs.GRID, grid0); g.fill(gs.PREDICT, 4.0)
         e = _c5_grid(gs, ctx, lines, n, gs.SOLVER_THOMAS, grid0, lt, rt)
@@ -523,8 +523,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gridsplines_b200 has no CPU path")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a host-side group: ranks that only WAIT must not park an NCCL kernel on a GPU another rank is driving
+        cpu_group = dist.new_group(backend="gloo")
     nlines, n = args.lines, args.nodes
     stream = torch.cuda.Stream()
     ctx = gs.Context(local, stream=stream.cuda_stream)
@@ -630,12 +633,16 @@ def run_ours(args):
                     torch.cuda.empty_cache()
         else:
             def abi():
+                # rank 0 drives every GPU of the box from one process; the other ranks idle on the HOST (a gloo barrier): an
+                # NCCL barrier would spin in a kernel on their GPUs and time-slice with rank 0's kernels there
                 out = None
+                torch.cuda.synchronize()
+                dist.barrier(group=cpu_group)
                 try:
                     out = bench_c4_strong_abi(gs, torch, world, rank)
                 except Exception as exc:
                     out = {"error": f"{type(exc).__name__}: {exc}"}
-                dist.barrier()
+                dist.barrier(group=cpu_group)
                 return out
 
             for name, fn in (("c4_strong", lambda: bench_c4_strong(gs, torch, dist, stream, ctx, world, rank, local)),
