@@ -1471,8 +1471,8 @@ static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, i
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * ss, k5t_smem(xdir, wide, ss, nt, 1)) == cudaSuccess) {
       for (int c2 = std::min(16, per_sm * ctx->sm_count / strips); c2 >= 2; --c2) {
         const int mm = seg_len(c2);
-        // the first CTA stages [2][c2 * ss][32] doubles in its (idle) stage tiles between the phases
-        if (!mm || (size_t)2 * c2 * ss * 256 > (size_t)ss * nt * (wide ? K5T_WTILE : K5T_TILE)) continue;
+        // the first CTA stages [2][c2 * ss][32] doubles in its output tiles (idle until phase C stores)
+        if (!mm || (size_t)2 * c2 * ss * 256 > (size_t)ss * (xdir ? 1 : 2) * K5T_TILE) continue;
         sf_cs = c2; sf_nt = nt; sf_m = mm;
         break;
       }

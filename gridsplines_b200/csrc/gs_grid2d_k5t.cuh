@@ -215,6 +215,11 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
       ts = (ts + 1 == NTS) ? 0 : ts + 1;
     }
   }
+  // phase C's first loads (the segment's last chunks) do not depend on the reduced system: they fly during the exchange
+  constexpr int SS = GOLD ? 2 : 1;   // tiles per stage
+  const int D = NT / SS;             // stages
+  if (lane == 0)
+    for (int kk = 0; kk < min(D, nst); ++kk) issue(kk * SS, kk % NTS, nst - 1 - kk, GOLD, true);
   // segment results go where the reduced system is solved: this CTA's arrays, or -- clustered strips -- the first
   // CTA's [ST][32] gather arrays through distributed shared memory, or -- soft groups -- global memory
   double *gLam = nullptr, *gQ = nullptr, *gE = nullptr;
@@ -244,11 +249,11 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(arrive) : "memory");
     }
     if (crank == 0) {
-      // the whole first CTA copies the strip's [ST][32] segment results into shared memory (its stage tiles are idle
-      // between the phases) in ONE round trip to L2, warp 0 solves there, and all warps publish the result
+      // the whole first CTA copies the strip's [ST][32] segment results into shared memory (its output tiles are idle
+      // until phase C stores) in ONE round trip to L2, warp 0 solves there, and all warps publish the result
       if (threadIdx.x == 0) gs_spin_until(arrive, q.epoch * (unsigned)csz, q.status);
       __syncthreads();
-      double *sl = reinterpret_cast<double *>(base + (size_t)S * NOUT * K5T_TILE), *sq = sl + ST * 32;
+      double *sl = reinterpret_cast<double *>(base), *sq = sl + ST * 32;   // the CTA's output tiles (idle until phase C stores)
       for (int i = threadIdx.x; i < ST * 32; i += blockDim.x) {
         sl[i] = __ldcg(&gLam[i]);
         sq[i] = __ldcg(&gQ[i]);
@@ -279,7 +284,6 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
     const int kg = crank * S + k;
     Es[k * 32 + lane] = __ldcg(&gE[kg * 32 + lane]);
     if (k == 0) Qs[lane] = kg > 0 ? __ldcg(&gE[(kg - 1) * 32 + lane]) : 0.0;
-    gs_fence_proxy_async();   // the first CTA's scratch (generic proxy) is overwritten by phase C's TMA loads
     __syncthreads();
   } else {
   // ---- reduced system (first CTA's warp 0; lane = line).  Afterwards Es[k] = x at the end of segment k and
@@ -311,10 +315,6 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
   if (nch == 0) return;
   const double L = (k > 0) ? Es[(k - 1) * 32 + lane] : Qs[lane];   // x just before the segment
   double x = Es[k * 32 + lane];                                // x_e
-  constexpr int SS = GOLD ? 2 : 1;   // tiles per stage
-  const int D = NT / SS;             // stages
-  if (lane == 0)
-    for (int kk = 0; kk < min(D, nst); ++kk) issue(kk * SS, kk % NTS, nst - 1 - kk, GOLD, true);
   double ck_next = (nch > 1) ? ckpt[(size_t)(nch - 2) * ck_pitch] : 0.0;               // checkpoint before the last chunk
   double om_next = (nch > 1) ? d.omega_end[(s + (nch - 1) * K5_CH - 1) / K5_CH] : 0.0;  // omega at its end
   {
