@@ -2071,16 +2071,20 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   if (fused) {
     // literal constants: one faces warp keeps up with the chain warp; tables: two (each takes half of a chunk's nodes)
     void (*kern)(K7Params, const K7Maps);
-    // faces warps per CTA: literal constants 1; tables 2, or 3 while every SM holds at most two strips (the faces warps
-    // then bound the pipeline: 4096^2 1.255 -> 1.172 ms per step; with 3.5 strips per SM the SM itself is busy and three
-    // measured 7.35 against 7.24 ms at 16384^2; four need a 102-register cap and spill: 8.48 ms)
+    // faces warps per CTA: literal constants 1; tables: while an SM holds few strips the faces warps bound the pipeline and
+    // more of them pay -- MEASURED ms per step with 2 / 3 / 4 faces warps: 4096^2 (one strip per SM) 1.229 / 1.160 / 0.934
+    // (eight: 1.116), 8192^2 (two per SM) 2.770 / 2.585 / 3.536, 16384^2 (3.5 per SM: the SM itself is busy) 7.24 / 7.35 / -
+    // (four warps at the 102 registers that keep four CTAs resident spill: 8.48)
     int nfw = 2;
     if (ctx->opt_k7f_nfw >= 2 && ctx->opt_k7f_nfw <= 4) nfw = (int)ctx->opt_k7f_nfw;
+    else if (strips <= ctx->sm_count) nfw = 4;          // one strip per SM: four faces warps with all the registers they want
     else if (strips <= 2 * ctx->sm_count) nfw = 3;
     if (lit) nfw = 1;
-    if (xdir) kern = lit ? k7f_sweep<true, false, true, 1> : (nfw == 4 ? k7f_sweep<true, false, false, 4> : nfw == 3 ? k7f_sweep<true, false, false, 3> : k7f_sweep<true, false, false, 2>);
-    else if (fuse) kern = lit ? k7f_sweep<false, true, true, 1> : (nfw == 4 ? k7f_sweep<false, true, false, 4> : nfw == 3 ? k7f_sweep<false, true, false, 3> : k7f_sweep<false, true, false, 2>);
-    else kern = lit ? k7f_sweep<false, false, true, 1> : (nfw == 4 ? k7f_sweep<false, false, false, 4> : nfw == 3 ? k7f_sweep<false, false, false, 3> : k7f_sweep<false, false, false, 2>);
+#define K7F_PICK(X, F) (lit ? k7f_sweep<X, F, true, 1> : nfw == 4 ? k7f_sweep<X, F, false, 4> : nfw == 3 ? k7f_sweep<X, F, false, 3> : k7f_sweep<X, F, false, 2>)
+    if (xdir) kern = K7F_PICK(true, false);
+    else if (fuse) kern = K7F_PICK(false, true);
+    else kern = K7F_PICK(false, false);
+#undef K7F_PICK
     const int threads = 32 + 32 * nfw;
     // function attributes are per device: remembered per context
     const void *key = reinterpret_cast<const void *>(kern);

@@ -602,7 +602,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
 }
 
 template <bool XDIR, bool FUSE, bool LIT, int NFW>
-__global__ void __launch_bounds__(32 + 32 * NFW, 4) k7f_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
+__global__ void __launch_bounds__(32 + 32 * NFW, NFW >= 4 ? 1 : 4) k7f_sweep(K7Params q, const __grid_constant__ K7Maps tm) {
   extern __shared__ unsigned char k7raw[];
   unsigned char *k7s = k7raw + ((1024u - (gs_smem_u32(k7raw) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

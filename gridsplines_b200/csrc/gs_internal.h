@@ -83,7 +83,7 @@ struct gs_ctx {
   int64_t opt_k7_fuse = 2;      // K7: faces evaluated inside the sweep by a producer warp (k7f_sweep): 0 never, 1 literal constants, 2 tables too
   int64_t opt_k7_nsb = 8;       // K7: most stages of the backward ring (as many as fit shared memory, up to this)
   int64_t opt_k7_promo = 0;     // K7 x sweep: 256-byte L2 promotion of the 16-column boxes
-  int64_t opt_k7f_nfw = 0;      // K7F: faces warps per CTA for tables (2, 3 or 4; 0 = automatic)
+  int64_t opt_k7f_nfw = 0;      // K7F: faces warps per CTA for tables (2, 3 or 4; 0 = automatic: 4 / 3 / 2 for at most one / two / more strips per SM)
   int64_t opt_k7 = 1;           // K7: exact sweeps from precomputed faces (0: first-draft k_xsweep / k_ysweep)
   int64_t opt_host_chunk_mb = 64;
   int64_t opt_ck_block = 16;
