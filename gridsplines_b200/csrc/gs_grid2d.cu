@@ -1542,13 +1542,16 @@ static int k5_prepare(gs_grid2d *g, bool xdir, double time) {
   const gs_dim2d &d = xdir ? g->x : g->y;
   const int n = d.n;
   const int sf = xdir ? GS_LEFT : GS_UPP, sl = xdir ? GS_RIGHT : GS_LOW;
+  // (caller-owned arrays bound with gs_grid2d_bind_device may be less than 16-byte aligned: no tensor maps then)
+  const bool al = aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
   if (kd.valid && kd.time == time && kd.kind_first == g->b[sf].kind && kd.kind_last == g->b[sl].kind &&
-      kd.pool_gen == ctx->spline_off.size() && kd.opt_sig == k5_opt_sig(ctx))
+      kd.pool_gen == ctx->spline_off.size() && kd.opt_sig == k5_opt_sig(ctx) && kd.aligned == al)
     return GS_OK;
+  kd.aligned = al;
   kd.cs = k5_cluster(ctx, xdir ? k5_sweep<true, false, 2> : k5_sweep<false, false, 2>, xdir, n, xdir ? g->rows : g->cols, &kd.m, &kd.S);
   // K5T: tensor-map strides are multiples of 16 bytes (an even number of columns)
   kd.soft = false;
-  kd.tma = !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, xdir ? g->rows : g->cols, &kd.m, &kd.S, &kd.NT, &kd.cs, &kd.soft);
+  kd.tma = al && !(g->cols & 1) && k5t_plan(ctx, xdir ? 0 : 1, n, xdir ? g->rows : g->cols, &kd.m, &kd.S, &kd.NT, &kd.cs, &kd.soft);
   kd.opt_sig = k5_opt_sig(ctx);
   if (!kd.tab) {
     GS_CUDA(cudaMalloc(&kd.tab, (size_t)n * sizeof(double4)));
@@ -1648,7 +1651,7 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
     q.strip = std::max(24, (q.d.nlines + ctx->sm_count - 1) / ctx->sm_count);
     blocks = (q.d.nlines + q.strip - 1) / q.strip;
   }
-  if (kd.tma && aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result)) {
+  if (kd.tma) {
     K5TMaps tm;
     const uint64_t c = (uint64_t)g->cols, r = (uint64_t)g->rows;
     // lines per CTA: one CTA per SM and a memory-bound kernel, so what counts is waves x strip width (4096 lines: 147

@@ -101,6 +101,7 @@ struct gs_k5dir {
   double time = 0.0;
   int kind_first = -1, kind_last = -1, m = 0, S = 0, cs = 1;   // S: segments (warps) per CTA, cs: CTAs per strip
   bool tma = false;     // K5T (tensor-map TMA rings) instead of k5_sweep
+  bool aligned = true;  // the grid's arrays were 16-byte aligned when the shape was chosen
   int NT = 0;           // K5T: tiles per warp ring
   long long opt_sig = -1;   // the tuning options the shape was chosen under
   // K5T strip groups without a hardware cluster (more CTAs per strip than fit one GPC): segment results and the solved

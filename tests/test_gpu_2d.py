@@ -529,6 +529,37 @@ def test_k5t_x_sweep_bits_equal_k5_with_the_same_segments(gs, ctx):
     assert_bit_equal(out["k5t"], out["k5"], "K5T x sweep vs k5_sweep")
 
 
+def test_k5_on_caller_owned_arrays_that_are_not_16_byte_aligned(gs):
+    """gs_grid2d_bind_device with buffers that start 8 bytes into an allocation: tensor maps need 16-byte alignment, so the
+    constant-coefficient sweeps fall back from K5T to k5_sweep (clusters, not soft groups) -- same answer as library-owned
+    arrays far inside the tolerance."""
+    import torch
+
+    p = cases.bc_problem("TFFT", xdir=1, ydir=0, cols=2048, rows=96, coefs="const")
+    ref = p.build_gs(gs)
+    ref.set_solver(gs.SOLVER_PARTITIONED)
+    ref.iteration(900.0, nsteps=2)
+    want = cases.snapshot(ref)
+    g = p.build_gs(gs)
+    g.set_solver(gs.SOLVER_PARTITIONED)
+    n = p.grid0.size
+    keep = []
+    for which, init in ((gs.GRID, p.grid0), (gs.PREDICT, p.predict0 if hasattr(p, "predict0") else p.grid0), (gs.RESULT, None)):
+        buf = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+        view = buf[1:]
+        assert view.data_ptr() % 16 == 8
+        if init is not None:
+            view.copy_(torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64).ravel()))
+        torch.cuda.synchronize()
+        g.bind_device(which, view.data_ptr())
+        keep.append(buf)
+    g.iteration(900.0, nsteps=2)
+    got = cases.snapshot(g)
+    assert g.status == 0
+    for k in ("grid", "predict"):
+        assert max_rel_err(got[k], want[k]) <= 2e-13, k
+
+
 def test_k5_triple_buffer_variant(O, gs, ctx):
     """Option k5_nb = 3: three tile buffers per warp on the y sweep (measured slower, kept as a tested variant)."""
     ctx.set_option("k5_nb", 3)
