@@ -250,10 +250,18 @@ def _device_arrays(gs, torch, g, n):
     return out
 
 
-def _roof(updates, bytes_per_update, ms, peak):
+def _roof(updates, bytes_per_update, ms, peak, config=None):
+    """Roofline of one extra config on the algorithmic-bytes model; `traffic` = DRAM bytes per step of its kernels from the
+    committed ncu --set full summaries (profiles/traffic.json), or null."""
     achieved = bytes_per_update * updates / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "algorithmic_bytes_per_update": bytes_per_update}
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "algorithmic_bytes_per_update": bytes_per_update}
+    if config is not None:
+        t = ((ncu_traffic() or {}).get("configs") or {}).get(config)
+        out["traffic"] = t["bytes_per_step"] if t else None
+        if t:
+            out["traffic_gbs"] = t["bytes_per_step"] / (ms * 1e-3) / 1e9
+    return out
 
 
 def bench_c1(gs, ctx, torch, stream):
@@ -299,7 +307,7 @@ def bench_c3(gs, ctx, torch, stream, peak, steps=20, n=4096):
     exact.close(); fast.close()
     cells = float(n) * n
     return {"workload": f"C3: 2-D ortho x ortho {n}x{n}, constant properties, Dirichlet 20/4 + Neumann 50/0, one 64x64 flat patch",
-            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
+            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak, "C3"),
             "solver": "AUTO -> K5T (hoisted partitioned sweeps on tensor-map TMA rings, tolerance family)",
             "parity": {"after_steps": 100, "against": "GS_SOLVER_THOMAS (K7, bit-exact vs the oracle: tests/test_gpu_k7.py)", **par},
             "exact_solver": {"ms_per_step": ms_exact, "updates_per_s": cells / (ms_exact * 1e-3),
@@ -329,7 +337,7 @@ def bench_c4(gs, ctx, torch, stream, peak, steps=5, n=16384):
     g.close()
     cells = float(n) * n
     return {"workload": f"C4: 2-D radial x ortho {n}x{n}, M1Hermite3 k(T), c(T), alpha = k / c, Dirichlet 30 / 7",
-            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak),
+            "ms_per_step": ms, "updates_per_s": cells / (ms * 1e-3), "roofline": _roof(cells, BYTES_PER_UPDATE_2D, ms, peak, "C4"),
             "solver": "AUTO -> K7F (faces warps + per-thread Thomas in the reference's order: bit-exact)",
             "parity": {"statement": "bit-exact vs the oracle (tests/test_gpu_k7.py: 4096^2 C4 shape, every node, 2 steps)"},
             "tolerance_family": {"solver": "GS_SOLVER_PARTITIONED -> K6", "ms_per_step": ms_part,
@@ -355,7 +363,7 @@ def bench_c5(gs, ctx, torch, stream, peak, steps=5, lines=4096, n=65536, parity=
     ms = _time_steps(torch, stream, lambda: g.step(TIME_STEP), steps, 2)
     out = {"workload": f"C5: {lines} lines x {n} nodes, ortho, constant properties, per-line Dirichlet ends",
            "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
-           "roofline": _roof(float(lines) * n, BYTES_PER_UPDATE_1D, ms, peak),
+           "roofline": _roof(float(lines) * n, BYTES_PER_UPDATE_1D, ms, peak, "C5"),
            "solver": "AUTO -> K5T (partitioned Thomas: segments + reduced system on TMA rings, tolerance family)"}
     if parity:
         g.upload(gs.GRID, grid0); g.fill(gs.PREDICT, 4.0)
