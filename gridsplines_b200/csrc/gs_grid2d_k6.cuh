@@ -89,19 +89,25 @@ GS_DEV K6Tab k6_tab(const double *h) { return gs_tab_view(h); }
 GS_DEV bool k6_face_fast(const K6Tab &z, double p0, double p1, double &v) {
   const bool lt = p0 < p1;
   const double lo = lt ? p0 : p1, hi = lt ? p1 : p0;
-  bool good = z.fast && (lo > z.lowerX) && (hi < z.upperX) && (lo < hi) && (lo >= z.k0);
+  bool good = z.fast && (lo > z.lowerX) && (hi < z.upperX) && (lo < hi);   // (lo >= knots[0] follows from lo >= ka below)
   int i = (int)((lo - z.k0) * z.inv_h);          // saturating conversion; NaN -> 0
   i = max(0, min(z.np - 1, i));
-  double ka = z.knots[i], kb = z.knots[i + 1];
-  if (lo < ka) { i = max(i - 1, 0); kb = ka; ka = z.knots[i]; }
-  else if (lo >= kb) { i = min(i + 1, z.np - 1); ka = kb; kb = z.knots[i + 1]; }
+  // one-step fix-up of the arithmetic piece index, written with selects (the four knots around it are loaded up front):
+  // a data-dependent branch here would keep the compiler from interleaving the faces of a batch
+  const double km = z.knots[max(i - 1, 0)], k1 = z.knots[i], k2 = z.knots[i + 1], kc = z.knots[min(i + 2, z.np)];
+  const bool down = lo < k1, up = !down && (lo >= k2);
+  i = down ? max(i - 1, 0) : (up ? min(i + 1, z.np - 1) : i);
+  const double ka = down ? km : (up ? k2 : k1), kb = down ? k1 : (up ? kc : k2);
   good = good && (lo >= ka) && (hi < kb);
   const double *pc = z.pieces + i * GS_PIECE;
   const double x0 = pc[0], a1 = pc[1], a2 = pc[5], a3 = pc[6], a4 = pc[7];
   const double su = hi - x0, sl = lo - x0;
   const double Au = fma(fma(fma(fma(a4, su, a3), su, a2), su, a1), su, 0.0);   // gs_cubic_antider
   const double Al = fma(fma(fma(fma(a4, sl, a3), sl, a2), sl, a1), sl, 0.0);
-  const double area = 0.0 + (Au - Al) + 0.0;
+  // the reference's 0.0 + (Au - Al) + 0.0 (lowerArea + middleArea + upperArea) equals Au - Al bit for bit: adding +0.0
+  // changes nothing but -0.0, and Au - Al is never -0.0 (Au, Al end in fma(., ., +0.0), so neither is -0.0, and equal
+  // operands give +0.0 in round-to-nearest)
+  const double area = Au - Al;
   bool okd = true;
   v = gs_div<true>(area, gs_rcp<true>(hi - lo, okd), okd);
   return good && okd;
