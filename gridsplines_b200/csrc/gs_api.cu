@@ -126,6 +126,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "k5t_wide")) ctx->opt_k5t_wide = (int)value;
   else if (!strcmp(name, "k5t_ystrip")) ctx->opt_k5t_ystrip = (int)value;
   else if (!strcmp(name, "k5t_soft")) ctx->opt_k5t_soft = value != 0;
+  else if (!strcmp(name, "k5t_pdl")) ctx->opt_k5t_pdl = value != 0;
   else if (!strcmp(name, "k5t_hints")) ctx->opt_k5t_hints = (int)value;
   else if (!strcmp(name, "k6")) ctx->opt_k6 = value;
   else if (!strcmp(name, "faces1d")) ctx->opt_faces1d = value;

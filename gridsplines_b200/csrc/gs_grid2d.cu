@@ -1504,8 +1504,10 @@ static int k5t_soft_buffers(gs_ctx *ctx, gs_k5dir &kd, int strips) {
   }
   return GS_OK;
 }
-static int k5t_launch(gs_ctx *ctx, int kind, bool wide, int blocks, int S, int NT, int cs, const K5Params &q, const K5TMaps &tm) {
+static int k5t_launch(gs_ctx *ctx, int kind, bool wide, int blocks, int S, int NT, int cs, const K5Params &q0, const K5TMaps &tm) {
+  K5Params q = q0;
   const int hw = q.soft ? 1 : cs;   // soft groups: plain CTAs
+  q.pdl = ctx->opt_k5t_pdl ? 1 : 0;
   k5t_kern_t kern = k5t_kernel(kind, S, wide);
   GS_TRY(k5t_configure(ctx, kern));
   cudaLaunchConfig_t cfg = {};
@@ -1513,11 +1515,14 @@ static int k5t_launch(gs_ctx *ctx, int kind, bool wide, int blocks, int S, int N
   cfg.blockDim = dim3(32 * S);
   cfg.dynamicSmemBytes = k5t_smem(kind == 0, wide, S, NT, hw);
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = hw; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the CTAs' set-up overlaps the tail of the previous kernel of the stream
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = q.pdl ? 2 : 1;
   GS_CUDA(cudaLaunchKernelEx(&cfg, kern, q, NT, (int)ctx->opt_k5t_hints, tm));
   return GS_OK;
 }
@@ -1606,7 +1611,7 @@ static int launch_k5(gs_grid2d *g, double time, bool xdir) {
   GS_TRY(k5_prepare(g, xdir, time));
   gs_k5dir &kd = xdir ? g->k5x : g->k5y;
   K5Params q;
-  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr;
+  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr; q.pdl = 0;
   q.d.n = xdir ? g->cols : g->rows;
   q.d.nlines = xdir ? g->rows : g->cols;
   q.d.m = kd.m; q.d.S = kd.S;
@@ -1747,7 +1752,7 @@ int gs_k5_1d_step(gs_grid1d *g, double time, int nsteps) {
     kd.time = time;
   }
   K5Params q;
-  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr;
+  q.soft = 0; q.epoch = 0; q.g_buf = nullptr; q.g_sync = nullptr; q.pdl = 0;
   q.d.n = n;
   q.d.nlines = (int)g->nlines;
   q.d.m = kd.m; q.d.S = kd.S;

@@ -54,6 +54,7 @@ struct K5Params {
   unsigned epoch;        // number of this launch on these buffers (1, 2, ...)
   double *g_buf;         // [3][strips][csize * S][32]: lambda_e, Q, x at the segment ends
   unsigned *g_sync;      // [strips][2]
+  int pdl;               // K5T: launched with programmatic stream serialisation (griddepcontrol.wait before the first access)
 };
 
 // ---- setup: line-independent elimination ------------------------------------------------------------------

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
   }
   gs_fence_proxy_async();
   __syncwarp();
+  // launched with programmatic stream serialisation: everything above overlaps the tail of the kernel before this one
+  // in the stream; nothing below may run before that kernel's writes are complete and visible
+  if (q.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const size_t ck_pitch = (size_t)((d.nlines + 31) / 32) * 32;
   const int s = (crank * S + k) * m, e = min(n, s + m) - 1;

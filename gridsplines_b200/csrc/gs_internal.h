@@ -69,6 +69,7 @@ struct gs_ctx {
   int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles)
   int opt_k5t_sx = 0, opt_k5t_sy = 0, opt_k5t_s1 = 0;   // K5T: warps (segments) per CTA of the x / y / 1-D sweeps (0 = automatic)
   int opt_k5t_promo = 1;       // K5T x sweep: L2 promotion of the tensor maps (0: 128 B, 1: 256 B; measured: x sweep 4096^2 75 -> 72 us, 16384^2 1.21 -> 1.15 ms)
+  int opt_k5t_pdl = 1;         // K5T: programmatic dependent launch (set-up overlaps the previous kernel's tail)
   int opt_k5t_soft = 1;        // K5T: strip groups through global memory when they put more CTAs to work than clusters
   int opt_k5t_ystrip = 0;      // K5T y sweep: columns per CTA (even, <= 32; 0 = automatic)
   int opt_k5t_wide = 1;        // K5T x sweep: 32-column stages loaded as one un-swizzled 34-column box (272-byte rows)
