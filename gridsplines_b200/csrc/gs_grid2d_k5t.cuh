@@ -108,8 +108,9 @@ __global__ void __launch_bounds__(MAXT) k5t_sweep(K5Params q, int NT, int hints,
   // box coordinates (innermost first) of the chunk / stage that starts at node i0
   auto c0_of = [&](int i0) { return XDIR ? i0 : (ONED ? 0 : line0); };
   auto c1_of = [&](int i0) { return XDIR ? line0 : (ONED ? strip_id * n + i0 : i0); };
-  // L2 hints (option): what phase A reads comes back in phase C (evict_last); phase C's reads and all results are
-  // not touched again by this kernel (evict_first)
+  // L2 hints (option k5t_hints, off: measured within noise or slower -- keeping only the half of a segment that phase C
+  // re-reads first was slower too, x sweep 81 against 70 us): what phase A reads comes back in phase C (evict_last);
+  // phase C's reads and all results are not touched again by this kernel (evict_first)
   const uint64_t pol_keep = gs_policy_evict_last(), pol_stream = gs_policy_evict_first();
   // lane 0: stage number `sc` of the segment (nodes s + sc * CPS * 16 ...) -> tile `st` (+ the tile after it for the old
   // grid values) and table slot `ts`
