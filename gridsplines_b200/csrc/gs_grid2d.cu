@@ -2009,11 +2009,10 @@ static bool use_k7(gs_grid2d *g, bool xdir) {
   if (n < 4 || (g->cols & 1)) return false;
   return aligned16(g->grid) && aligned16(g->predict) && aligned16(g->result);
 }
-static int k7_promo = 0;   // x sweep boxes: 256-byte L2 promotion (set from option k7_promo before a launch encodes its maps)
-static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox, bool pred_box = false) {
+static int k7_encode(K7Map *out, const void *base, int cols, int rows, bool xbox, bool pred_box = false, int promo = 0) {
   // pred_box (fused faces): one more node along the line, 18 columns (a 16-byte multiple) without the swizzle for x
   return gs_encode_map2d(out, base, (uint64_t)cols, (uint64_t)rows, xbox ? (pred_box ? 18u : 16u) : 32u,
-                         xbox ? 32u : (pred_box ? 17u : 16u), xbox && !pred_box, xbox ? k7_promo : 0);
+                         xbox ? 32u : (pred_box ? 17u : 16u), xbox && !pred_box, xbox ? promo : 0);
 }
 
 static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
@@ -2070,11 +2069,11 @@ static int launch_k7(gs_grid2d *g, double time, bool xdir, bool fuse) {
   q.nsb = (int)ctx->opt_k7_nsb;
   q.maps = fq.sw.maps;
   K7Maps tm;
-  k7_promo = (int)ctx->opt_k7_promo;
-  GS_TRY(k7_encode(&tm.F, fused ? (const void *)g->predict : (const void *)fq.F, g->cols, g->rows, xdir));
-  GS_TRY(k7_encode(&tm.rhs, fq.sw.rhs, g->cols, g->rows, xdir));
-  GS_TRY(k7_encode(&tm.gold, g->grid, g->cols, g->rows, xdir));
-  GS_TRY(k7_encode(&tm.out, g->result, g->cols, g->rows, xdir));
+  const int promo = (int)ctx->opt_k7_promo;   // x sweep boxes: 256-byte L2 promotion (measured neutral: off)
+  GS_TRY(k7_encode(&tm.F, fused ? (const void *)g->predict : (const void *)fq.F, g->cols, g->rows, xdir, false, promo));
+  GS_TRY(k7_encode(&tm.rhs, fq.sw.rhs, g->cols, g->rows, xdir, false, promo));
+  GS_TRY(k7_encode(&tm.gold, g->grid, g->cols, g->rows, xdir, false, promo));
+  GS_TRY(k7_encode(&tm.out, g->result, g->cols, g->rows, xdir, false, promo));
   GS_TRY(k7_encode(&tm.pred, g->predict, g->cols, g->rows, xdir, true));
   if (fused) {
     // literal constants: one faces warp keeps up with the chain warp; tables: two (each takes half of a chunk's nodes)
