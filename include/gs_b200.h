@@ -146,7 +146,10 @@ int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double *rightT, in
 int gs_grid1d_step(gs_grid1d *g, double time, int nsteps);
 /* The drop-in OneDGrid.step with HOST state (the public `grid` array, A/OneDGrid.scala:20): upload grid, nsteps
  * steps, download grid -- chunked over line blocks and pipelined (H2D / compute / D2H overlap).  host_grid is
- * LINE_MAJOR [nlines][n], updated in place; `predict` (private in the reference) stays on the device. */
+ * LINE_MAJOR [nlines][n], updated in place; `predict` (private in the reference) stays on the device.
+ * Solver: always the per-thread Thomas kernels (bit-exact), chunk by chunk -- also for long constant-property lines,
+ * where gs_grid1d_step under GS_SOLVER_AUTO takes the partitioned solver (tolerance 1e-12): a chunk of lines does not
+ * change what a line computes, so results equal gs_grid1d_step with GS_SOLVER_THOMAS. */
 int gs_grid1d_step_host(gs_grid1d *g, double time, int nsteps, double *host_grid, const double *leftT,
                         const double *rightT, int bc_stride);
 int gs_grid1d_set_solver(gs_grid1d *g, int solver);
