@@ -238,3 +238,15 @@ def test_long_lines_k5t_variants(O, gs, ctx, nlines, n):
     finally:
         for k, v in defaults.items():
             ctx.set_option(k, v)
+
+
+def test_long_line_kernels_are_deterministic(gs):
+    """Same idea as tests/test_gpu_2d.py::test_ring_kernels_are_deterministic for the 1-D K5T paths: soft groups (few
+    strips), clusters and plain CTAs must give the same bits on every run."""
+    for nlines, n in ((64, 16384), (600, 8192), (33, 2048)):
+        kw = dict(nlines=nlines, n=n, steps=3, spline="const", random_grid=True)
+        first = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
+        for _ in range(4):
+            again = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
+            for k in ("grid", "predict"):
+                assert_bit_equal(again[k], first[k], f"{nlines} x {n} {k}")

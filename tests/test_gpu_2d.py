@@ -560,6 +560,28 @@ def test_k5_on_caller_owned_arrays_that_are_not_16_byte_aligned(gs):
         assert max_rel_err(got[k], want[k]) <= 2e-13, k
 
 
+@pytest.mark.parametrize("cols,rows,coefs,solver", [(4096, 300, "const", 2), (2048, 64, "const", 2), (64, 2048, "const", 2),
+                                                    (1000, 140, "const", 2), (512, 384, "hermite", 1), (130, 257, "hermite", 1)])
+def test_ring_kernels_are_deterministic(gs, cols, rows, coefs, solver):
+    """compute-sanitizer is closed on this pool (profiles/r2_sanitizer_closed.txt), so the mbarrier rings, cluster /
+    soft-group rendezvous and in-place shared-memory rewrites of K5T and K7F are checked the other way round: a race there
+    shows up as run-to-run differences.  Five runs of three steps from the same state must agree bit for bit."""
+    sol = gs.SOLVER_PARTITIONED if solver == 2 else gs.SOLVER_THOMAS
+    p = cases.bc_problem("TFFT" if coefs == "const" else "TTTT", xdir=1, ydir=0, cols=cols, rows=rows, coefs=coefs)
+    first = None
+    for run in range(5):
+        g = p.build_gs(gs)
+        g.set_solver(sol)
+        g.iteration(900.0, nsteps=3)
+        snap = cases.snapshot(g)
+        assert g.status == 0
+        if first is None:
+            first = snap
+        else:
+            for k in ("grid", "predict"):
+                assert_bit_equal(snap[k], first[k], f"run {run} {k}")
+
+
 def test_k5_triple_buffer_variant(O, gs, ctx):
     """Option k5_nb = 3: three tile buffers per warp on the y sweep (measured slower, kept as a tested variant)."""
     ctx.set_option("k5_nb", 3)
