@@ -117,7 +117,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "k5_xstrip")) ctx->opt_k5_xstrip = value;
   else if (!strcmp(name, "k5_cluster")) ctx->opt_k5_cluster = value != 0;
   else if (!strcmp(name, "k5_nb")) ctx->opt_k5_nb = (int)value;
-  else if (!strcmp(name, "k5t")) ctx->opt_k5t = value != 0;
+  else if (!strcmp(name, "k5t")) ctx->opt_k5t = (int)value;   // 0 never, 1 from 2^20 nodes per sweep, 2 always
   else if (!strcmp(name, "k5t_sx")) ctx->opt_k5t_sx = (int)value;
   else if (!strcmp(name, "k5t_sy")) ctx->opt_k5t_sy = (int)value;
   else if (!strcmp(name, "k5t_s1")) ctx->opt_k5t_s1 = (int)value;

@@ -1378,7 +1378,7 @@ static int k5_cluster(gs_ctx *ctx, void (*kern)(K5Params), bool xdir, int n, int
 // K5T (gs_grid2d_k5t.cuh): the tuning options a shape was chosen under, and the shape itself.
 // kind: 0 = x sweep, 1 = y sweep (2-D), 2 = 1-D batch.  Returns false where K5T does not apply (k5_sweep then runs).
 static long long k5_opt_sig(gs_ctx *ctx) {
-  return (long long)ctx->opt_k5t | ((long long)(ctx->opt_k5t_sx & 255) << 1) | ((long long)(ctx->opt_k5t_sy & 255) << 9) |
+  return ((long long)(ctx->opt_k5t & 3) << 40) | ((long long)(ctx->opt_k5t_sx & 255) << 1) | ((long long)(ctx->opt_k5t_sy & 255) << 9) |
          ((long long)(ctx->opt_k5t_s1 & 255) << 17) | ((long long)(ctx->opt_k5t_nt & 255) << 25) |
          ((long long)ctx->opt_k5_cluster << 33) | ((long long)ctx->opt_k5t_wide << 34) | ((long long)ctx->opt_k5t_soft << 36);
 }
@@ -1409,6 +1409,9 @@ static int k5t_configure(gs_ctx *ctx, k5t_kern_t kern) {
 // cluster must be resident at once).  Returns false where K5T does not apply (k5_sweep then runs).
 static bool k5t_plan(gs_ctx *ctx, int kind, int n, int nlines, int *m, int *S, int *NT, int *cs_out, bool *soft_out) {
   if (!ctx->opt_k5t) return false;
+  // small problems are latency-bound and k5_sweep's cp.async tiles start faster than tensor-map boxes (MEASURED ms per
+  // step K5T / K5: 256^2 0.0285 / 0.0247, 512^2 0.0298 / 0.0268, 1024^2 0.0343 / 0.0360, 2048^2 0.0556 / 0.0699)
+  if (ctx->opt_k5t < 2 && (long long)n * nlines < (1ll << 20)) return false;
   const bool xdir = kind == 0, wide = k5t_wide(ctx, kind, n);
   int smax = kind == 0 ? ctx->opt_k5t_sx : (kind == 1 ? ctx->opt_k5t_sy : ctx->opt_k5t_s1);
   if (smax <= 0) smax = (xdir && !wide) ? 16 : 8;

@@ -66,7 +66,7 @@ struct gs_ctx {
   int64_t opt_k5_xstrip = 0;   // 0 = automatic
   int opt_k5_nb = 2;           // K5: tile buffers per warp (3: triple buffer where it fits; measured slower)
   int opt_k5_cluster = 1;      // K5: clusters of 2 / 4 / 8 CTAs per strip when strips alone would not fill the chip
-  int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles)
+  int opt_k5t = 1;             // K5T: K5's sweeps on tensor-map TMA rings (0: k5_sweep with its cp.async tiles; 1: from 2^20 nodes per sweep; 2: always)
   int opt_k5t_sx = 0, opt_k5t_sy = 0, opt_k5t_s1 = 0;   // K5T: warps (segments) per CTA of the x / y / 1-D sweeps (0 = automatic)
   int opt_k5t_promo = 1;       // K5T x sweep: L2 promotion of the tensor maps (0: 128 B, 1: 256 B; measured: x sweep 4096^2 75 -> 72 us, 16384^2 1.21 -> 1.15 ms)
   int opt_k5t_pdl = 1;         // K5T: programmatic dependent launch (set-up overlaps the previous kernel's tail)

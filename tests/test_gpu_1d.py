@@ -229,7 +229,7 @@ def test_long_lines_k5t_variants(O, gs, ctx, nlines, n):
     defaults = {"k5t": 1, "k5t_soft": 1, "k5_cluster": 1, "k5t_s1": 0}
     try:
         for opts in ({}, {"k5t": 0}, {"k5t_soft": 0}, {"k5_cluster": 0}, {"k5t_s1": 4}):
-            for k, v in {**defaults, **opts}.items():
+            for k, v in {**defaults, "k5t": 2, **opts}.items():   # k5t = 2: K5T also below its size threshold
                 ctx.set_option(k, v)
             got = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
             for k in ("grid", "predict"):
@@ -243,10 +243,14 @@ def test_long_lines_k5t_variants(O, gs, ctx, nlines, n):
 def test_long_line_kernels_are_deterministic(gs):
     """Same idea as tests/test_gpu_2d.py::test_ring_kernels_are_deterministic for the 1-D K5T paths: soft groups (few
     strips), clusters and plain CTAs must give the same bits on every run."""
-    for nlines, n in ((64, 16384), (600, 8192), (33, 2048)):
-        kw = dict(nlines=nlines, n=n, steps=3, spline="const", random_grid=True)
-        first = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
-        for _ in range(4):
-            again = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
-            for k in ("grid", "predict"):
-                assert_bit_equal(again[k], first[k], f"{nlines} x {n} {k}")
+    gs.default_context().set_option("k5t", 2)   # K5T also below its size threshold
+    try:
+        for nlines, n in ((64, 16384), (600, 8192), (33, 2048)):
+            kw = dict(nlines=nlines, n=n, steps=3, spline="const", random_grid=True)
+            first = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
+            for _ in range(4):
+                again = cases.run_batch(gs, solver=gs.SOLVER_PARTITIONED, **kw)
+                for k in ("grid", "predict"):
+                    assert_bit_equal(again[k], first[k], f"{nlines} x {n} {k}")
+    finally:
+        gs.default_context().set_option("k5t", 1)

@@ -494,7 +494,7 @@ def test_k5t_tma_rings_match_k5(O, gs, ctx, cols, rows, combo):
     defaults = {"k5t": 1, "k5t_wide": 1, "k5t_sx": 0, "k5t_soft": 1, "k5t_hints": 0, "k5t_promo": 1, "k5t_nt": 0}
     try:
         for name, opts in variants:
-            for k, v in {**defaults, **opts}.items():
+            for k, v in {**defaults, "k5t": 2, **opts}.items():   # k5t = 2: K5T also below its size threshold
                 ctx.set_option(k, v)
             g = p.build_gs(gs)
             g.set_solver(gs.SOLVER_PARTITIONED)
@@ -516,7 +516,7 @@ def test_k5t_x_sweep_bits_equal_k5_with_the_same_segments(gs, ctx):
     p = cases.bc_problem("TFFT", xdir=0, ydir=0, cols=4096, rows=70, coefs="const")
     out = {}
     try:
-        for name, opts in (("k5", {"k5t": 0, "k5_cluster": 0}), ("k5t", {"k5t": 1, "k5_cluster": 0, "k5t_wide": 0, "k5t_sx": 16})):
+        for name, opts in (("k5", {"k5t": 0, "k5_cluster": 0}), ("k5t", {"k5t": 2, "k5_cluster": 0, "k5t_wide": 0, "k5t_sx": 16})):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             g = p.build_gs(gs)
@@ -569,17 +569,21 @@ def test_ring_kernels_are_deterministic(gs, cols, rows, coefs, solver):
     sol = gs.SOLVER_PARTITIONED if solver == 2 else gs.SOLVER_THOMAS
     p = cases.bc_problem("TFFT" if coefs == "const" else "TTTT", xdir=1, ydir=0, cols=cols, rows=rows, coefs=coefs)
     first = None
-    for run in range(5):
-        g = p.build_gs(gs)
-        g.set_solver(sol)
-        g.iteration(900.0, nsteps=3)
-        snap = cases.snapshot(g)
-        assert g.status == 0
-        if first is None:
-            first = snap
-        else:
-            for k in ("grid", "predict"):
-                assert_bit_equal(snap[k], first[k], f"run {run} {k}")
+    gs.default_context().set_option("k5t", 2)   # K5T also below its size threshold
+    try:
+        for run in range(5):
+            g = p.build_gs(gs)
+            g.set_solver(sol)
+            g.iteration(900.0, nsteps=3)
+            snap = cases.snapshot(g)
+            assert g.status == 0
+            if first is None:
+                first = snap
+            else:
+                for k in ("grid", "predict"):
+                    assert_bit_equal(snap[k], first[k], f"run {run} {k}")
+    finally:
+        gs.default_context().set_option("k5t", 1)
 
 
 def test_k5_triple_buffer_variant(O, gs, ctx):
