@@ -11,17 +11,22 @@
 //   * results leave through per-warp output tiles as box stores (UTMASTG): x sweep `result`; y sweep the new grid and
 //     the new predict (Grid.update :474-481 applied on the way out); the old grid values of Grid.update arrive as a
 //     second box of the stage (2-D) or are the right-hand side itself (1-D batches).
-//   * WIDE x sweep: the TMA unit pays per box ROW, and a 128-byte row per request caps an SM at ~15 B/clk (measured:
-//     4.3 TB/s chip-wide).  The wide variant loads 32 columns per stage as ONE un-swizzled box of 34 columns (272-byte
+//   * WIDE x sweep (lines of >= 8192 nodes): 32 columns per stage arrive as ONE un-swizzled box of 34 columns (272-byte
 //     rows: the two extra columns make the row pitch 17 x 16 bytes, so that a lane reads its row 16 bytes at a time
-//     without bank conflicts) and handles it as two chunks of 16; results still leave as swizzled 16-column boxes.
+//     without bank conflicts) and are handled as two chunks of 16; results still leave as swizzled 16-column boxes.
+//     Wider row pieces per request measured +3 % at 16384^2 and nothing at 4096^2, where the 70 us kernel is made of
+//     its ramps.
 // Shared memory per warp: NT stage tiles (4 KB; wide x: 8.5 KB), NT + 1 table slots (the slot of the chunk being
 // processed must survive the refill), 1 (x) or 2 (y) output tiles, NT mbarriers.  One CTA = S warps = S segments.
 // Restrictions (the host falls back to k5_sweep otherwise): an even number of columns and 16-byte aligned arrays
 // (tensor-map strides), 1-D batches with n % 16 == 0 (a box must not straddle two 32-line blocks).
-// With few strips (a shard of a batch, a small grid) a strip belongs to a thread-block cluster of csize CTAs, as in
-// k5_sweep: CTA `crank` owns segments crank * S .. crank * S + S - 1, the first CTA's warp 0 solves the reduced system
-// of all of them through distributed shared memory.
+// With few strips (a shard of a batch, a small grid) a strip is split over csize CTAs -- CTA `crank` owns segments
+// crank * S .. crank * S + S - 1 -- either a thread-block cluster (any size up to 8 that is fully resident; the first
+// CTA's warp 0 solves the reduced system of all segments through distributed shared memory, as in k5_sweep) or a SOFT
+// group (q.soft: plain CTAs, all resident, that meet through global memory: segment results published with a release,
+// arrival counter, the first CTA stages and solves in shared memory and releases a `done` word; bounded spins), taken
+// when it puts more CTAs to work than the GPCs allow clusters to.  Kernels are launched with programmatic stream
+// serialisation (q.pdl): everything before griddepcontrol.wait overlaps the previous kernel's tail.
 #pragma once
 #include <cooperative_groups.h>
 
