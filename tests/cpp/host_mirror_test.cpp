@@ -170,6 +170,27 @@ static void device_sections(Context &ctx) {
     g.write(w, "\n");
     print_text("patched_write", w.str());
   }
+  {  // one TwoDGrid behind gs_sharded2d_* (here: one device), constant coefficients
+    std::vector<double> xr(64), yr(48);
+    for (int i = 0; i < 64; ++i) xr[i] = 0.01 * (i + 1);
+    for (int i = 0; i < 48; ++i) yr[i] = 0.02 * (i + 1);
+    XDim x(0.0, xr, 0.65, GS_ORTHO);
+    YDim y(0.0, yr, 0.98, GS_ORTHO);
+    TwoDGrid::BoundSpec manyTemp{GS_DENSE, GS_TEMP};
+    ShardedTwoDGrid s(x, y, {0}, manyTemp, manyTemp, manyTemp, manyTemp);
+    s.setConstantCoef(Spline::constant(1.5), Spline::constant(2.2e6), Spline::constant(1.5 / 2.2e6));
+    s.setBound(GS_UPP, 20.0);
+    s.setBound(GS_LOW, 4.0);
+    s.setBound(GS_RIGHT, 9.0);
+    s.setBound(GS_LEFT, 30.0);
+    std::vector<double> init(64 * 48);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = 7.0 + 0.01 * (double)((i * 131) % 97);
+    s.upload(GS_GRID, init);
+    s.upload(GS_PREDICT, init);
+    s.iteration(900.0, 2);
+    print_array("sharded_grid", s.download(GS_GRID));
+    printf("sharded_status %u %d\n", s.status(), s.deviceCount());
+  }
 }
 
 int main(int argc, char **argv) {

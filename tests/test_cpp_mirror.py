@@ -165,3 +165,16 @@ def test_cpp_mirror_device_sections_agree_with_the_python_mirror(tmp_path):
     w = io.StringIO()
     gs.api.twod_write(t, w, "\n")
     assert _text(vals, "patched_write") == w.getvalue()
+    # ShardedTwoDGrid on one device
+    xs = gs.XDim(0.0, [0.01 * (i + 1) for i in range(64)], 0.65, gs.ORTHO)
+    ys = gs.YDim(0.0, [0.02 * (i + 1) for i in range(48)], 0.98, gs.ORTHO)
+    many = (gs.Many, gs.Temp)
+    sh = gs.ShardedTwoDGrid(xs, ys, [0], upp=many, low=many, right=many, left=many)
+    sh.set_constant_coef(S.const(1.5), S.const(2.2e6), S.const(1.5 / 2.2e6))
+    for side, v in ((gs.UPP, 20.0), (gs.LOW, 4.0), (gs.RIGHT, 9.0), (gs.LEFT, 30.0)):
+        sh.set_bound(side, v)
+    init = np.array([7.0 + 0.01 * float((i * 131) % 97) for i in range(64 * 48)]).reshape(48, 64)
+    sh.upload(gs.GRID, init)
+    sh.upload(gs.PREDICT, init)
+    sh.iteration(900.0, nsteps=2)
+    assert vals["sharded_grid"] == _hex(sh.download(gs.GRID)) and vals["sharded_status"] == f"{sh.status} 1"
