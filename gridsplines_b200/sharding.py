@@ -1,7 +1,7 @@
 """Partition helpers for the multi-GPU paths.  One process per GPU (torchrun); batched 1-D lines
 are independent, so sharding them needs NO collective on the data path -- torch.distributed is only used for
-barriers and for the max-over-ranks of device timings.  Row sharding of 2-D grids (next round) uses the same
-contiguous-block rule."""
+barriers and for the max-over-ranks of device timings.  Row sharding of 2-D grids (sharded2d.py, csrc/gs_sharded2d.cu) uses the
+same contiguous-block rule."""
 from __future__ import annotations
 
 from typing import Tuple
