@@ -72,7 +72,7 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
   }
   double a = condL * L.pd[0];
   double c = condR * L.pd[1];
-  double vect = gs_div<FAST>(-G[0], L.rt, ok) - a * t1;
+  double vect = gs_div<FAST, true>(-G[0], L.rt, ok) - a * t1;
   gs_forward_first<FAST>(-(a + c) - L.inv_time, c, vect, delta, lambda, ok);
   sc[0] = make_double2(delta, lambda);
   int i = 1;
@@ -92,7 +92,7 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
     }
     a = condL * L.pd[2 * i];
     c = condR * L.pd[2 * i + 1];
-    vect = gs_div<FAST>(-G[i * GS_LB], L.rt, ok);
+    vect = gs_div<FAST, true>(-G[i * GS_LB], L.rt, ok);
     gs_forward_unit<FAST>(a, -(a + c) - L.inv_time, c, vect, delta, lambda, flags, ok);
     sc[i * GS_LB] = make_double2(delta, lambda);
   }
@@ -108,7 +108,7 @@ GS_DEV bool forward_line(const Line1d &L, const double *__restrict__ G, const do
   }
   a = condL * L.pd[2 * i];
   c = condR * L.pd[2 * i + 1];
-  vect = gs_div<FAST>(-G[i * GS_LB], L.rt, ok) - c * t3;
+  vect = gs_div<FAST, true>(-G[i * GS_LB], L.rt, ok) - c * t3;
   gs_forward_last<FAST>(a, -(a + c) - L.inv_time, vect, delta, lambda, ok);
   return ok;
 }
@@ -277,7 +277,7 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
       }
       a = condL * L.pd[0];
       c_ = condR * L.pd[1];
-      vect = gs_div<FAST>(-sG[0], L.rt, ok) - a * t1;
+      vect = gs_div<FAST, true>(-sG[0], L.rt, ok) - a * t1;
       gs_forward_first<FAST>(-(a + c_) - L.inv_time, c_, vect, delta, lambda, ok);
       so[0] = make_double2(delta, lambda);
       mb = 1;
@@ -301,7 +301,7 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
         }
         a = condL * L.pd[2 * i];
         c_ = condR * L.pd[2 * i + 1];
-        vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok);
+        vect = gs_div<FAST, true>(-sG[m * GS_LB], L.rt, ok);
         gs_forward_unit<FAST>(a, -(a + c_) - L.inv_time, c_, vect, delta, lambda, flags, ok);
         so[m * GS_LB] = make_double2(delta, lambda);
       }
@@ -321,7 +321,7 @@ GS_DEV bool forward_block_tma(const Line1d &L, char *wsm, uint64_t *full, uint32
       }
       a = condL * L.pd[2 * i];
       c_ = condR * L.pd[2 * i + 1];
-      vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok) - c_ * t3;
+      vect = gs_div<FAST, true>(-sG[m * GS_LB], L.rt, ok) - c_ * t3;
       gs_forward_last<FAST>(a, -(a + c_) - L.inv_time, vect, delta, lambda, ok);
     }
     gs_fence_proxy_async_smem();
@@ -567,7 +567,7 @@ GS_DEV void hoist_fwd_node(double g, const double *t, const GsRcp &rt, double &l
   GsRcp rd;
   rd.b = t[1];
   rd.y = t[2];
-  double vect = gs_div<FAST>(-g, rt, ok);
+  double vect = gs_div<FAST, true>(-g, rt, ok);
   lambda = gs_div<FAST>(vect - t[0] * lambda, rd, ok);  // lam :234
 }
 
@@ -619,13 +619,13 @@ GS_DEV bool forward_block_hoist(const LineH &L, char *wsm, uint64_t *full, uint3
           GsRcp rd;
           rd.b = ti[1];
           rd.y = ti[2];
-          double vect = gs_div<FAST>(-sG[0], L.rt, ok) - ti[0] * firstT;   // :65
+          double vect = gs_div<FAST, true>(-sG[0], L.rt, ok) - ti[0] * firstT;   // :65
           lambda = gs_div<FAST>(vect, rd, ok);                              // forwardFirst :245-248
         } else if (i == n - 1) {
           GsRcp rd;
           rd.b = ti[1];
           rd.y = ti[2];
-          double vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok) - c_last * lastT;   // :89
+          double vect = gs_div<FAST, true>(-sG[m * GS_LB], L.rt, ok) - c_last * lastT;   // :89
           lambda = gs_div<FAST>(vect - ti[0] * lambda, rd, ok);
         } else {
           hoist_fwd_node<FAST>(sG[m * GS_LB], ti, L.rt, lambda, ok);
@@ -839,7 +839,7 @@ GS_DEV bool ck_pass1(const LineH &L, char *wsm, uint64_t *full, uint32_t &phase,
         GsRcp rd;
         rd.b = ti[1];
         rd.y = ti[2];
-        double vect = gs_div<FAST>(-sG[m * GS_LB], L.rt, ok);
+        double vect = gs_div<FAST, true>(-sG[m * GS_LB], L.rt, ok);
         if (i == 0) {
           lambda = gs_div<FAST>(vect - ti[0] * firstT, rd, ok);       // :65, forwardFirst :245-248
         } else {
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(128, 3) k_step1d_hoist_ck(Step1dParams p, cons
               GsRcp rd;
               rd.b = ti[1];
               rd.y = ti[2];
-              double vect = gs_div<true>(-g, L.rt, ok2);
+              double vect = gs_div<true, true>(-g, L.rt, ok2);
               if (i == 0) lam = gs_div<true>(vect - ti[0] * firstT, rd, ok2);
               else {
                 if (i == n - 1) vect = vect - c_last * lastT;
@@ -1101,7 +1101,7 @@ GS_DEV void faces_node(const Line1d &L, int i, double g, double condL, double co
   const int n = L.n;
   const double a = condL * L.pd[2 * i];
   const double c = condR * L.pd[2 * i + 1];
-  double vect = gs_div<FAST>(-g, L.rt, ok);
+  double vect = gs_div<FAST, true>(-g, L.rt, ok);
   const double diag = -(a + c) - L.inv_time;
   if (i == 0) {
     vect = vect - a * firstT;                                              // :65

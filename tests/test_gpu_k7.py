@@ -147,3 +147,24 @@ def test_k7_c4_shape_4096_vs_oracle(O, gs, k7):
     o.iteration(900.0); o.iteration(900.0)
     _snap_equal(g, o, "C4 shape 4096^2")
     assert g.status == 0
+
+
+@pytest.mark.parametrize("coefs", ["hermite", "const"])
+@pytest.mark.parametrize("value", [0.0, 7.0, -0.0])
+def test_k7_uniform_and_zero_fields_stay_exact(O, gs, coefs, value):
+    """A field that starts uniform -- and one of exactly 0.0 -- is ordinary input (AT/GridTest.scala fills 7.0): equal
+    neighbours make average = apply, temperatures a few ulps apart make the antiderivative difference cancel to 0.0 (a
+    face value of 0.0), zeros make -t / tau = -0.0.  All of it must stay on the straight-line tiers' bits = the oracle's
+    (signs of zero included), for several steps while the boundary layer grows into the field."""
+    p = cases.bc_problem("TTTT", xdir=1, ydir=0, cols=96, rows=70, coefs=coefs)
+    p.grid0 = np.full(p.grid0.shape, value)
+    p.predict0 = p.grid0.copy()
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    g.set_solver(gs.SOLVER_THOMAS)
+    for step in range(4):
+        g.iteration(900.0)
+        o.iteration(900.0)
+        got, want = cases.snapshot(g), cases.snapshot(o)
+        for k in ("grid", "predict", "result"):
+            assert_bit_equal(got[k], want[k], f"{coefs} from {value!r}, step {step}: {k}")
+    assert g.status == 0
