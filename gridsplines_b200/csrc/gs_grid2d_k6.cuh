@@ -124,6 +124,27 @@ GS_DEV bool k6_face_fast(const K6Tab &z, double p0, double p1, double &v) {
 GS_DEV bool k6_face_equal(const K6Tab &z, double p0, double p1, double &v) {
   return __double_as_longlong(p0) == __double_as_longlong(p1) && gs_tab_apply_fast(z, p0, v);
 }
+// Both temperatures at or beyond the same clamp (a field hotter than the table's upperX -- which the reference's
+// greatestK puts one knot below the last one, SURVEY App. B Q1 -- or colder than lowerX): AlwaysDefinedSpline.area is
+// (lowerArea + middleArea) + upperArea with middleArea = 0.0 and one of the others (hi - lo) * Y
+// (A/AlwaysDefinedSpline.scala:20-41), the average that over (hi - lo); equal temperatures give apply = Y.  `h` is the
+// table's header (lowerX, upperX, lowerY, upperY at 2 .. 5).  Same doubles as gs_ads_average, without the general walk.
+GS_DEV bool k6_face_clamped(const double *h, double p0, double p1, double &v) {
+  const bool lt = p0 < p1;
+  const double lo = lt ? p0 : p1, hi = lt ? p1 : p0;
+  const bool below = hi <= h[2], above = lo >= h[3];
+  if (!(below || above) || (below && above)) return false;   // (NaN, or a degenerate table: the general walk)
+  const double Y = below ? h[4] : h[5];
+  if (p0 == p1) {
+    if (__double_as_longlong(p0) != __double_as_longlong(p1)) return false;   // +0.0 / -0.0
+    v = Y;
+    return true;
+  }
+  const double d = hi - lo;
+  const double area = below ? ((d * Y + 0.0) + 0.0) : ((0.0 + 0.0) + d * Y);
+  v = area / d;
+  return true;
+}
 // second tier: what the straight-line path leaves out but is still one or two table pieces strictly inside the clamps
 // and the knots -- equal temperatures (average = apply), an interval that straddles ONE knot, and one-piece intervals
 // of tables the first tier does not take (Line / Const pieces, unevenly spaced knots).  Follows gs_ads_average /
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(256, 3) k6_faces(K6FacesParams q) {
             z = k6_tab(k6sm + off);
           }
           double v;
-          if (!k6_face_fast(z, c0[u], c1[u], v) && !k6_face_equal(z, c0[u], c1[u], v)) {
+          if (!k6_face_fast(z, c0[u], c1[u], v) && !k6_face_equal(z, c0[u], c1[u], v) && !k6_face_clamped(k6sm + off, c0[u], c1[u], v)) {
             if (!k6_face_mid(k6sm + off, c0[u], c1[u], &v)) v = k6_face_general(p.pool, off, c0[u], c1[u], p.status);
           }
           frow[ccol[u]] = v;
@@ -451,7 +472,7 @@ __global__ void __launch_bounds__(512) k6_sweep(K6Params q) {
       ztab = k6_tab(poolsm + zoff);
     }
     double v;
-    if (!k6_face_fast(ztab, p0, p1, v) && !k6_face_equal(ztab, p0, p1, v)) {
+    if (!k6_face_fast(ztab, p0, p1, v) && !k6_face_equal(ztab, p0, p1, v) && !k6_face_clamped(poolsm + zoff, p0, p1, v)) {
       if (!k6_face_mid(poolsm + zoff, p0, p1, &v)) v = k6_face_general(q.pool, zoff, p0, p1, q.status);
     }
     return v;

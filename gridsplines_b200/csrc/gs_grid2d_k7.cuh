@@ -515,7 +515,7 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
       off = map_off(q.maps, GS_SEL_APPLY, XDIR ? i : line, XDIR ? line : i, q.cols);
       z = k6_tab(pool_sm + (off - q.stage_off));
     }
-    if (!k6_face_fast(z, p0, p1, v) && !k6_face_equal(z, p0, p1, v)) {
+    if (!k6_face_fast(z, p0, p1, v) && !k6_face_equal(z, p0, p1, v) && !k6_face_clamped(pool_sm + (off - q.stage_off), p0, p1, v)) {
       if (!k6_face_mid(pool_sm + (off - q.stage_off), p0, p1, &v)) v = k6_face_general(q.pool, off, p0, p1, q.status);
     }
     return v;
@@ -568,14 +568,15 @@ GS_DEV void k7f_faces(const K7Params &q, const K7Maps &tm, K7FBars *bars, unsign
           if (!good && (EVEN || h + j < j1)) bad |= 1u << j;
         }
         if (bad) {
-          // a uniform region (equal neighbours: average = apply) fails the straight-line tier for whole batches: take
-          // its faces through the equal-temperature tier together, again as independent instruction streams, before
+          // a uniform region (equal neighbours: average = apply) or one beyond the table's clamps fails the straight-line
+          // tier for whole batches: take its faces through the equal-temperature / clamped tiers together, again as independent instruction streams, before
           // anything goes to the one-by-one path (512^2 from a uniform start: 520 -> 300 us per step)
           if (!LIT) {
 #pragma unroll
             for (int j = 0; j < B; ++j) {
               double ve;
-              const bool eq = k6_face_equal(z, pred0(h + j), pred0(h + j + 1), ve);
+              const bool eq = k6_face_equal(z, pred0(h + j), pred0(h + j + 1), ve) ||
+                              k6_face_clamped(pool_sm + (off - q.stage_off), pred0(h + j), pred0(h + j + 1), ve);
               if (eq && ((bad >> j) & 1u)) {
                 v[j] = ve;
                 bad &= ~(1u << j);

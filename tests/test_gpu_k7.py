@@ -168,3 +168,27 @@ def test_k7_uniform_and_zero_fields_stay_exact(O, gs, coefs, value):
         for k in ("grid", "predict", "result"):
             assert_bit_equal(got[k], want[k], f"{coefs} from {value!r}, step {step}: {k}")
     assert g.status == 0
+
+
+@pytest.mark.parametrize("value,upp,low", [(76.0, 79.0, 72.0), (-24.0, -22.0, -30.0), (69.0, 75.0, 71.0)])
+def test_k7_fields_beyond_the_table_clamps_stay_exact(O, gs, value, upp, low):
+    """Temperatures at or beyond the same clamp of the table (hotter than upperX = the second-to-last knot under the
+    reference's greatestK rule, or colder than lowerX) take the clamped face tier: ((hi - lo) * Y) / (hi - lo) as
+    AlwaysDefinedSpline.area / average compute it; a field that straddles the clamp (third case) mixes every tier."""
+    p = cases.bc_problem("TTTT", xdir=1, ydir=0, cols=96, rows=70, coefs="hermite")
+    r = np.random.default_rng(5)
+    p.grid0 = value + r.uniform(-0.5, 0.5, p.grid0.shape)
+    p.grid0[:20, :30] = value          # a uniform patch beyond the clamp: apply = Y
+    p.predict0 = p.grid0.copy()
+    g, o = p.build_gs(gs), p.build_oracle(O)
+    for side, v in ((gs.UPP, upp), (gs.LOW, low), (gs.LEFT, upp), (gs.RIGHT, low)):
+        getattr(g.bounds, {gs.UPP: "upp", gs.LOW: "low", gs.LEFT: "left", gs.RIGHT: "right"}[side]).update(v)
+        o.set_bound(side, O.TEMP, O.DENSE, np.full(p.cols if side in (gs.UPP, gs.LOW) else p.rows, v))
+    g.set_solver(gs.SOLVER_THOMAS)
+    for step in range(3):
+        g.iteration(900.0)
+        o.iteration(900.0)
+        got, want = cases.snapshot(g), cases.snapshot(o)
+        for k in ("grid", "predict", "result"):
+            assert_bit_equal(got[k], want[k], f"around {value}, step {step}: {k}")
+    assert g.status == 0
