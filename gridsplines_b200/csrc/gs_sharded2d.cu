@@ -90,14 +90,14 @@ extern "C" int gs_sharded2d_create(int ndev, const int *devices, int cols, int r
       int can = 0;
       cudaDeviceCanAccessPeer(&can, s->dev[p], s->dev[q]);
       if (!can) {
-        delete s;
         gs_set_error("device %d cannot access device %d as a peer", s->dev[p], s->dev[q]);
+        delete s;
         return GS_ERR_CUDA;
       }
       cudaError_t e = cudaDeviceEnablePeerAccess(s->dev[q], 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-        delete s;
         gs_set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", s->dev[p], s->dev[q], cudaGetErrorString(e));
+        delete s;
         return GS_ERR_CUDA;
       }
       cudaGetLastError();
