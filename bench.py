@@ -281,6 +281,52 @@ def bench_c1(gs, ctx, torch, stream):
             "note": "a single 200-node line is launch-latency bound by construction"}
 
 
+def bench_c2t(gs, ctx, torch, stream, peak, steps=5, lines=1 << 20, n=256):
+    """C2's shape with a temperature-dependent conductivity table (M1Hermite3, the README's eleven points) instead of
+    constant properties: the north star's first bullet.  AUTO -> K2T; parity: every line against K2, bits."""
+    r = np.random.default_rng(SEED + 2)
+    rho = [0.598, 0.826, 1.121, 1.496, 1.966, 2.547, 3.258, 4.122, 5.156, 6.397, 7.862]
+    pts = [(-20.0 + 10.0 * i, 1e-6 * (1.0 + 0.1 * rho[i])) for i in range(11)]
+    rangeX = 0.01 * np.arange(1, n + 1)
+    g = gs.BatchedOneDGrid(0.0, rangeX, 0.01 * (n + 1), gs.Spline.m1Hermite3(pts), 1.0, nlines=lines, ctx=ctx)
+    h = torch.empty((lines, n), dtype=torch.float64)
+    h.uniform_(0.0, 30.0, generator=torch.Generator().manual_seed(SEED + 2))
+    lt, rt = r.uniform(10.0, 30.0, lines), r.uniform(0.0, 10.0, lines)
+    g.upload_ptr(gs.GRID, h.data_ptr())
+    g.upload_ptr(gs.PREDICT, h.data_ptr())
+    g.set_bc(lt, rt)
+    # parity inside the run: every line against K2 (the scratch-array kernel; both are bit-exact against the oracle in
+    # tests/test_gpu_1d.py) after two steps
+    g.step(TIME_STEP, nsteps=2)
+    got = g.download(gs.GRID)
+    ctx.set_option("k2t", 0)
+    try:
+        k2 = gs.BatchedOneDGrid(0.0, rangeX, 0.01 * (n + 1), gs.Spline.m1Hermite3(pts), 1.0, nlines=lines, ctx=ctx)
+        k2.upload_ptr(gs.GRID, h.data_ptr())
+        k2.upload_ptr(gs.PREDICT, h.data_ptr())
+        k2.set_bc(lt, rt)
+        k2.step(TIME_STEP, nsteps=2)
+        ms_k2 = _time_steps(torch, stream, lambda: k2.step(TIME_STEP), steps, 1, reps=1)
+        k2.upload_ptr(gs.GRID, h.data_ptr())
+        k2.upload_ptr(gs.PREDICT, h.data_ptr())
+        k2.step(TIME_STEP, nsteps=2)
+        exact = bool(np.array_equal(got.view(np.uint64), k2.download(gs.GRID).view(np.uint64)))
+        k2.close()
+    finally:
+        ctx.set_option("k2t", 1)
+    del got
+    ms = _time_steps(torch, stream, lambda: g.step(TIME_STEP), steps, 2)
+    out = {"workload": f"C2T: {lines} lines x {n} nodes, ortho, conductivity from an M1Hermite3 table (11 points), per-line Dirichlet ends",
+           "ms_per_step": ms, "updates_per_s": float(lines) * n / (ms * 1e-3),
+           "roofline": _roof(float(lines) * n, BYTES_PER_UPDATE_1D, ms, peak, "C2T"),
+           "solver": "AUTO -> K2T (per-thread Thomas, exact: faces warp + chain warp per 32-line block, L2-resident (delta, lambda))",
+           "parity": {"bit_identical_to_K2": exact, "lines": lines, "after_steps": 2,
+                      "note": "K2 = the scratch-array kernel; both bit-exact vs the oracle in tests/test_gpu_1d.py"},
+           "k2_ms_per_step": ms_k2, "status": int(g.status)}
+    g.close()
+    return out
+
+
 def bench_c3(gs, ctx, torch, stream, peak, steps=20, n=4096):
     f = _field2d(torch, n, "C3")
     fast = _grid2d(gs, ctx, torch, "C3", n, gs.SOLVER_AUTO, f)
@@ -630,6 +676,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         if world == 1:
             for name, fn in (("C1", lambda: bench_c1(gs, ctx, torch, stream)),
+                             ("C2T", lambda: bench_c2t(gs, ctx, torch, stream, peak)),
                              ("C3", lambda: bench_c3(gs, ctx, torch, stream, peak)),
                              ("C4", lambda: bench_c4(gs, ctx, torch, stream, peak)),
                              ("C5", lambda: bench_c5(gs, ctx, torch, stream, peak))):
@@ -706,7 +753,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--opt", action="append", default=[], help="gs_ctx_set_option name=value")
-    ap.add_argument("--configs", default="all", help="extra configs to measure: all | none | comma list of C1,C3,C4,C5")
+    ap.add_argument("--configs", default="all", help="extra configs to measure: all | none | comma list of C1,C2T,C3,C4,C5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

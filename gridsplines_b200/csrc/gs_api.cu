@@ -130,6 +130,10 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "k5t_hints")) ctx->opt_k5t_hints = (int)value;
   else if (!strcmp(name, "k6")) ctx->opt_k6 = value;
   else if (!strcmp(name, "faces1d")) ctx->opt_faces1d = value;
+  else if (!strcmp(name, "k2t")) ctx->opt_k2t = value;
+  else if (!strcmp(name, "k2t_cps")) ctx->opt_k2t_cps = value;
+  else if (!strcmp(name, "k2t_ctas")) ctx->opt_k2t_ctas = value;
+  else if (!strcmp(name, "k2t_hints")) ctx->opt_k2t_hints = value;
   else if (!strcmp(name, "k6_chunk")) ctx->opt_k6_chunk = value;   // accepted for compatibility; chunks are 8 nodes
   else if (!strcmp(name, "k6_cluster")) ctx->opt_k6_cluster = value != 0;
   else if (!strcmp(name, "k6_fuse")) ctx->opt_k6_fuse = value != 0;

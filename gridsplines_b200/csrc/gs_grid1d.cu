@@ -1566,9 +1566,35 @@ extern "C" int gs_grid1d_set_bc(gs_grid1d *g, const double *leftT, const double 
   return GS_OK;
 }
 
+#include "gs_grid1d_k2t.cuh"
+
+// K2T applies to one table of at most K2T_POOL bytes on lines of at least 32 nodes.  Option k2t = 1 (default) takes it
+// for tables its straight-line lookup serves -- cubic pieces on equally spaced knots (M1Hermite3 / Hermite3 / Lagrange on
+// a regular temperature axis); Const / Line pieces and uneven knots would send every lookup of the faces warp to the
+// out-of-line general evaluation (measured with a one-piece constant table: 4.26 ms against K2's 3.55), so they stay on
+// K2 -- k2t = 2 forces K2T for any single table (tests), 0 switches it off.
+static int k2t_table_len(const gs_grid1d *g) {
+  const gs_ctx *ctx = g->ctx;
+  if (!ctx->opt_pipeline || !ctx->opt_k2t || g->spline_mode != GS_SPLINE_SINGLE || g->n < 32) return 0;
+  if (g->all_const && ctx->opt_const_hoist) return 0;
+  const size_t off = (size_t)g->single_off;
+  if (off + GS_HDR > ctx->pool.size()) return 0;
+  const int np = (int)ctx->pool[off + 1];
+  const size_t len = GS_HDR + (size_t)np + 1 + (size_t)np * GS_PIECE;
+  if (np < 1 || len * sizeof(double) > K2T_POOL || off + len > ctx->pool.size()) return 0;
+  const bool fast_table = (int)ctx->pool[off] == GS_CUBIC && ctx->pool[off + 6] != 0.0;
+  if (!fast_table && ctx->opt_k2t < 2) return 0;
+  return (int)len;
+}
+
 // steps the line blocks [blk0, blk1) (all of them for the public entry point)
 static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, long long blk1) {
   gs_ctx *ctx = g->ctx;
+  // K2T works one step per launch (the next step's faces need this step's predict')
+  if (nsteps > 1 && k2t_table_len(g) > 0) {
+    for (int s = 0; s < nsteps; ++s) GS_TRY(step_blocks(g, time, 1, blk0, blk1));
+    return GS_OK;
+  }
   // K2f works one step per launch pair (faces, elimination)
   if (nsteps > 1 && ctx->opt_pipeline && ctx->opt_faces1d && g->spline_mode == GS_SPLINE_SINGLE &&
       !(g->all_const && ctx->opt_const_hoist) && blk0 == 0 && blk1 == g->pitch / GS_LB) {
@@ -1677,6 +1703,27 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
       default: GS_LAUNCH_HOIST(8, 4); break;
     }
 #undef GS_LAUNCH_HOIST
+  } else if (nsteps == 1 && k2t_table_len(g) > 0) {
+    // K2T: faces warp + chain warp per 32-line block, persistent CTAs with an L2-resident (delta, lambda) block each
+    const int cps = (int)std::max<int64_t>(2, std::min<int64_t>(8, ctx->opt_k2t_cps));
+    void (*kern)(Step1dParams, int, int) = cps == 2 ? k2t_step<2> : cps == 3 ? k2t_step<3> : cps == 4 ? k2t_step<4>
+                                           : cps == 5 ? k2t_step<5> : cps == 6 ? k2t_step<6> : cps == 7 ? k2t_step<7>
+                                           : k2t_step<8>;
+    const int k2t_smem = K2T_SMEM(K2T_NS(cps));
+    const void *key = reinterpret_cast<const void *>(kern);
+    if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
+      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2t_smem));
+      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      ctx->configured.push_back(key);
+    }
+    int per_sm = 0;
+    GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, k2t_smem));
+    GS_REQUIRE(per_sm >= 1, "line kernel does not fit on an SM");
+    // one scratch block per CTA: never more CTAs than the scratch array was sized for
+    long long ctas = std::min<long long>(nwarps, (long long)std::min(per_sm, cps) * ctx->sm_count);
+    if (ctx->opt_k2t_ctas > 0) ctas = std::min<long long>(ctas, ctx->opt_k2t_ctas);   // tests: several blocks per CTA on small batches
+    p.nwarps = ctas;
+    kern<<<(unsigned)ctas, 64, k2t_smem, ctx->stream>>>(p, k2t_table_len(g), (int)ctx->opt_k2t_hints);
   } else if (ctx->opt_pipeline && ctx->opt_faces1d && g->spline_mode == GS_SPLINE_SINGLE && nsteps == 1 &&
              blk0 == 0 && blk1 == g->pitch / GS_LB) {
     // K2f: faces kernel + elimination with checkpoint/recompute (one step per launch pair: the faces of step k+1

@@ -49,7 +49,7 @@ def test_batch_vs_golden(gs, name, args):
 def options(ctx):
     """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
     defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0,
-                "hoist_ck": 1, "ck_block": 16, "faces1d": 0}
+                "hoist_ck": 1, "ck_block": 16, "faces1d": 0, "k2t": 1, "k2t_cps": 6, "k2t_hints": 15, "k2t_ctas": 0}
 
     def set_(**kw):
         for k, v in kw.items():
@@ -67,15 +67,19 @@ PATHS = {
     "hoist_scratch": {"hoist_ck": 0},
     "hoist_ck32": {"ck_block": 32},
     "hoist_ck_native": {"native_div": 1},
-    "general": {"const_hoist": 0},                          # K2: TMA ring + (delta, lambda) scratch
-    "k2f": {"const_hoist": 0, "faces1d": 1},                # K2f: faces kernel + elimination with checkpoint/recompute
-    "k2f_native_div": {"const_hoist": 0, "faces1d": 1, "native_div": 1},
+    "general": {"const_hoist": 0, "k2t": 0},                # K2: TMA ring + (delta, lambda) scratch
+    "k2t": {"const_hoist": 0, "k2t": 2},                            # K2T: faces warp + chain warp, L2-resident scratch (2: any table; cubic tables on equal knots take it by default)
+    "k2t_native_div": {"const_hoist": 0, "native_div": 1, "k2t": 2},
+    "k2t_cps4_nohints": {"const_hoist": 0, "k2t": 2, "k2t_cps": 4, "k2t_hints": 0},   # three-stage rings
+    "k2t_few_ctas": {"const_hoist": 0, "k2t": 2, "k2t_ctas": 3},      # persistent CTAs: every CTA walks several line blocks
+    "k2f": {"const_hoist": 0, "faces1d": 1, "k2t": 0},      # K2f: faces kernel + elimination with checkpoint/recompute
+    "k2f_native_div": {"const_hoist": 0, "faces1d": 1, "native_div": 1, "k2t": 0},
     "direct": {"const_hoist": 0, "pipeline": 0},
     "native_div": {"native_div": 1, "hoist_ck": 0},
-    "general_native_div": {"const_hoist": 0, "native_div": 1},
+    "general_native_div": {"const_hoist": 0, "native_div": 1, "k2t": 0},
     "ring1": {"pipe_cfg": 1, "hoist_ck": 0},
-    "general_ring2": {"const_hoist": 0, "pipe_cfg": 2},
-    "few_warps": {"threads_per_sm_1d": 32},
+    "general_ring2": {"const_hoist": 0, "pipe_cfg": 2, "k2t": 0},
+    "few_warps": {"threads_per_sm_1d": 32, "k2t": 0},
 }
 
 
@@ -112,6 +116,56 @@ def test_zero_and_tiny_values_take_the_ieee_division_path(O, gs):
         O.batch1d_step(0, s["leftX"], s["rangeX"], s["rightX"], spl(O), 1.0, og, op, lt, rt, 900.0, nsteps=3)
         assert_bit_equal(g.download(gs.GRID), og, "zeros grid")
         assert_bit_equal(g.download(gs.PREDICT), op, "zeros predict")
+
+
+@pytest.mark.parametrize("n", [32, 48, 64, 250])
+def test_k2t_special_values(O, gs, n):
+    """K2T (the default for a cubic table on equal knots) on data that leaves its straight-line tiers: zeros and
+    denormal-range values (the block is redone with plain division), temperatures beyond the table's clamps and exactly on
+    its knots (general evaluation out of line), line ends far outside the table; full and partial last chunks; padding lanes
+    (70 lines = 2 blocks + 6 lanes).  Bit-exact against the oracle, and the same bits as K2."""
+    nlines = 70
+    s = cases.batch_setup(nlines, n)
+    r = np.random.default_rng(11)
+    pts = [(-20.0 + 10.0 * i, 1e-6 * (1.0 + 0.1 * cases.README_RHO[i])) for i in range(11)]
+    grid0 = r.uniform(-60.0, 120.0, (nlines, n))          # well beyond the table's [-20, 80]
+    grid0[::3, ::5] = 0.0
+    grid0[1::7, ::4] = 1e-300
+    grid0[2::9] = np.round(grid0[2::9] / 10.0) * 10.0      # exactly on knots
+    grid0[5] = 7.0                                         # a uniform line
+    lt, rt = r.uniform(-100.0, 150.0, nlines), r.uniform(-100.0, 150.0, nlines)
+    lt[::4] = 0.0
+    outs = {}
+    for k2t in (1, 0):
+        gs.default_context().set_option("k2t", k2t)
+        try:
+            g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], gs.Spline.m1Hermite3(pts), 1.0, nlines=nlines)
+            g.upload(gs.GRID, grid0)
+            g.upload(gs.PREDICT, grid0)
+            g.step(900.0, lt, rt, nsteps=4)
+            outs[k2t] = (g.download(gs.GRID), g.download(gs.PREDICT), g.status)
+        finally:
+            gs.default_context().set_option("k2t", 1)
+    og, op = grid0.copy(), grid0.copy()
+    O.batch1d_step(0, s["leftX"], s["rangeX"], s["rightX"], O.Spline.m1Hermite3(pts), 1.0, og, op, lt, rt, 900.0, nsteps=4)
+    for k2t in (1, 0):
+        assert_bit_equal(outs[k2t][0], og, f"k2t={k2t} n={n} grid")
+        assert_bit_equal(outs[k2t][1], op, f"k2t={k2t} n={n} predict")
+    assert outs[1][2] == outs[0][2], "K2T and K2 raise the same status flags"
+
+
+def test_k2t_nan_is_flagged(gs):
+    """A NaN in predict makes the reference's tree lookup throw; K2T raises GS_FLAG_SPLINE_UNDEFINED like K2."""
+    nlines, n = 40, 64
+    s = cases.batch_setup(nlines, n)
+    pts = [(-20.0 + 10.0 * i, 1e-6 * (1.0 + 0.1 * cases.README_RHO[i])) for i in range(11)]
+    g = gs.BatchedOneDGrid(s["leftX"], s["rangeX"], s["rightX"], gs.Spline.m1Hermite3(pts), 1.0, nlines=nlines)
+    f = np.full((nlines, n), 5.0)
+    g.upload(gs.GRID, f)
+    f[17, 33] = np.nan
+    g.upload(gs.PREDICT, f)
+    g.step(900.0, np.zeros(nlines), np.zeros(nlines), nsteps=1)
+    assert g.status & gs.FLAG_SPLINE_UNDEFINED
 
 
 @pytest.mark.parametrize("direction", [0, 1])
