@@ -1709,10 +1709,11 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
     void (*kern)(Step1dParams, int, int) = cps == 2 ? k2t_step<2> : cps == 3 ? k2t_step<3> : cps == 4 ? k2t_step<4>
                                            : cps == 5 ? k2t_step<5> : cps == 6 ? k2t_step<6> : cps == 7 ? k2t_step<7>
                                            : k2t_step<8>;
-    const int k2t_smem = K2T_SMEM(K2T_NS(cps));
+    // shared memory: barriers | NS stages | the table itself (eight CTAs per SM fit only while the table is small)
+    const int k2t_smem = K2T_SMEM(K2T_NS(cps)) - K2T_POOL + ((k2t_table_len(g) * (int)sizeof(double) + 127) / 128) * 128;
     const void *key = reinterpret_cast<const void *>(kern);
     if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
-      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2t_smem));
+      GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2T_SMEM(K2T_NS(cps))));
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       ctx->configured.push_back(key);
     }

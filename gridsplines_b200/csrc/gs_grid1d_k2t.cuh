@@ -6,22 +6,24 @@
 //     issues the chain warp's loads (grid tile, the nodes' preDef pairs); the CHAIN warp runs ONE THREAD PER LINE in the
 //     reference's operation order (faces_node: the very operations of K2) and never waits for a spline or a load of its own.
 //   * PERSISTENT CTAs walk the line blocks and REUSE one (delta, lambda) scratch block each, so the scratch footprint is
-//     CTAs x n x 512 B instead of K2's 24 warps per SM x n x 512 B.  With four CTAs per SM (C2 shape: 78 MB) the backward
-//     walk reads it back from the 126 MB L2: ncu counts 24.9 B/node of DRAM reads (grid, predict, grid again: every scratch
-//     read hits) and 28.3 written (grid', predict' and 12 B/node of scratch that L2 writes back anyway) = 53 B/node against
-//     K2's 70 (tools/l2_scratch.cu is the microbenchmark behind the idea).  With SIX per SM (the default; 116 MB, two-stage
-//     rings) the residency is mostly lost again (63 B/node, profiles/r2_k2t_hermite_summary.txt) but the extra chains hide
-//     more latency than the saved bytes are worth: 3.13 ms against 3.31.  The step's own arrays travel with evict_first.
+//     CTAs x n x 512 B instead of K2's 24 warps per SM x n x 512 B and the backward walk reads it back from the 126 MB L2
+//     (tools/l2_scratch.cu is the microbenchmark behind the idea); every chunk of it is DISCARDED from L2
+//     (discard.global.L2, SASS CCTL.E.RML2) as soon as the backward walk has it in shared memory, so the dead dirty lines
+//     are dropped instead of written back.  ncu, C2 shape with an M1Hermite3 table, DRAM bytes per node read + written:
+//     four CTAs per SM 24.9 + 28.3 without the discards, 22.4 + 18.9 = 41 with them; six 31.7 + 31.3 -> 24.7 + 22.2 = 47
+//     (K2: 70).  The step's own arrays travel with evict_first.
 //   * the backward walk (backwardPassion :345-365, predictor arraygrid.aVal :85-87, grid <- result) is the chain warp's:
 //     stages of 16 nodes of (delta, lambda) + the old grid tile through a bulk-copy ring that reuses the forward stages.
 //   * the hot loops hold the straight-line tiers only (fallbacks out of line, native-division walk rolled): with so few
 //     warps per SM an instruction-cache miss is not hidden -- the first build (20 k SASS instructions) spent 25 % of its
 //     stall samples on no_instructions; this one has 4.4 k.
-// MEASURED (B200, 1 M lines x 256 nodes, M1Hermite3 table): 3.12 - 3.19 ms per step against K2's 3.43 (CTAs per SM 3 / 4 /
-// 5 / 6 / 7 / 8: 4.19 / 3.31 / 3.42 / 3.13 / 3.16 / 3.12), 151 warp instructions per node-row against K2's 308, 5.4 TB/s of
-// DRAM traffic; forward walk alone 1.7 - 1.8 ms (5 TB/s of its 32 B/node), backward walk 1.3 - 1.4 ms: both near the DRAM
-// rate of their own traffic, and they do not overlap inside a CTA.
-// Shared memory per CTA: barriers 512 B | NS stages x 12.5 KB (NS = 2 from six CTAs per SM, else 3) | the table (<= 4 KB).
+// MEASURED (B200, 1 M lines x 256 nodes, M1Hermite3 table), ms per step: K2 3.43; K2T without discards, CTAs per SM 3 / 4 /
+// 5 / 6 / 7 / 8: 4.19 / 3.31 / 3.42 / 3.13 / 3.16 / 3.12; with discards 4 / 6 / 7 / 8: 3.18 / 2.95 / 3.17 / 2.86 (eight: 128
+// registers, 44 bytes of spills; seven puts the warps unevenly on the four schedulers).  151 warp instructions per node-row
+// against K2's 308.  Forward walk alone 1.7 - 1.8 ms, backward walk 1.3 - 1.4 ms (before the discards); the two do not
+// overlap inside a CTA, so more CTAs per SM is what helps.
+// Shared memory per CTA: barriers 512 B | NS stages x 12.5 KB (NS = 2 from six CTAs per SM, else 3) | the table (<= 4 KB; eight
+// CTAs per SM fit while it is below ~1.5 KB).
 // Applies to a SINGLE table of at most 4 KB on lines of at least 32 nodes; everything else stays on K2.
 #pragma once
 
@@ -77,6 +79,10 @@ __device__ __noinline__ double k2t_apply_general(const double *pool_sm, double x
   return v;
 }
 __device__ __noinline__ double k2t_div3(double d) { return d / 3.0; }
+// the 128-byte line at p is dead: L2 may drop it instead of writing it back (p 128-byte aligned)
+__device__ __forceinline__ void k2t_discard(const void *p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void k2t_st_first(double *p, double v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(64, CPS) k2t_step(Step1dParams p, int stage_le
   __syncthreads();
   const size_t block_elems = (size_t)n * GS_LB;
   double2 *sc = p.scratch + (size_t)blockIdx.x * block_elems;
-  // the step's own arrays stream through L2: evict_first (hints: 1 grid forward, 2 predict, 4 grid backward loads; 8 the stores of grid' / predict') leaves the
+  // the step's own arrays stream through L2: evict_first (hints: 1 grid forward, 2 predict, 4 grid backward loads; 8 the stores of grid' / predict'; 16: scratch lines discarded once read back) leaves the
   // L2 to the reused scratch blocks
   const uint64_t pol = gs_policy_evict_first();
   unsigned flags = 0;
@@ -324,6 +330,12 @@ __global__ void __launch_bounds__(64, CPS) k2t_step(Step1dParams p, int stage_le
       const unsigned char *st = region + r.head * K2T_BSTAGE;
       const double2 *dl = reinterpret_cast<const double2 *>(st) + lane;
       const double *gold = reinterpret_cast<const double *>(st + K2T_CH * 512) + lane;
+      if (hints & 16) {
+        // this chunk of (delta, lambda) is in shared memory now and dead in global memory until the next block's forward
+        // walk overwrites it: without this L2 writes the dirty lines back when it evicts them (12 B/node of DRAM writes)
+        const unsigned char *dead = reinterpret_cast<const unsigned char *>(sc + (size_t)i0 * 32);
+        for (int l = lane; l < len * 4; l += 32) k2t_discard(dead + (size_t)l * 128);
+      }
       double *G = Gblk + (size_t)i0 * 32 + lane, *P = Pblk + (size_t)i0 * 32 + lane;
       double xs[K2T_CH];
       if (len == K2T_CH) {

@@ -78,9 +78,9 @@ struct gs_ctx {
   int64_t opt_k6 = 1;
   int64_t opt_faces1d = 0;   // K2f measured slower than K2 on B200 (5.7 vs 4.3 ms on the C2 shape with a Hermite table)
   int64_t opt_k2t = 1;          // K2T: 1-D lines with one table on faces warp + chain warp CTAs with L2-resident scratch (0: K2; 1: cubic tables on equal knots; 2: any single table)
-  int64_t opt_k2t_cps = 6;      // K2T: CTAs per SM (2..8; 6+ with two-stage rings); the scratch footprint is CTAs x n x 512 B
+  int64_t opt_k2t_cps = 8;      // K2T: CTAs per SM (2..8; 6+ with two-stage rings); the scratch footprint is CTAs x n x 512 B
   int64_t opt_k2t_ctas = 0;     // K2T: cap on the number of CTAs (0 = none)
-  int64_t opt_k2t_hints = 15;   // K2T: evict_first on 1 grid (forward), 2 predict, 4 grid (backward) loads, 8 grid' / predict' stores
+  int64_t opt_k2t_hints = 31;   // K2T: evict_first on 1 grid (forward), 2 predict, 4 grid (backward) loads, 8 grid' / predict' stores; 16 discard.L2 of scratch lines once read back
   int64_t opt_k6_chunk = 8;
   int opt_k6_fuse = 0;          // K6: the sweep evaluates the faces along its lines itself (no separate faces pass); measured slower, off
   int opt_k6_cluster = 1;       // K6: give a strip to a cluster of 2 / 4 CTAs when strips alone would not fill the chip

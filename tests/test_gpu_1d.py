@@ -49,7 +49,7 @@ def test_batch_vs_golden(gs, name, args):
 def options(ctx):
     """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
     defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0,
-                "hoist_ck": 1, "ck_block": 16, "faces1d": 0, "k2t": 1, "k2t_cps": 6, "k2t_hints": 15, "k2t_ctas": 0}
+                "hoist_ck": 1, "ck_block": 16, "faces1d": 0, "k2t": 1, "k2t_cps": 8, "k2t_hints": 31, "k2t_ctas": 0}
 
     def set_(**kw):
         for k, v in kw.items():
@@ -70,7 +70,7 @@ PATHS = {
     "general": {"const_hoist": 0, "k2t": 0},                # K2: TMA ring + (delta, lambda) scratch
     "k2t": {"const_hoist": 0, "k2t": 2},                            # K2T: faces warp + chain warp, L2-resident scratch (2: any table; cubic tables on equal knots take it by default)
     "k2t_native_div": {"const_hoist": 0, "native_div": 1, "k2t": 2},
-    "k2t_cps4_nohints": {"const_hoist": 0, "k2t": 2, "k2t_cps": 4, "k2t_hints": 0},   # three-stage rings
+    "k2t_cps4_nohints": {"const_hoist": 0, "k2t": 2, "k2t_cps": 4, "k2t_hints": 0},   # three-stage rings, no L2 hints / discards
     "k2t_few_ctas": {"const_hoist": 0, "k2t": 2, "k2t_ctas": 3},      # persistent CTAs: every CTA walks several line blocks
     "k2f": {"const_hoist": 0, "faces1d": 1, "k2t": 0},      # K2f: faces kernel + elimination with checkpoint/recompute
     "k2f_native_div": {"const_hoist": 0, "faces1d": 1, "native_div": 1, "k2t": 0},
