@@ -11,9 +11,10 @@ every line = nlines * n grid-point updates.  Inputs (4.3 GB of grid + predict pe
 `e2e`     : same metric through the C ABI with HOST buffers (gs_grid1d_step_host, the drop-in OneDGrid.step): per step
             H2D of the public `grid` array + the per-line end temperatures from pinned memory, the step, D2H of `grid`
             (`predict` is private to OneDGrid, A/OneDGrid.scala:21, and stays on the device).
-`configs` : (N = 1) the other BASELINE.json configs on the same GPU -- C1, C3, C4, C5 with SURVEY 8(d)'s inputs: ms per
-            step, updates/s, roofline fraction, solver, a parity figure measured in the run, and for C3 an end-to-end
-            number (upload grid, iteration, download grid).
+`configs` : (N = 1) the other BASELINE.json configs on the same GPU -- C1, C3, C4, C5 with SURVEY 8(d)'s inputs, and C2T
+            (C2's shape with a temperature-dependent M1Hermite3 table instead of constant properties): ms per step,
+            updates/s, roofline fraction, solver, a parity figure measured in the run, and for C3 an end-to-end number
+            (upload grid, iteration, download grid).
 `c4_strong`, `c5_strong` : (N > 1, under torchrun) the sharded configs on all N GPUs -- C4 16384^2 row-sharded with the
             reduced-system exchange (NCCL all-gather inside the step), C5 with its lines split -- next to the same problem
             on one GPU measured in the same run.
