@@ -17,11 +17,14 @@
 //   * the hot loops hold the straight-line tiers only (fallbacks out of line, native-division walk rolled): with so few
 //     warps per SM an instruction-cache miss is not hidden -- the first build (20 k SASS instructions) spent 25 % of its
 //     stall samples on no_instructions; this one has 4.4 k.
-// MEASURED (B200, 1 M lines x 256 nodes, M1Hermite3 table), ms per step: K2 3.43; K2T without discards, CTAs per SM 3 / 4 /
-// 5 / 6 / 7 / 8: 4.19 / 3.31 / 3.42 / 3.13 / 3.16 / 3.12; with discards 4 / 6 / 7 / 8: 3.18 / 2.95 / 3.17 / 2.86 (eight: 128
-// registers, 44 bytes of spills; seven puts the warps unevenly on the four schedulers).  151 warp instructions per node-row
-// against K2's 308.  Forward walk alone 1.7 - 1.8 ms, backward walk 1.3 - 1.4 ms (before the discards); the two do not
-// overlap inside a CTA, so more CTAs per SM is what helps.
+// MEASURED (B200, 1 M lines x 256 nodes, M1Hermite3 table), ms per step: K2 3.43; K2T fully unrolled over the 16 nodes of a
+// chunk, without discards, CTAs per SM 3 / 4 / 5 / 6 / 7 / 8: 4.19 / 3.31 / 3.42 / 3.13 / 3.16 / 3.12; with discards 4 / 6 / 7 /
+// 8: 3.18 / 2.95 / 3.17 / 2.86 (seven puts the warps unevenly on the four schedulers); with the chain's loop unrolled by 4 and the
+// backward walk rolled over quarters of a chunk (3.8 k -> 3.0 k SASS instructions, 128 registers without spills, still 17 % of
+// the stall samples on no_instructions before): eight CTAs per SM **2.57** (six: 2.74; chain unrolled by 2: 2.60).  ~155 warp
+// instructions per node-row against K2's 308.  Forward walk alone 1.7 - 1.8 ms, backward walk 1.3 - 1.4 ms (first build);
+// the two do not overlap inside a CTA, so more CTAs per SM is what helps.  Small batches are latency-bound and gain most:
+// 4096 x 256 0.056 ms per step against K2's 0.217, 100 x 200 0.045 against 0.170 (profiles/r2_k2t_small_batches.txt).
 // Shared memory per CTA: barriers 512 B | NS stages x 12.5 KB (NS = 2 from six CTAs per SM, else 3) | the table (<= 4 KB; eight
 // CTAs per SM fit while it is below ~1.5 KB).
 // Applies to a SINGLE table of at most 4 KB on lines of at least 32 nodes; everything else stays on K2.
@@ -179,7 +182,7 @@ GS_DEV bool k2t_forward(const Line1d &L, const Step1dParams &p, K2TBars *bars, u
     const double2 *cf = reinterpret_cast<const double2 *>(st + K2T_OFF_CF);
     double2 *so = sc + (size_t)i0 * 32 + lane;
     if (FAST && c != 0 && i0 + K2T_CH < n) {
-#pragma unroll
+#pragma unroll 4
       for (int j = 0; j < K2T_CH; ++j) {
         const double F = cF[j * 32];
         const double a = fprev * cf[j].x;
@@ -337,26 +340,31 @@ __global__ void __launch_bounds__(64, CPS) k2t_step(Step1dParams p, int stage_le
         for (int l = lane; l < len * 4; l += 32) k2t_discard(dead + (size_t)l * 128);
       }
       double *G = Gblk + (size_t)i0 * 32 + lane, *P = Pblk + (size_t)i0 * 32 + lane;
-      double xs[K2T_CH];
       if (len == K2T_CH) {
+        // quarters of the chunk: the recurrence first (two dependent FP64 operations per node), then the quarter's
+        // predictor and stores as independent work; rolled over the quarters to keep the loop in the instruction cache
+#pragma unroll 1
+        for (int h = K2T_CH - 4; h >= 0; h -= 4) {
+          double xs[4];
 #pragma unroll
-        for (int j = K2T_CH - 1; j >= 0; --j) {
-          const double2 v = dl[j * 32];
-          u = v.x * u + v.y;
-          xs[j] = u;
-        }
+          for (int j = 3; j >= 0; --j) {
+            const double2 v = dl[(h + j) * 32];
+            u = v.x * u + v.y;
+            xs[j] = u;
+          }
 #pragma unroll
-        for (int j = 0; j < K2T_CH; ++j) {
-          const double d = xs[j] - gold[j * 32];
-          bool okd = true;
-          double q = gs_div<true>(d, r3, okd);
-          if (!(okd && fast_allowed)) q = k2t_div3(d);
-          if (hints & 8) {
-            k2t_st_first(P + j * 32, xs[j] + q, pol);    // arraygrid.aVal :85-87
-            k2t_st_first(G + j * 32, xs[j], pol);
-          } else {
-            P[j * 32] = xs[j] + q;
-            G[j * 32] = xs[j];
+          for (int j = 0; j < 4; ++j) {
+            const double d = xs[j] - gold[(h + j) * 32];
+            bool okd = true;
+            double q = gs_div<true>(d, r3, okd);
+            if (!(okd && fast_allowed)) q = k2t_div3(d);
+            if (hints & 8) {
+              k2t_st_first(P + (h + j) * 32, xs[j] + q, pol);    // arraygrid.aVal :85-87
+              k2t_st_first(G + (h + j) * 32, xs[j], pol);
+            } else {
+              P[(h + j) * 32] = xs[j] + q;
+              G[(h + j) * 32] = xs[j];
+            }
           }
         }
       } else {
