@@ -113,6 +113,7 @@ extern "C" int gs_ctx_set_option(gs_ctx *ctx, const char *name, int64_t value) {
   else if (!strcmp(name, "pipe_cfg")) ctx->opt_pipe_cfg = value;
   else if (!strcmp(name, "seg_len")) ctx->opt_seg_len = value;
   else if (!strcmp(name, "hoist_ck")) ctx->opt_hoist_ck = value;
+  else if (!strcmp(name, "k2r")) ctx->opt_k2r = value;
   else if (!strcmp(name, "k5")) ctx->opt_k5 = value;
   else if (!strcmp(name, "k5_xstrip")) ctx->opt_k5_xstrip = value;
   else if (!strcmp(name, "k5_cluster")) ctx->opt_k5_cluster = value != 0;

@@ -785,6 +785,106 @@ __global__ void __launch_bounds__(256) k_step1d_hoist(Step1dParams p, const doub
 }
 
 // ---------------------------------------------------------------------------------
+// K2r: K2h's recurrence for SMALL constant-property batches, resident in shared memory.
+//
+// A batch of a few line blocks (C1: one 200-node line) is latency-bound: K2c / K2h spend ~350 clk per node on the round
+// trips of one warp's bulk-copy ring (35.6 us per step for C1).  When the block's grid and lambda columns fit in shared
+// memory (n x 512 B + the hoisted table), one warp loads its block ONCE, runs all nsteps steps of the call on it with
+// K2h's very operations (hoist_fwd_node, the same backward recurrence and predictor: identical bits), and writes grid'
+// and the last step's predict' back at the end.  `predict` is not read on the constant-property path (as in K2c).
+// ---------------------------------------------------------------------------------
+template <bool FAST>
+GS_DEV bool resident_forward(const double *tab, const GsRcp &rt, int n, const double *sG, double *sL, double firstT,
+                             double lastT) {
+  bool ok = true;
+  double lambda = 0.0;
+  const double c_last = tab[4 * (size_t)n];
+  {
+    GsRcp rd;
+    rd.b = tab[1];
+    rd.y = tab[2];
+    double vect = gs_div<FAST, true>(-sG[0], rt, ok) - tab[0] * firstT;             // :65
+    lambda = gs_div<FAST>(vect, rd, ok);                                            // forwardFirst :245-248
+    sL[0] = lambda;
+  }
+  // unrolled: the loads and the lambda-independent -t / time of the next nodes run under the dependent chain
+#pragma unroll 8
+  for (int i = 1; i < n - 1; ++i) {
+    hoist_fwd_node<FAST>(sG[i * GS_LB], tab + 4 * (size_t)i, rt, lambda, ok);
+    sL[i * GS_LB] = lambda;
+  }
+  if (n > 1) {
+    const int i = n - 1;
+    const double *ti = tab + 4 * (size_t)i;
+    GsRcp rd;
+    rd.b = ti[1];
+    rd.y = ti[2];
+    double vect = gs_div<FAST, true>(-sG[i * GS_LB], rt, ok) - c_last * lastT;      // :89
+    lambda = gs_div<FAST>(vect - ti[0] * lambda, rd, ok);
+    sL[i * GS_LB] = lambda;
+  }
+  return ok;
+}
+
+__global__ void __launch_bounds__(32) k_step1d_hoist_resident(Step1dParams p, const double *table) {
+  extern __shared__ __align__(16) double rsm[];
+  const int n = p.n;
+  const int lane = threadIdx.x;
+  double *tab = rsm;                                   // [4n + 2]
+  double *sG = rsm + ((4 * n + 2 + 1) & ~1) + lane;    // [n][32]
+  double *sL = sG + (size_t)n * GS_LB;                 // [n][32]
+  for (int i = lane; i < 4 * n + 2; i += 32) tab[i] = table[i];
+  __syncwarp();
+  const long long blk = p.blk0 + blockIdx.x;
+  if (blk >= p.nblocks) return;
+  bool fast_allowed = p.allow_fast != 0 && tab[4 * (size_t)n + 1] != 0.0;
+  const GsRcp rt = gs_rcp_invariant(p.time, fast_allowed);
+  const GsRcp r3 = gs_rcp_invariant(3.0, fast_allowed);
+  const size_t block_elems = (size_t)n * GS_LB;
+  const long long line = blk * GS_LB + lane;
+  const bool valid = line < p.nlines;
+  const long long bcl = (valid ? line : p.nlines - 1) * p.bc_stride;
+  double *Gp = p.grid + (size_t)blk * block_elems + lane;
+  double *Pp = p.predict + (size_t)blk * block_elems + lane;
+  const double firstT = p.leftT[bcl], lastT = p.rightT[bcl];
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) sG[i * GS_LB] = Gp[i * GS_LB];
+  unsigned flags = 0;
+  bool try_fast = fast_allowed;
+  for (int step = 0; step < p.nsteps; ++step) {
+    bool ok = false;
+    if (try_fast) {
+      ok = resident_forward<true>(tab, rt, n, sG, sL, firstT, lastT);
+      ok = __all_sync(0xffffffffu, ok);
+    }
+    if (!ok) {
+      // operands outside the proven range of the shared-reciprocal division: redo with plain IEEE division
+      try_fast = false;
+      resident_forward<false>(tab, rt, n, sG, sL, firstT, lastT);
+    }
+    // backward (backwardPassion :345-365) + predictor (arraygrid.aVal :85-87) + grid <- result
+    const bool last_step = step == p.nsteps - 1;
+    double u = 0.0;
+#pragma unroll 8
+    for (int i = n - 1; i >= 0; --i) {
+      u = tab[4 * (size_t)i + 3] * u + sL[i * GS_LB];
+      if (last_step) {
+        const double d = u - sG[i * GS_LB];
+        bool okd = fast_allowed;
+        double q = gs_div<true>(d, r3, okd);
+        if (!okd) q = d / 3.0;
+        Pp[i * GS_LB] = u + q;
+      }
+      sG[i * GS_LB] = u;
+    }
+    if (valid && !(fabs(u) <= 1.7976931348623157e308)) flags |= GS_FLAG_NONFINITE;
+  }
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) Gp[i * GS_LB] = sG[i * GS_LB];
+  gs_raise(p.status, flags);
+}
+
+// ---------------------------------------------------------------------------------
 // K2c: hoisted coefficients + checkpoint/recompute -- no scratch traffic at all.
 //
 // K2h's remaining excess traffic is the lambda round trip (8 B written + 8 B read per node, all of it
@@ -1663,6 +1763,22 @@ static int step_blocks(gs_grid1d *g, double time, int nsteps, long long blk0, lo
     int blocks = (int)((nwarps + pblock / 32 - 1) / (pblock / 32));
     size_t tab_bytes = (4 * (size_t)g->n + 2) * sizeof(double);
     int smem_table = tab_bytes <= 24 * 1024 ? 1 : 0;
+    // K2r: a few blocks whose grid and lambda columns fit in shared memory stay resident for the whole call
+    {
+      const size_t rbytes = (((4 * (size_t)g->n + 2 + 1) & ~(size_t)1) + 2 * (size_t)g->n * GS_LB) * sizeof(double);
+      // (a single step does not amortise the block's load and store: measured 49 us against K2c's 42 on C1's line)
+      if (ctx->opt_k2r && nsteps >= 2 && nblocks <= 2LL * ctx->sm_count && rbytes <= 200 * 1024) {
+        const void *key = reinterpret_cast<const void *>(k_step1d_hoist_resident);
+        if (std::find(ctx->configured.begin(), ctx->configured.end(), key) == ctx->configured.end()) {
+          GS_CUDA(cudaFuncSetAttribute(k_step1d_hoist_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          ctx->configured.push_back(key);
+        }
+        k_step1d_hoist_resident<<<(unsigned)nblocks, 32, rbytes, ctx->stream>>>(p, g->hoist_table);
+        ctx->launches++;
+        GS_CUDA(cudaGetLastError());
+        return GS_OK;
+      }
+    }
     // K2c (checkpoint + recompute) when the per-block checkpoints fit in shared memory
     {
       const int K = ctx->opt_ck_block == 32 ? 32 : 16;

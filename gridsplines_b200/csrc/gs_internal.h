@@ -62,6 +62,7 @@ struct gs_ctx {
   int64_t opt_pipe_cfg = 0;
   int64_t opt_seg_len = 32;
   int64_t opt_hoist_ck = 1;
+  int64_t opt_k2r = 1;          // K2r: small constant-property batches (<= 2 blocks per SM, block fits shared memory) stay resident for the call
   int64_t opt_k5 = 1;
   int64_t opt_k5_xstrip = 0;   // 0 = automatic
   int opt_k5_nb = 2;           // K5: tile buffers per warp (3: triple buffer where it fits; measured slower)

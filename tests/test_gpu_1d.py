@@ -49,7 +49,7 @@ def test_batch_vs_golden(gs, name, args):
 def options(ctx):
     """Sets tuning / path-selection options on the shared context and restores the defaults afterwards."""
     defaults = {"const_hoist": 1, "pipeline": 1, "native_div": 0, "pipe_cfg": 0, "threads_per_sm_1d": 0,
-                "hoist_ck": 1, "ck_block": 16, "faces1d": 0, "k2t": 1, "k2t_cps": 8, "k2t_hints": 31, "k2t_ctas": 0}
+                "hoist_ck": 1, "ck_block": 16, "faces1d": 0, "k2t": 1, "k2t_cps": 8, "k2t_hints": 31, "k2t_ctas": 0, "k2r": 1}
 
     def set_(**kw):
         for k, v in kw.items():
@@ -63,10 +63,12 @@ def options(ctx):
 # every code path of K2: hoisted coefficients (K2h), the general TMA pipeline, the direct-load kernel,
 # plain IEEE division instead of the shared-reciprocal one, other ring shapes
 PATHS = {
-    "default": {},
-    "hoist_scratch": {"hoist_ck": 0},
-    "hoist_ck32": {"ck_block": 32},
-    "hoist_ck_native": {"native_div": 1},
+    "default": {},                                          # constants: K2r for these small batches (K2c beyond 2 blocks per SM)
+    "k2r_native_div": {"native_div": 1},
+    "k2c": {"k2r": 0},                                      # K2c: hoisted coefficients, checkpoint / recompute
+    "hoist_scratch": {"hoist_ck": 0, "k2r": 0},
+    "hoist_ck32": {"ck_block": 32, "k2r": 0},
+    "hoist_ck_native": {"native_div": 1, "k2r": 0},
     "general": {"const_hoist": 0, "k2t": 0},                # K2: TMA ring + (delta, lambda) scratch
     "k2t": {"const_hoist": 0, "k2t": 2},                            # K2T: faces warp + chain warp, L2-resident scratch (2: any table; cubic tables on equal knots take it by default)
     "k2t_native_div": {"const_hoist": 0, "native_div": 1, "k2t": 2},
@@ -75,11 +77,11 @@ PATHS = {
     "k2f": {"const_hoist": 0, "faces1d": 1, "k2t": 0},      # K2f: faces kernel + elimination with checkpoint/recompute
     "k2f_native_div": {"const_hoist": 0, "faces1d": 1, "native_div": 1, "k2t": 0},
     "direct": {"const_hoist": 0, "pipeline": 0},
-    "native_div": {"native_div": 1, "hoist_ck": 0},
+    "native_div": {"native_div": 1, "hoist_ck": 0, "k2r": 0},
     "general_native_div": {"const_hoist": 0, "native_div": 1, "k2t": 0},
-    "ring1": {"pipe_cfg": 1, "hoist_ck": 0},
+    "ring1": {"pipe_cfg": 1, "hoist_ck": 0, "k2r": 0},
     "general_ring2": {"const_hoist": 0, "pipe_cfg": 2, "k2t": 0},
-    "few_warps": {"threads_per_sm_1d": 32, "k2t": 0},
+    "few_warps": {"threads_per_sm_1d": 32, "k2t": 0, "k2r": 0},
 }
 
 
