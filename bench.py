@@ -277,7 +277,7 @@ def bench_c1(gs, ctx, torch, stream):
     g = mk()
     ms = _time_steps(torch, stream, lambda: g.step(900.0, 20.0, 4.0, nsteps=1000), 3, 1)
     return {"workload": "C1: 1-D radial, 200 nodes, 1000 implicit steps, constant properties (one line: replicas only)",
-            "ms_per_step": ms / 1000.0, "updates_per_s": 200 * 1000 / (ms * 1e-3), "solver": "K2c (per-thread Thomas, exact)",
+            "ms_per_step": ms / 1000.0, "updates_per_s": 200 * 1000 / (ms * 1e-3), "solver": "K2r (per-thread Thomas, exact; the block stays in shared memory for the 1000 steps of the call)",
             "parity": {"bit_identical_to_fixture": exact, "fixture": "tests/golden/c1_radial_200x1000.npz (oracle)"},
             "note": "a single 200-node line is launch-latency bound by construction"}
 
